@@ -1,0 +1,146 @@
+/* libmae_b200.so -- C ABI of the B200-native MAE pre-training hot path (sm_100a only).
+ *
+ * The reference (giolucasd/ssrl-vit-mae-jepa) has no FFI layer: its hot path is Python
+ * (src/models/mae.py, src/training/mae.py) calling lightly 1.5.22 / timm 1.0.21 / ATen.  This header
+ * is the boundary a maintainer would bind underneath those Python classes (see INTEGRATION.md for
+ * the ctypes stub).  Each entry point names the reference call it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are DEVICE pointers owned by the caller
+ *  - no allocation, no synchronisation: every call only enqueues work on `stream` (re-entrant,
+ *    stream-ordered, CUDA-graph capturable)
+ *  - returns MAE_OK (0) or a negative MAE_ERR_* code; never throws; there is NO CPU fallback
+ *  - bf16 tensors are passed as `void*` (raw __nv_bfloat16 storage); indices are int64 as in torch
+ *  - all matrices are dense row-major
+ */
+#ifndef MAE_B200_H_
+#define MAE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* mae_stream_t; /* == cudaStream_t */
+
+enum {
+  MAE_OK = 0,
+  MAE_ERR_SHAPE = -1,  /* unsupported / inconsistent dimension */
+  MAE_ERR_NULL = -2,   /* required pointer is null */
+  MAE_ERR_ALIGN = -3,  /* pointer or leading dimension not 16-byte aligned */
+  MAE_ERR_DRIVER = -4, /* driver entry point / tensor-map encode failed */
+  MAE_ERR_LAUNCH = -5  /* cudaGetLastError() after launch */
+};
+
+/* epilogues of mae_gemm_tn */
+enum {
+  MAE_EPI_BF16 = 0,       /* out(bf16) = acc + bias                                  (qkv, embed, pred, dgrads) */
+  MAE_EPI_GELU_BF16 = 1,  /* pre_out(bf16) = acc + bias; out(bf16) = gelu_erf(pre)   (mlp.fc1)                  */
+  MAE_EPI_RESID_F32 = 2,  /* out(f32) = aux(f32) + acc + bias                        (attn.proj, mlp.fc2)       */
+  MAE_EPI_DGELU_BF16 = 4  /* out(bf16) = acc * gelu_erf'(aux(bf16 pre-activation))   (fc2 dgrad)                */
+};
+
+int mae_version(void);
+const char* mae_error_string(int code);
+
+/* lightly.models.utils.random_token_mask (called at reference src/models/mae.py:79-83), with the
+ * torch.rand draw hoisted to the caller: noise (B,L) f32.  Column 0 (class token) is treated as -1.
+ * Stable ascending sort per row (ties -> lower index); idx_keep (B,num_keep), idx_mask (B,L-num_keep)
+ * int64.  L <= 256.  Integer path: bit-exact. */
+int mae_random_token_mask(const float* noise, int B, int L, int num_keep, int64_t* idx_keep, int64_t* idx_mask,
+                          mae_stream_t stream);
+
+/* The im2col half of timm PatchEmbed (Conv2d k=s=patch; reference src/models/mae.py:28-36,55) fused with
+ * get_at_index(idx_keep): for kept tokens j=1..num_keep-1 writes patch idx_keep[b,j]-1 of image b in conv
+ * weight order (c,py,px) as bf16 row b*(num_keep-1)+j-1 of patches (B*(num_keep-1), C*patch*patch). */
+int mae_gather_patches(const float* images, const int64_t* idx_keep, int B, int C, int img, int patch, int num_keep,
+                       void* patches_bf16, mae_stream_t stream);
+
+/* cat(cls_token, tokens) + pos_embed restricted to kept tokens (lightly MaskedVisionTransformerTIMM.
+ * preprocess + get_at_index; reference src/models/mae.py:55): x (B,num_keep,D) f32. */
+int mae_assemble_tokens(const void* tok_bf16, const float* cls, const float* pos, const int64_t* idx_keep, int B,
+                        int num_keep, int D, float* x, mae_stream_t stream);
+
+/* nn.LayerNorm(D, eps) forward over `rows` rows (timm Block.norm1/norm2, vit.norm, decoder_norm).  If
+ * gather_idx != NULL, output row r=(b,j) reads source row b*L_src + gather_idx[b*n_sel+j] (get_at_index at
+ * reference src/models/mae.py:72 commuted with the row-wise norm).  Writes xn bf16 (rows,D) and fp32
+ * mean/rstd (rows). */
+int mae_layernorm_fwd(const float* x, const float* gamma, const float* beta, const int64_t* gather_idx, int n_sel,
+                      int L_src, int rows, int D, float eps, void* xn_bf16, float* mean, float* rstd,
+                      mae_stream_t stream);
+
+/* LayerNorm backward.  g bf16 (rows,D) is the gradient w.r.t. the normalised output; x/mean/rstd as in the
+ * forward (same gather mapping; dx_out rows are written at the mapped row).  dx_out = (dx_in ? dx_in : 0) +
+ * LN'(g); optional bf16 copy of dx_out; dgamma/dbeta (D) are ACCUMULATED with fp32 atomics. */
+int mae_layernorm_bwd(const void* g_bf16, const float* x, const float* mean, const float* rstd, const float* gamma,
+                      const float* dx_in, const int64_t* gather_idx, int n_sel, int L_src, int rows, int D,
+                      float* dx_out, void* dx_out_bf16, float* dgamma, float* dbeta, mae_stream_t stream);
+
+/* out = epi(A[M,K] * B[N,K]^T): every nn.Linear forward (B = weight (out,in)) and every dgrad (B = weight^T)
+ * of timm Block / MAEDecoderTIMM (reference src/models/mae.py:55,59,71,73).  A, B bf16; fp32 accumulation in
+ * TMEM via tcgen05.mma; K % 16 == 0, N % 16 == 0. */
+int mae_gemm_tn(const void* A_bf16, const void* B_bf16, int M, int N, int K, int epi, const float* bias, void* out,
+                void* pre_out_bf16, const void* aux, mae_stream_t stream);
+
+/* out[p*so_p + q*so_q] += sum_m P[m,p] * Q[m,q]: weight gradients (autograd of the Linears above).
+ * P bf16 (M,Pc), Q bf16 (M,Qc), Qc <= 256, Qc % 16 == 0, Pc % 8 == 0.  fp32 atomics: zero `out` first. */
+int mae_gemm_wgrad(const void* P_bf16, int Pc, const void* Q_bf16, int Qc, int M, float* out, long long so_p,
+                   long long so_q, mae_stream_t stream);
+
+/* timm Attention core: F.scaled_dot_product_attention on qkv (B,L,3,H,hd) bf16 -> out (B,L,H*hd) bf16,
+ * scale hd^-0.5, plus lse (B,H,L) f32 for the backward.  hd in {24,32}; L <= 160. */
+int mae_attention_fwd(const void* qkv_bf16, int B, int L, int H, int hd, void* out_bf16, float* lse,
+                      mae_stream_t stream);
+int mae_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse, int B,
+                      int L, int H, int hd, void* dqkv_bf16, mae_stream_t stream);
+
+/* repeat_token(mask_token) + set_at_index(idx_keep, embed) + decoder_pos_embed add (reference
+ * src/models/mae.py:61-69 and MAEDecoderTIMM.decode's pos add): x_dec (B,L,D) f32. */
+int mae_scatter_decoder_tokens(const void* emb_bf16, const float* mask_token, const float* dec_pos,
+                               const int64_t* idx_keep, const int64_t* idx_mask, int B, int L, int num_keep, int D,
+                               float* x_dec, mae_stream_t stream);
+
+/* patchify + get_at_index(idx_mask-1) + MSELoss (reference src/models/mae.py:90-92, src/training/mae.py:40,48):
+ * pred bf16 (B,n_mask,C*patch*patch); target read straight from the images in (py,px,c) order.
+ * loss (1) f32 = mean((pred-target)^2) (deterministic two-stage reduction through `partials`, >= 4096 floats);
+ * optional dpred bf16 = 2*(pred-target)/numel; optional target f32 (B,n_mask,C*p*p).
+ * norm_pix != 0 normalises each target patch by its own mean/var (opt-in; the reference does not). */
+int mae_masked_mse(const void* pred_bf16, const float* images, const int64_t* idx_mask, int B, int C, int img,
+                   int patch, int n_mask, int norm_pix, float* loss, float* partials, void* dpred_bf16,
+                   float* target, mae_stream_t stream);
+
+/* out[n] += sum_m x[m,n] (bias gradients). x bf16 (M,N). */
+int mae_colsum_bf16(const void* x_bf16, int M, int N, float* out, mae_stream_t stream);
+
+/* Row gather + cast: out bf16 (B*n_sel, D) <- src f32 row b*L_src + (idx ? idx[b*n_sel+j] : row_offset+j).
+ * (autograd of set_at_index / cat at reference src/models/mae.py:64-69). */
+int mae_gather_rows_bf16(const float* src, const int64_t* idx, int B, int n_sel, int L_src, int row_offset, int D,
+                         void* out_bf16, mae_stream_t stream);
+
+/* out[d] += sum over the same row selection of src[.,d]  (mask_token / cls_token gradients). */
+int mae_colsum_rows_f32(const float* src, const int64_t* idx, int B, int n_sel, int L_src, int row_offset, int D,
+                        float* out, mae_stream_t stream);
+
+/* dst(bf16)[i] = src(f32)[i] */
+int mae_cast_bf16(const float* src, void* dst_bf16, long long n, mae_stream_t stream);
+
+/* Multi-tensor transposing cast: for each entry t of table (n_entries x 4 int64: src_off, rows, cols, dst_off;
+ * device memory) writes dst[dst_off + c*rows + r] = bf16(src[src_off + r*cols + c]). */
+int mae_transpose_cast_bf16(const float* src, void* dst_bf16, const long long* table, int n_entries,
+                            mae_stream_t stream);
+
+/* Lightning gradient_clip_val=1.0 ("norm") + torch.optim.AdamW step (reference
+ * scripts/training/pretrain_mae.py:124-125, src/training/mae.py:59-65) over one flat fp32 buffer of n
+ * elements.  Two launches: mae_grad_sumsq writes per-block partial sums; mae_clip_adamw reduces them in a
+ * fixed order, computes coef = min(1, max_norm/(norm+1e-6)), applies decoupled weight decay + Adam and
+ * refreshes the bf16 shadow copy of the parameters.  grad_norm_out (1) f32 receives the pre-clip norm. */
+int mae_grad_sumsq(const float* g, long long n, float* partials, int max_partials, mae_stream_t stream);
+int mae_clip_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, float max_norm, int step, const float* partials,
+                   int n_partials, float* grad_norm_out, mae_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAE_B200_H_ */

@@ -1,0 +1,6 @@
+"""B200-native MAE pre-training hot path (drop-in for giolucasd/ssrl-vit-mae-jepa's ``src/models/mae.py`` +
+``src/training/mae.py``).  Import as ``ssrl_vit_mae_jepa_b200`` (alias package; the directory name carries the
+reference's hyphens)."""
+from .build import build  # noqa: F401
+from .mae import MAEEngine, MaskedAutoencoder, num_keep_tokens, sincos_2d  # noqa: F401
+from .training import MAEPretrainModule, FusedTrainer  # noqa: F401

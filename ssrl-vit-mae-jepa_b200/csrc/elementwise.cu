@@ -1,0 +1,668 @@
+// HBM-bound kernels of the MAE step: token masking (warp bitonic sort), patch gather, token assembly,
+// LayerNorm fwd/bwd, decoder scatter, masked MSE, column sums, casts, clip+AdamW.
+#include "mae_internal.h"
+#include "ptx.cuh"
+
+namespace mae {
+
+// ---------------------------------------------------------------------------------------------
+// random_token_mask: one warp sorts one row of <= 256 (key,index) pairs with a register/shuffle
+// bitonic network.  Composite 64-bit keys (monotone float bits << 32 | index) make the order total,
+// which is exactly a stable ascending sort.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_to_ordered(float x) {
+  x = x + 0.0f;  // -0.0 -> +0.0 so that they compare equal like torch
+  uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(128) token_mask_kernel(const float* __restrict__ noise, int B, int L, int num_keep,
+                                                        int64_t* __restrict__ idx_keep,
+                                                        int64_t* __restrict__ idx_mask) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const int lane = threadIdx.x & 31;
+  unsigned long long v[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int i = lane * 8 + r;
+    if (i < L) {
+      const float x = (i == 0) ? -1.0f : noise[size_t(row) * L + i];
+      v[r] = (static_cast<unsigned long long>(float_to_ordered(x)) << 32) | static_cast<unsigned>(i);
+    } else {
+      v[r] = ~0ull;
+    }
+  }
+#pragma unroll
+  for (int k = 2; k <= 256; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 8) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, v[r], j >> 3);
+          const int i = lane * 8 + r;
+          const bool up = (i & k) == 0;
+          const bool lower = (i & j) == 0;
+          const unsigned long long mn = v[r] < other ? v[r] : other;
+          const unsigned long long mx = v[r] < other ? other : v[r];
+          v[r] = (up == lower) ? mn : mx;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          if ((r & j) == 0) {
+            const int i = lane * 8 + r;
+            const bool up = (i & k) == 0;
+            const unsigned long long a = v[r], b = v[r | j];
+            const bool sw = (a > b) == up;
+            v[r] = sw ? b : a;
+            v[r | j] = sw ? a : b;
+          }
+        }
+      }
+    }
+  }
+  const int n_mask = L - num_keep;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int i = lane * 8 + r;
+    const int64_t idx = static_cast<int64_t>(v[r] & 0xffffffffull);
+    if (i < num_keep) idx_keep[size_t(row) * num_keep + i] = idx;
+    else if (i < L) idx_mask[size_t(row) * n_mask + (i - num_keep)] = idx;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// patch gather (im2col of the kept patches only), one warp per kept patch
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_patches_kernel(const float* __restrict__ images,
+                                                            const int64_t* __restrict__ idx_keep, int B, int C,
+                                                            int img, int patch, int num_keep,
+                                                            __nv_bfloat16* __restrict__ out) {
+  const int nk = num_keep - 1;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (long long)B * nk) return;
+  const int lane = threadIdx.x & 31;
+  const int b = int(w / nk), j = int(w % nk) + 1;
+  const int pidx = int(idx_keep[size_t(b) * num_keep + j]) - 1;
+  const int grid = img / patch;
+  const int pr = pidx / grid, pcn = pidx % grid;
+  const int pp = patch * patch, pd = C * pp;
+  const float* src = images + size_t(b) * C * img * img;
+  __nv_bfloat16* dst = out + size_t(w) * pd;
+  for (int q = lane; q < pd; q += 32) {
+    const int c = q / pp, py = (q % pp) / patch, px = q % patch;
+    dst[q] = __float2bfloat16_rn(src[(size_t(c) * img + pr * patch + py) * img + pcn * patch + px]);
+  }
+}
+
+__global__ void __launch_bounds__(256) assemble_tokens_kernel(const __nv_bfloat16* __restrict__ tok,
+                                                             const float* __restrict__ cls,
+                                                             const float* __restrict__ pos,
+                                                             const int64_t* __restrict__ idx_keep, int B,
+                                                             int num_keep, int D, float* __restrict__ x) {
+  const long long n = (long long)B * num_keep * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int d = int(i % D);
+    const long long r = i / D;
+    const int j = int(r % num_keep), b = int(r / num_keep);
+    const int tokidx = int(idx_keep[size_t(b) * num_keep + j]);
+    float v = (j == 0) ? cls[d] : __bfloat162float(tok[(size_t(b) * (num_keep - 1) + (j - 1)) * D + d]);
+    x[i] = v + pos[size_t(tokidx) * D + d];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm forward / backward: one warp per row, D <= 256, D % 4 == 0; lane owns columns
+// {4*lane .. 4*lane+3} and {128 + 4*lane ..}.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long map_row(long long r, const int64_t* gather_idx, int n_sel, int L_src) {
+  if (gather_idx == nullptr) return r;
+  const long long b = r / n_sel;
+  return b * L_src + gather_idx[r];
+}
+
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta,
+                                                           const int64_t* __restrict__ gather_idx, int n_sel,
+                                                           int L_src, int rows, int D, float eps,
+                                                           __nv_bfloat16* __restrict__ xn, float* __restrict__ mean,
+                                                           float* __restrict__ rstd) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int c0 = lane * 4, c1 = 128 + lane * 4;
+  const bool h0 = c0 < D, h1 = c1 < D;
+  float4 g0 = make_float4(0, 0, 0, 0), g1 = g0, b0 = g0, b1 = g0;
+  if (h0) { g0 = *reinterpret_cast<const float4*>(gamma + c0); b0 = *reinterpret_cast<const float4*>(beta + c0); }
+  if (h1) { g1 = *reinterpret_cast<const float4*>(gamma + c1); b1 = *reinterpret_cast<const float4*>(beta + c1); }
+  const float invD = 1.0f / D;
+  for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * wpb) {
+    const float* src = x + map_row(r, gather_idx, n_sel, L_src) * D;
+    float4 v0 = make_float4(0, 0, 0, 0), v1 = v0;
+    if (h0) v0 = *reinterpret_cast<const float4*>(src + c0);
+    if (h1) v1 = *reinterpret_cast<const float4*>(src + c1);
+    const float mu = warp_sum(v0.x + v0.y + v0.z + v0.w + v1.x + v1.y + v1.z + v1.w) * invD;
+    float sq = 0.f;
+    if (h0) { float a = v0.x - mu, b = v0.y - mu, c = v0.z - mu, d = v0.w - mu; sq += a * a + b * b + c * c + d * d; }
+    if (h1) { float a = v1.x - mu, b = v1.y - mu, c = v1.z - mu, d = v1.w - mu; sq += a * a + b * b + c * c + d * d; }
+    const float rs = rsqrtf(warp_sum(sq) * invD + eps);
+    __nv_bfloat16* dst = xn + r * D;
+    if (h0) {
+      uint2 o;
+      o.x = pack_bf16x2((v0.x - mu) * rs * g0.x + b0.x, (v0.y - mu) * rs * g0.y + b0.y);
+      o.y = pack_bf16x2((v0.z - mu) * rs * g0.z + b0.z, (v0.w - mu) * rs * g0.w + b0.w);
+      *reinterpret_cast<uint2*>(dst + c0) = o;
+    }
+    if (h1) {
+      uint2 o;
+      o.x = pack_bf16x2((v1.x - mu) * rs * g1.x + b1.x, (v1.y - mu) * rs * g1.y + b1.y);
+      o.y = pack_bf16x2((v1.z - mu) * rs * g1.z + b1.z, (v1.w - mu) * rs * g1.w + b1.w);
+      *reinterpret_cast<uint2*>(dst + c1) = o;
+    }
+    if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
+  }
+}
+
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(
+    const __nv_bfloat16* __restrict__ g, const float* __restrict__ x, const float* __restrict__ mean,
+    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dx_in,
+    const int64_t* __restrict__ gather_idx, int n_sel, int L_src, int rows, int D, float* __restrict__ dx_out,
+    __nv_bfloat16* __restrict__ dx_out_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float s_dg[256], s_db[256];
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+  __syncthreads();
+  const int c0 = lane * 4, c1 = 128 + lane * 4;
+  const bool h0 = c0 < D, h1 = c1 < D;
+  float4 w0 = make_float4(0, 0, 0, 0), w1 = w0;
+  if (h0) w0 = *reinterpret_cast<const float4*>(gamma + c0);
+  if (h1) w1 = *reinterpret_cast<const float4*>(gamma + c1);
+  float dg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, db[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const float invD = 1.0f / D;
+  for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * wpb) {
+    const long long xr = map_row(r, gather_idx, n_sel, L_src);
+    const float mu = mean[r], rs = rstd[r];
+    float gv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, xh[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (h0) {
+      const uint2 gg = *reinterpret_cast<const uint2*>(g + r * D + c0);
+      const float4 xv = *reinterpret_cast<const float4*>(x + xr * D + c0);
+      gv[0] = bf16_lo(gg.x); gv[1] = bf16_hi(gg.x); gv[2] = bf16_lo(gg.y); gv[3] = bf16_hi(gg.y);
+      xh[0] = (xv.x - mu) * rs; xh[1] = (xv.y - mu) * rs; xh[2] = (xv.z - mu) * rs; xh[3] = (xv.w - mu) * rs;
+    }
+    if (h1) {
+      const uint2 gg = *reinterpret_cast<const uint2*>(g + r * D + c1);
+      const float4 xv = *reinterpret_cast<const float4*>(x + xr * D + c1);
+      gv[4] = bf16_lo(gg.x); gv[5] = bf16_hi(gg.x); gv[6] = bf16_lo(gg.y); gv[7] = bf16_hi(gg.y);
+      xh[4] = (xv.x - mu) * rs; xh[5] = (xv.y - mu) * rs; xh[6] = (xv.z - mu) * rs; xh[7] = (xv.w - mu) * rs;
+    }
+    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    float s1 = 0.f, s2 = 0.f, dxh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      dg[i] += gv[i] * xh[i];
+      db[i] += gv[i];
+      dxh[i] = gv[i] * wv[i];
+      s1 += dxh[i];
+      s2 += dxh[i] * xh[i];
+    }
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = rs * (dxh[i] - s1 - xh[i] * s2);
+    if (h0) {
+      if (dx_in) {
+        const float4 a = *reinterpret_cast<const float4*>(dx_in + xr * D + c0);
+        o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
+      }
+      *reinterpret_cast<float4*>(dx_out + xr * D + c0) = make_float4(o[0], o[1], o[2], o[3]);
+      if (dx_out_bf16)
+        *reinterpret_cast<uint2*>(dx_out_bf16 + xr * D + c0) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+    }
+    if (h1) {
+      if (dx_in) {
+        const float4 a = *reinterpret_cast<const float4*>(dx_in + xr * D + c1);
+        o[4] += a.x; o[5] += a.y; o[6] += a.z; o[7] += a.w;
+      }
+      *reinterpret_cast<float4*>(dx_out + xr * D + c1) = make_float4(o[4], o[5], o[6], o[7]);
+      if (dx_out_bf16)
+        *reinterpret_cast<uint2*>(dx_out_bf16 + xr * D + c1) = make_uint2(pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (h0) { atomicAdd(&s_dg[c0 + i], dg[i]); atomicAdd(&s_db[c0 + i], db[i]); }
+    if (h1) { atomicAdd(&s_dg[c1 + i], dg[4 + i]); atomicAdd(&s_db[c1 + i], db[4 + i]); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    atomicAdd(dgamma + i, s_dg[i]);
+    atomicAdd(dbeta + i, s_db[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// decoder input: mask tokens everywhere, embedded kept tokens at idx_keep, + decoder pos embed
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) scatter_decoder_kernel(const __nv_bfloat16* __restrict__ emb,
+                                                             const float* __restrict__ mask_token,
+                                                             const float* __restrict__ dec_pos,
+                                                             const int64_t* __restrict__ idx_keep,
+                                                             const int64_t* __restrict__ idx_mask, int B, int L,
+                                                             int num_keep, int D, float* __restrict__ x_dec) {
+  const int D4 = D >> 2;
+  const long long n = (long long)B * L * D4;
+  const int n_mask = L - num_keep;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int d = int(i % D4) * 4;
+    const long long r = i / D4;
+    const int jj = int(r % L), b = int(r / L);
+    int l;
+    float4 v;
+    if (jj < num_keep) {
+      l = int(idx_keep[size_t(b) * num_keep + jj]);
+      const uint2 e = *reinterpret_cast<const uint2*>(emb + (size_t(b) * num_keep + jj) * D + d);
+      v = make_float4(bf16_lo(e.x), bf16_hi(e.x), bf16_lo(e.y), bf16_hi(e.y));
+    } else {
+      l = int(idx_mask[size_t(b) * n_mask + (jj - num_keep)]);
+      v = *reinterpret_cast<const float4*>(mask_token + d);
+    }
+    const float4 p = *reinterpret_cast<const float4*>(dec_pos + size_t(l) * D + d);
+    v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    *reinterpret_cast<float4*>(x_dec + (size_t(b) * L + l) * D + d) = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// masked MSE: one warp per masked patch; the target is read straight from the image
+// ---------------------------------------------------------------------------------------------
+static constexpr int kMsePartials = 4096;
+static constexpr int kMaxPatchDim = 768;  // 16*16*3
+
+__global__ void __launch_bounds__(256) masked_mse_kernel(const __nv_bfloat16* __restrict__ pred,
+                                                        const float* __restrict__ images,
+                                                        const int64_t* __restrict__ idx_mask, int B, int C, int img,
+                                                        int patch, int n_mask, int norm_pix, float inv_numel,
+                                                        float* __restrict__ partials,
+                                                        __nv_bfloat16* __restrict__ dpred,
+                                                        float* __restrict__ target) {
+  extern __shared__ float s_t[];  // per warp: patch_dim floats (target in (py,px,c) order)
+  __shared__ float s_red[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int pp = patch * patch, pd = C * pp, grid = img / patch;
+  float* st = s_t + wid * pd;
+  float acc = 0.f;
+  const long long nrows = (long long)B * n_mask;
+  for (long long r = (long long)blockIdx.x * wpb + wid; r < nrows; r += (long long)gridDim.x * wpb) {
+    const int b = int(r / n_mask);
+    int pidx = int(idx_mask[r]) - 1;
+    if (pidx < 0) pidx = 0;  // torch.clamp(idx_mask - 1, min=0)
+    const int pr = pidx / grid, pcn = pidx % grid;
+    const float* src = images + size_t(b) * C * img * img;
+    float s = 0.f, ss = 0.f;
+    for (int q = lane; q < pd; q += 32) {  // q in image order (c,py,px): 32-byte runs
+      const int c = q / pp, py = (q % pp) / patch, px = q % patch;
+      const float v = src[(size_t(c) * img + pr * patch + py) * img + pcn * patch + px];
+      st[(py * patch + px) * C + c] = v;
+      s += v; ss += v * v;
+    }
+    __syncwarp();
+    float mu = 0.f, rsd = 1.f;
+    if (norm_pix) {  // opt-in MAE-paper variant: (t - mean) / sqrt(var_unbiased + 1e-6)
+      s = warp_sum(s); ss = warp_sum(ss);
+      mu = s / pd;
+      const float var = (ss - pd * mu * mu) / (pd - 1);
+      rsd = rsqrtf(var + 1e-6f);
+    }
+    const __nv_bfloat16* pr_row = pred + r * pd;
+    for (int e = lane; e < pd; e += 32) {
+      const float t = (st[e] - mu) * rsd;
+      const float d = __bfloat162float(pr_row[e]) - t;
+      acc += d * d;
+      if (dpred) dpred[r * pd + e] = __float2bfloat16_rn(2.0f * d * inv_numel);
+      if (target) target[r * pd + e] = t;
+    }
+    __syncwarp();
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) s_red[wid] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < wpb; ++i) t += s_red[i];
+    partials[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) finalize_loss_kernel(const float* __restrict__ partials, int n, float scale,
+                                                           float* __restrict__ loss) {
+  __shared__ float s[256];
+  float t = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) t += partials[i];
+  s[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss[0] = s[0] * scale;
+}
+
+// ---------------------------------------------------------------------------------------------
+// column sums and row gathers
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int M, int N,
+                                                         int rows_per_block, float* __restrict__ out) {
+  const int col = (blockIdx.y * 128 + threadIdx.x) * 2;
+  if (col >= N) return;
+  const int m0 = blockIdx.x * rows_per_block;
+  int m1 = m0 + rows_per_block;
+  if (m1 > M) m1 = M;
+  float a = 0.f, b = 0.f;
+  for (int m = m0; m < m1; ++m) {
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(x + size_t(m) * N + col);
+    a += bf16_lo(v); b += bf16_hi(v);
+  }
+  atomicAdd(out + col, a);
+  atomicAdd(out + col + 1, b);
+}
+
+__device__ __forceinline__ long long sel_row(long long r, const int64_t* idx, int n_sel, int L_src, int row_offset) {
+  const long long b = r / n_sel, j = r % n_sel;
+  return b * L_src + (idx ? idx[r] : (row_offset + j));
+}
+
+__global__ void __launch_bounds__(256) gather_rows_bf16_kernel(const float* __restrict__ src,
+                                                              const int64_t* __restrict__ idx, int B, int n_sel,
+                                                              int L_src, int row_offset, int D,
+                                                              __nv_bfloat16* __restrict__ out) {
+  const int D4 = D >> 2;
+  const long long n = (long long)B * n_sel * D4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int d = int(i % D4) * 4;
+    const long long r = i / D4;
+    const float4 v = *reinterpret_cast<const float4*>(src + sel_row(r, idx, n_sel, L_src, row_offset) * D + d);
+    *reinterpret_cast<uint2*>(out + r * D + d) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+__global__ void __launch_bounds__(256) colsum_rows_f32_kernel(const float* __restrict__ src,
+                                                             const int64_t* __restrict__ idx, int B, int n_sel,
+                                                             int L_src, int row_offset, int D, int rows_per_block,
+                                                             float* __restrict__ out) {
+  const int d = threadIdx.x;
+  if (d >= D) return;
+  const long long nrows = (long long)B * n_sel;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > nrows) r1 = nrows;
+  float a = 0.f;
+  for (long long r = r0; r < r1; ++r) a += src[sel_row(r, idx, n_sel, L_src, row_offset) * D + d];
+  atomicAdd(out + d, a);
+}
+
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                       long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+__global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __restrict__ src,
+                                                            __nv_bfloat16* __restrict__ dst,
+                                                            const long long* __restrict__ table) {
+  __shared__ float tile[32][33];
+  const long long* t = table + size_t(blockIdx.z) * 4;
+  const long long src_off = t[0], dst_off = t[2 + 1];
+  const int rows = int(t[1]), cols = int(t[2]);
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  if (r0 >= rows || c0 >= cols) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? src[src_off + (long long)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (r < rows && c < cols) dst[dst_off + (long long)c * rows + r] = __float2bfloat16_rn(tile[tx][i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// clip-by-global-norm + AdamW over one flat buffer
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) grad_sumsq_kernel(const float* __restrict__ g, long long n,
+                                                        float* __restrict__ partials) {
+  __shared__ float s[8];
+  float t = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = g[i];
+    t += v * v;
+  }
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int i = 0; i < 8; ++i) a += s[i];
+    partials[blockIdx.x] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256) clip_adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v,
+                                                        __nv_bfloat16* __restrict__ p_bf16, long long n, float lr,
+                                                        float beta1, float beta2, float eps, float wd, float max_norm,
+                                                        float inv_bc1, float inv_sqrt_bc2,
+                                                        const float* __restrict__ partials, int n_partials,
+                                                        float* __restrict__ grad_norm_out) {
+  __shared__ float s[256];
+  // every block reduces the same partials in the same order -> identical, deterministic norm
+  float t = 0.f;
+  for (int i = threadIdx.x; i < n_partials; i += 256) t += partials[i];
+  s[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  const float norm = sqrtf(s[0]);
+  const float coef = fminf(1.0f, max_norm / (norm + 1e-6f));
+  if (blockIdx.x == 0 && threadIdx.x == 0 && grad_norm_out) grad_norm_out[0] = norm;
+  const float decay = 1.0f - lr * wd;
+  const float step_size = lr * inv_bc1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * coef;
+    float pi = p[i] * decay;
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    pi -= step_size * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+    if (p_bf16) p_bf16[i] = __float2bfloat16_rn(pi);
+  }
+}
+
+static int grid_for(long long n, int threads, int cap = 148 * 16) {
+  long long g = (n + threads - 1) / threads;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return int(g);
+}
+
+}  // namespace mae
+
+using namespace mae;
+
+extern "C" int mae_version(void) { return 100; }
+
+extern "C" const char* mae_error_string(int code) {
+  switch (code) {
+    case MAE_OK: return "ok";
+    case MAE_ERR_SHAPE: return "unsupported or inconsistent shape";
+    case MAE_ERR_NULL: return "required pointer is null";
+    case MAE_ERR_ALIGN: return "pointer or leading dimension not 16-byte aligned";
+    case MAE_ERR_DRIVER: return "CUDA driver entry point / tensor map encode failed";
+    case MAE_ERR_LAUNCH: return "kernel launch failed";
+    default: return "unknown error";
+  }
+}
+
+extern "C" int mae_random_token_mask(const float* noise, int B, int L, int num_keep, int64_t* idx_keep,
+                                     int64_t* idx_mask, cudaStream_t stream) {
+  if (B <= 0) return MAE_OK;
+  if (!noise || !idx_keep || (!idx_mask && num_keep < L)) return MAE_ERR_NULL;
+  if (L < 1 || L > 256 || num_keep < 1 || num_keep > L) return MAE_ERR_SHAPE;
+  token_mask_kernel<<<(B + 3) / 4, 128, 0, stream>>>(noise, B, L, num_keep, idx_keep, idx_mask);
+  return MAE_CHECK_LAUNCH();
+}
+
+extern "C" int mae_gather_patches(const float* images, const int64_t* idx_keep, int B, int C, int img, int patch,
+                                  int num_keep, void* patches, cudaStream_t stream) {
+  if (B <= 0 || num_keep <= 1) return MAE_OK;
+  if (!images || !idx_keep || !patches) return MAE_ERR_NULL;
+  if (patch <= 0 || img % patch) return MAE_ERR_SHAPE;
+  const long long warps = (long long)B * (num_keep - 1);
+  gather_patches_kernel<<<unsigned((warps + 7) / 8), 256, 0, stream>>>(images, idx_keep, B, C, img, patch, num_keep,
+                                                                       reinterpret_cast<__nv_bfloat16*>(patches));
+  return MAE_CHECK_LAUNCH();
+}
+
+extern "C" int mae_assemble_tokens(const void* tok, const float* cls, const float* pos, const int64_t* idx_keep, int B,
+                                   int num_keep, int D, float* x, cudaStream_t stream) {
+  if (B <= 0) return MAE_OK;
+  if (!tok || !cls || !pos || !idx_keep || !x) return MAE_ERR_NULL;
+  assemble_tokens_kernel<<<grid_for((long long)B * num_keep * D, 256), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(tok), cls, pos, idx_keep, B, num_keep, D, x);
+  return MAE_CHECK_LAUNCH();
+}
+
+extern "C" int mae_layernorm_fwd(const float* x, const float* gamma, const float* beta, const int64_t* gather_idx,
+                                 int n_sel, int L_src, int rows, int D, float eps, void* xn, float* mean, float* rstd,
+                                 cudaStream_t stream) {
+  if (rows <= 0) return MAE_OK;
+  if (!x || !gamma || !beta || !xn || !mean || !rstd) return MAE_ERR_NULL;
+  if (D > 256 || (D % 4) || (gather_idx && (n_sel <= 0 || L_src <= 0))) return MAE_ERR_SHAPE;
+  layernorm_fwd_kernel<<<grid_for(rows, 8), 256, 0, stream>>>(x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps,
+                                                             reinterpret_cast<__nv_bfloat16*>(xn), mean, rstd);
+  return MAE_CHECK_LAUNCH();
+}
+
+extern "C" int mae_layernorm_bwd(const void* g, const float* x, const float* mean, const float* rstd,
+                                 const float* gamma, const float* dx_in, const int64_t* gather_idx, int n_sel,
+                                 int L_src, int rows, int D, float* dx_out, void* dx_out_bf16, float* dgamma,
+                                 float* dbeta, cudaStream_t stream) {
+  if (rows <= 0) return MAE_OK;
+  if (!g || !x || !mean || !rstd || !gamma || !dx_out || !dgamma || !dbeta) return MAE_ERR_NULL;
+  if (D > 256 || (D % 4) || (gather_idx && (n_sel <= 0 || L_src <= 0))) return MAE_ERR_SHAPE;
+  layernorm_bwd_kernel<<<grid_for(rows, 8, 148 * 4), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(g), x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out,
+      reinterpret_cast<__nv_bfloat16*>(dx_out_bf16), dgamma, dbeta);
+  return MAE_CHECK_LAUNCH();
+}
+
+extern "C" int mae_scatter_decoder_tokens(const void* emb, const float* mask_token, const float* dec_pos,
+                                          const int64_t* idx_keep, const int64_t* idx_mask, int B, int L, int num_keep,
+                                          int D, float* x_dec, cudaStream_t stream) {
+  if (B <= 0) return MAE_OK;
+  if (!emb || !mask_token || !dec_pos || !idx_keep || !idx_mask || !x_dec) return MAE_ERR_NULL;
+  if (D % 4 || num_keep < 1 || num_keep > L) return MAE_ERR_SHAPE;
+  scatter_decoder_kernel<<<grid_for((long long)B * L * (D / 4), 256), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(emb), mask_token, dec_pos, idx_keep, idx_mask, B, L, num_keep, D, x_dec);
+  return MAE_CHECK_LAUNCH();
+}
+
+extern "C" int mae_masked_mse(const void* pred, const float* images, const int64_t* idx_mask, int B, int C, int img,
+                              int patch, int n_mask, int norm_pix, float* loss, float* partials, void* dpred,
+                              float* target, cudaStream_t stream) {
+  if (!pred || !images || !idx_mask || !loss || !partials) return MAE_ERR_NULL;
+  if (B <= 0 || n_mask <= 0) return MAE_ERR_SHAPE;
+  const int pd = C * patch * patch;
+  if (patch <= 0 || img % patch || pd > kMaxPatchDim) return MAE_ERR_SHAPE;
+  const long long nrows = (long long)B * n_mask;
+  int grid = int((nrows + 7) / 8);
+  if (grid > kMsePartials) grid = kMsePartials;
+  const float inv_numel = 1.0f / (float(nrows) * float(pd));
+  masked_mse_kernel<<<grid, 256, 8 * pd * sizeof(float), stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(pred), images, idx_mask, B, C, img, patch, n_mask, norm_pix, inv_numel,
+      partials, reinterpret_cast<__nv_bfloat16*>(dpred), target);
+  if (cudaGetLastError() != cudaSuccess) return MAE_ERR_LAUNCH;
+  finalize_loss_kernel<<<1, 256, 0, stream>>>(partials, grid, inv_numel, loss);
+  return MAE_CHECK_LAUNCH();
+}
+
+extern "C" int mae_colsum_bf16(const void* x, int M, int N, float* out, cudaStream_t stream) {
+  if (M <= 0) return MAE_OK;
+  if (!x || !out) return MAE_ERR_NULL;
+  if (N % 2) return MAE_ERR_SHAPE;
+  const int ny = (N + 255) / 256;
+  int nx = (148 * 8) / ny;
+  int rpb = (M + nx - 1) / nx;
+  if (rpb < 16) rpb = 16;
+  nx = (M + rpb - 1) / rpb;
+  colsum_bf16_kernel<<<dim3(nx, ny), 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), M, N, rpb, out);
+  return MAE_CHECK_LAUNCH();
+}
+
+extern "C" int mae_gather_rows_bf16(const float* src, const int64_t* idx, int B, int n_sel, int L_src, int row_offset,
+                                    int D, void* out, cudaStream_t stream) {
+  if (B <= 0 || n_sel <= 0) return MAE_OK;
+  if (!src || !out) return MAE_ERR_NULL;
+  if (D % 4) return MAE_ERR_SHAPE;
+  gather_rows_bf16_kernel<<<grid_for((long long)B * n_sel * (D / 4), 256), 256, 0, stream>>>(
+      src, idx, B, n_sel, L_src, row_offset, D, reinterpret_cast<__nv_bfloat16*>(out));
+  return MAE_CHECK_LAUNCH();
+}
+
+extern "C" int mae_colsum_rows_f32(const float* src, const int64_t* idx, int B, int n_sel, int L_src, int row_offset,
+                                   int D, float* out, cudaStream_t stream) {
+  if (B <= 0 || n_sel <= 0) return MAE_OK;
+  if (!src || !out) return MAE_ERR_NULL;
+  if (D > 256) return MAE_ERR_SHAPE;
+  const long long nrows = (long long)B * n_sel;
+  int nb = 148 * 4;
+  long long rpb = (nrows + nb - 1) / nb;
+  if (rpb < 8) rpb = 8;
+  nb = int((nrows + rpb - 1) / rpb);
+  colsum_rows_f32_kernel<<<nb, 256, 0, stream>>>(src, idx, B, n_sel, L_src, row_offset, D, int(rpb), out);
+  return MAE_CHECK_LAUNCH();
+}
+
+extern "C" int mae_cast_bf16(const float* src, void* dst, long long n, cudaStream_t stream) {
+  if (n <= 0) return MAE_OK;
+  if (!src || !dst) return MAE_ERR_NULL;
+  cast_bf16_kernel<<<grid_for(n, 256), 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  return MAE_CHECK_LAUNCH();
+}
+
+extern "C" int mae_transpose_cast_bf16(const float* src, void* dst, const long long* table, int n_entries,
+                                       cudaStream_t stream) {
+  if (n_entries <= 0) return MAE_OK;
+  if (!src || !dst || !table) return MAE_ERR_NULL;
+  // grid covers the largest weight (<= 1024 x 1024); smaller entries exit early
+  transpose_cast_kernel<<<dim3(32, 32, n_entries), 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), table);
+  return MAE_CHECK_LAUNCH();
+}
+
+extern "C" int mae_grad_sumsq(const float* g, long long n, float* partials, int max_partials, cudaStream_t stream) {
+  if (!g || !partials) return MAE_ERR_NULL;
+  if (n <= 0 || max_partials <= 0) return MAE_ERR_SHAPE;
+  grad_sumsq_kernel<<<max_partials, 256, 0, stream>>>(g, n, partials);
+  return MAE_CHECK_LAUNCH();
+}
+
+extern "C" int mae_clip_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr,
+                              float beta1, float beta2, float eps, float weight_decay, float max_norm, int step,
+                              const float* partials, int n_partials, float* grad_norm_out, cudaStream_t stream) {
+  if (!p || !g || !m || !v || !partials) return MAE_ERR_NULL;
+  if (n <= 0 || step < 1 || n_partials < 1) return MAE_ERR_SHAPE;
+  const double bc1 = 1.0 - pow(double(beta1), double(step));
+  const double bc2 = 1.0 - pow(double(beta2), double(step));
+  clip_adamw_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, stream>>>(
+      p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n, lr, beta1, beta2, eps, weight_decay, max_norm,
+      float(1.0 / bc1), float(1.0 / sqrt(bc2)), partials, n_partials, grad_norm_out);
+  return MAE_CHECK_LAUNCH();
+}

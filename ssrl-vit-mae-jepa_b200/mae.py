@@ -1,0 +1,641 @@
+"""Host-side mirror of the reference's ``src/models/mae.py`` on top of ``libmae_b200.so``.
+
+``MaskedAutoencoder`` keeps the reference's constructor (three config dicts with the same ``.get``
+defaults, ``src/models/mae.py:15-52``), attributes, ``forward(images) -> (x_pred, target)`` contract
+(``:77-94``), ``forward_encoder`` / ``forward_decoder`` (``:54-75``) and -- parameter for parameter --
+the 87-tensor ``state_dict`` layout of the lightly/timm module tree it replaces, so ``vit-mae.pt``
+checkpoints load either way.  The sub-modules are parameter holders only: every FLOP runs in the
+hand-written sm_100a kernels through :class:`MAEEngine`.  CPU tensors raise; there is no fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import EPI_BF16, EPI_DGELU_BF16, EPI_GELU_BF16, EPI_RESID_F32, calls
+
+LN_EPS = 1e-6  # timm VisionTransformer / lightly MAEDecoderTIMM use LayerNorm(eps=1e-6)
+
+
+# --------------------------------------------------------------------------------------
+# parameter-holder module tree (names == timm 1.0.21 / lightly 1.5.22 state_dict keys)
+# --------------------------------------------------------------------------------------
+class _HolderMixin:
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("this sub-module only holds parameters; run it through MaskedAutoencoder / MAEEngine")
+
+
+class _Attention(_HolderMixin, nn.Module):
+    def __init__(self, dim: int, num_heads: int):
+        super().__init__()
+        assert dim % num_heads == 0
+        self.num_heads, self.head_dim = num_heads, dim // num_heads
+        self.qkv = nn.Linear(dim, dim * 3, bias=True)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _Mlp(_HolderMixin, nn.Module):
+    def __init__(self, dim: int, hidden: int):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class _Block(_HolderMixin, nn.Module):
+    def __init__(self, dim: int, num_heads: int, mlp_ratio: float = 4.0):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=LN_EPS)
+        self.attn = _Attention(dim, num_heads)
+        self.norm2 = nn.LayerNorm(dim, eps=LN_EPS)
+        self.mlp = _Mlp(dim, int(dim * mlp_ratio))
+
+
+class _PatchEmbed(_HolderMixin, nn.Module):
+    def __init__(self, img_size: int, patch_size: int, in_chans: int, embed_dim: int):
+        super().__init__()
+        self.img_size, self.patch_size = img_size, patch_size
+        self.grid_size = img_size // patch_size
+        self.num_patches = self.grid_size**2
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size, bias=True)
+
+
+def sincos_2d(embed_dim: int, grid_size: int) -> torch.Tensor:
+    """Frozen 2-D sin-cos position table with a zero class-token row: the first half of the
+    channels encodes the column, the second half the row."""
+    assert embed_dim % 4 == 0
+    q = embed_dim // 4
+    omega = 1.0 / (10000.0 ** (torch.arange(q, dtype=torch.float64) / q))
+    pos = torch.arange(grid_size, dtype=torch.float64)
+    ang = pos[:, None] * omega[None, :]                      # (grid, q)
+    one = torch.cat([ang.sin(), ang.cos()], dim=1)           # (grid, D/2)
+    col = one[None, :, :].expand(grid_size, grid_size, -1)   # varies with the column index
+    row = one[:, None, :].expand(grid_size, grid_size, -1)   # varies with the row index
+    table = torch.cat([col, row], dim=2).reshape(grid_size * grid_size, embed_dim)
+    return torch.cat([torch.zeros(1, embed_dim, dtype=torch.float64), table], dim=0).float().unsqueeze(0)
+
+
+def _init_linear_ln(root: nn.Module) -> None:
+    for m in root.modules():
+        if isinstance(m, nn.Linear):
+            nn.init.xavier_uniform_(m.weight)
+            nn.init.zeros_(m.bias)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.ones_(m.weight)
+            nn.init.zeros_(m.bias)
+
+
+class _VisionTransformer(_HolderMixin, nn.Module):
+    """Holder with timm ``VisionTransformer`` parameter names (``src/models/mae.py:28-36``)."""
+
+    def __init__(self, img_size, patch_size, in_chans, embed_dim, depth, num_heads):
+        super().__init__()
+        self.embed_dim, self.num_heads, self.num_prefix_tokens = embed_dim, num_heads, 1
+        self.patch_embed = _PatchEmbed(img_size, patch_size, in_chans, embed_dim)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.pos_embed = nn.Parameter(torch.randn(1, self.patch_embed.num_patches + 1, embed_dim) * 0.02)
+        self.blocks = nn.Sequential(*[_Block(embed_dim, num_heads) for _ in range(depth)])
+        self.norm = nn.LayerNorm(embed_dim, eps=LN_EPS)
+
+
+class _MaskedViT(_HolderMixin, nn.Module):
+    """Holder with lightly ``MaskedVisionTransformerTIMM`` names: ``mask_token`` + ``vit.*``."""
+
+    def __init__(self, vit: _VisionTransformer):
+        super().__init__()
+        self.vit = vit
+        self.mask_token = nn.Parameter(torch.zeros(1, 1, vit.embed_dim))  # never used by the MAE path
+        w = vit.patch_embed.proj.weight.data
+        nn.init.xavier_uniform_(w.view(w.shape[0], -1))
+        nn.init.normal_(vit.cls_token, std=0.02)
+        _init_linear_ln(vit)
+        vit.pos_embed.data.copy_(sincos_2d(vit.embed_dim, vit.patch_embed.grid_size))
+        vit.pos_embed.requires_grad = False
+
+    @property
+    def sequence_length(self) -> int:
+        return self.vit.patch_embed.num_patches + self.vit.num_prefix_tokens
+
+
+class _MAEDecoder(_HolderMixin, nn.Module):
+    """Holder with lightly ``MAEDecoderTIMM`` names (``src/models/mae.py:45-52``)."""
+
+    def __init__(self, num_patches, patch_size, in_chans, embed_dim, decoder_embed_dim, decoder_depth, decoder_num_heads):
+        super().__init__()
+        self.decoder_embed = nn.Linear(embed_dim, decoder_embed_dim, bias=True)
+        self.mask_token = nn.Parameter(torch.zeros(1, 1, decoder_embed_dim))
+        self.decoder_pos_embed = nn.Parameter(torch.zeros(1, num_patches + 1, decoder_embed_dim), requires_grad=False)
+        self.decoder_blocks = nn.Sequential(*[_Block(decoder_embed_dim, decoder_num_heads) for _ in range(decoder_depth)])
+        self.decoder_norm = nn.LayerNorm(decoder_embed_dim, eps=LN_EPS)
+        self.decoder_pred = nn.Linear(decoder_embed_dim, patch_size**2 * in_chans, bias=True)
+        nn.init.normal_(self.mask_token, std=0.02)
+        self.decoder_pos_embed.data.copy_(sincos_2d(decoder_embed_dim, int(round(math.sqrt(num_patches)))))
+        _init_linear_ln(self)
+
+
+def num_keep_tokens(seq_len: int, mask_ratio: float) -> int:
+    """lightly ``random_token_mask``: ``max(1, int(L * (1 - mask_ratio)))`` (class token included)."""
+    return max(1, int(seq_len * (1 - mask_ratio)))
+
+
+# --------------------------------------------------------------------------------------
+# engine: flat parameter storage + kernel sequencing
+# --------------------------------------------------------------------------------------
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class _BlockW:
+    """Byte-offset bookkeeping of one transformer block inside the flat buffers."""
+    __slots__ = ("dim", "heads", "hd", "hidden", "n1w", "n1b", "qkvw", "qkvb", "projw", "projb", "n2w", "n2b",
+                 "fc1w", "fc1b", "fc2w", "fc2b")
+
+
+class MAEEngine:
+    """Owns the flat fp32 parameter / gradient / AdamW-state buffers (every ``nn.Parameter`` of the model
+    is a view into them), their bf16 shadows (W and W^T) and the activation workspace, and sequences the
+    C-ABI kernels for forward, backward and the fused clip+AdamW step."""
+
+    ALIGN = 64  # elements; keeps every tensor 128-byte aligned in the bf16 shadow (TMA needs 16)
+
+    def __init__(self, model: "MaskedAutoencoder"):
+        self.model = model
+        self.flat: Optional[torch.Tensor] = None
+        self._ws_key = None
+        self._shadow_version = -1
+        self.step_count = 0
+        self.norm_pix_loss = False
+
+    # ---------------- flat storage ----------------
+    def _ordered_params(self) -> List[Tuple[str, nn.Parameter]]:
+        named = list(self.model.named_parameters())
+        nograd = {"encoder.mask_token", "encoder.vit.pos_embed", "decoder.decoder_pos_embed"}
+        return [(n, p) for n, p in named if n not in nograd] + [(n, p) for n, p in named if n in nograd]
+
+    def _ensure_flat(self, device: torch.device) -> None:
+        first = next(self.model.parameters())
+        if self.flat is not None and self.flat.device == device and first.data_ptr() == self._first_ptr and \
+                first.device == device:
+            return
+        if device.type != "cuda":
+            raise RuntimeError("MaskedAutoencoder runs only on CUDA (sm_100a); there is no CPU fallback")
+        _lib.load()
+        params = self._ordered_params()
+        off, self.offsets, self.n_opt = 0, {}, None
+        for n, p in params:
+            if n == "encoder.mask_token":
+                self.n_opt = off
+            self.offsets[n] = off
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.n_total = off
+        flat = torch.zeros(off, dtype=torch.float32, device=device)
+        old_m = getattr(self, "exp_avg", None)
+        for n, p in params:
+            o = self.offsets[n]
+            flat[o:o + p.numel()].copy_(p.data.reshape(-1).to(device=device, dtype=torch.float32))
+            p.data = flat[o:o + p.numel()].view(p.shape)
+        self.flat = flat
+        self._first_ptr = first.data_ptr()
+        self.grads = torch.zeros(self.n_opt, dtype=torch.float32, device=device)
+        if old_m is None or old_m.numel() != self.n_opt:
+            self.exp_avg = torch.zeros(self.n_opt, dtype=torch.float32, device=device)
+            self.exp_avg_sq = torch.zeros(self.n_opt, dtype=torch.float32, device=device)
+        else:
+            self.exp_avg, self.exp_avg_sq = self.exp_avg.to(device), self.exp_avg_sq.to(device)
+        self.flat_bf16 = torch.empty(off, dtype=torch.bfloat16, device=device)
+        self.flat_bf16_t = torch.zeros(off, dtype=torch.bfloat16, device=device)
+        self.partials = torch.zeros(8192, dtype=torch.float32, device=device)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=device)
+        # transposed shadow table: every Linear weight that needs a dgrad
+        rows = []
+        for n, p in params:
+            if n.endswith(".weight") and p.dim() == 2:
+                rows.append([self.offsets[n], p.shape[0], p.shape[1], self.offsets[n]])
+        self.t_table = torch.tensor(rows, dtype=torch.int64, device=device)
+        self._shadow_version = -1
+        self._index_blocks()
+
+    def _o(self, name: str) -> int:
+        return self.offsets[name]
+
+    def _index_blocks(self) -> None:
+        def blk(prefix: str, dim: int, heads: int) -> _BlockW:
+            b = _BlockW()
+            b.dim, b.heads, b.hd, b.hidden = dim, heads, dim // heads, dim * 4
+            for a, k in [("n1w", "norm1.weight"), ("n1b", "norm1.bias"), ("qkvw", "attn.qkv.weight"),
+                         ("qkvb", "attn.qkv.bias"), ("projw", "attn.proj.weight"), ("projb", "attn.proj.bias"),
+                         ("n2w", "norm2.weight"), ("n2b", "norm2.bias"), ("fc1w", "mlp.fc1.weight"),
+                         ("fc1b", "mlp.fc1.bias"), ("fc2w", "mlp.fc2.weight"), ("fc2b", "mlp.fc2.bias")]:
+                setattr(b, a, self._o(prefix + k))
+            return b
+
+        m = self.model
+        vit = m.encoder.vit
+        self.enc_blocks = [blk(f"encoder.vit.blocks.{i}.", vit.embed_dim, vit.num_heads) for i in range(len(vit.blocks))]
+        dd = m.decoder.decoder_embed.out_features
+        dh = m.decoder.decoder_blocks[0].attn.num_heads if len(m.decoder.decoder_blocks) else 1
+        self.dec_blocks = [blk(f"decoder.decoder_blocks.{i}.", dd, dh) for i in range(len(m.decoder.decoder_blocks))]
+
+    def _refresh_shadow(self, stream: int) -> None:
+        """bf16 copies of W (same layout) and W^T; skipped when the fused optimizer already refreshed them."""
+        if self._shadow_version == self.flat._version:
+            return
+        calls.mae_cast_bf16(self.flat.data_ptr(), self.flat_bf16.data_ptr(), self.n_total, stream)
+        calls.mae_transpose_cast_bf16(self.flat.data_ptr(), self.flat_bf16_t.data_ptr(), self.t_table.data_ptr(),
+                                      self.t_table.shape[0], stream)
+        self._shadow_version = self.flat._version
+
+    # pointers into the flat buffers (element offsets -> byte addresses)
+    def pf(self, off: int) -> int:
+        return self.flat.data_ptr() + 4 * off
+
+    def pg(self, off: int) -> int:
+        return self.grads.data_ptr() + 4 * off
+
+    def pw(self, off: int) -> int:
+        return self.flat_bf16.data_ptr() + 2 * off
+
+    def pwt(self, off: int) -> int:
+        return self.flat_bf16_t.data_ptr() + 2 * off
+
+    # ---------------- workspace ----------------
+    def _ensure_ws(self, B: int, Lk: int, device: torch.device) -> None:
+        key = (B, Lk, device)
+        if self._ws_key == key:
+            return
+        m = self.model
+        L, Lm = m.sequence_length, m.sequence_length - Lk
+        De, Dd = m.encoder.vit.embed_dim, m.decoder.decoder_embed.out_features
+        pd = m.in_chans * m.patch_size**2
+        Me, Md, Mm = B * Lk, B * L, B * Lm
+        bf, f32 = torch.bfloat16, torch.float32
+
+        def e(shape, dt):
+            return torch.empty(shape, dtype=dt, device=device)
+
+        ws: Dict[str, Any] = {}
+        ws["idx_keep"] = e((B, Lk), torch.int64)
+        ws["idx_mask"] = e((B, Lm), torch.int64)
+        ws["patches"] = e((B * (Lk - 1), pd), bf)
+        ws["tok"] = e((B * (Lk - 1), De), bf)
+
+        def block_ws(M, D, H):
+            return {"x_in": e((M, D), f32), "xn1": e((M, D), bf), "mean1": e((M,), f32), "rstd1": e((M,), f32),
+                    "qkv": e((M, 3 * D), bf), "att": e((M, D), bf), "lse": e((M * H,), f32),
+                    "x_mid": e((M, D), f32), "xn2": e((M, D), bf), "mean2": e((M,), f32), "rstd2": e((M,), f32),
+                    "pre": e((M, 4 * D), bf), "h": e((M, 4 * D), bf)}
+
+        ws["enc"] = [block_ws(Me, De, b.heads) for b in self.enc_blocks]
+        ws["x_enc"] = e((Me, De), f32)
+        ws["xnf"], ws["meanf"], ws["rstdf"] = e((Me, De), bf), e((Me,), f32), e((Me,), f32)
+        ws["emb"] = e((Me, Dd), bf)
+        ws["dec"] = [block_ws(Md, Dd, b.heads) for b in self.dec_blocks]
+        ws["x_dec"] = e((Md, Dd), f32)
+        ws["xnd"], ws["meand"], ws["rstdd"] = e((Mm, Dd), bf), e((Mm,), f32), e((Mm,), f32)
+        ws["pred"] = e((B, Lm, pd), bf)
+        ws["dpred"] = e((B, Lm, pd), bf)
+        ws["loss"] = torch.zeros(1, dtype=f32, device=device)
+        ws["loss_partials"] = e((4096,), f32)
+        # backward scratch, shared by all blocks (sized for the decoder, the larger of the two)
+        Mx, Dx = max(Me, Md), max(De, Dd)
+        ws["dx_a"], ws["dx_b"] = e((Mx * Dx,), f32), e((Mx * Dx,), f32)
+        ws["dxb_a"], ws["dxb_b"] = e((Mx * Dx,), bf), e((Mx * Dx,), bf)
+        ws["dh"] = e((Mx * Dx * 4,), bf)
+        ws["g"] = e((Mx * Dx,), bf)
+        ws["datt"] = e((Mx * Dx,), bf)
+        ws["dqkv"] = e((Mx * Dx * 3,), bf)
+        ws["demb"] = e((Me, Dd), bf)
+        ws["dtok"] = e((B * (Lk - 1), De), bf)
+        self.ws, self._ws_key = ws, key
+        self.dims = dict(B=B, L=L, Lk=Lk, Lm=Lm, De=De, Dd=Dd, pd=pd, Me=Me, Md=Md, Mm=Mm)
+
+    # ---------------- forward pieces ----------------
+    def _block_fwd(self, w: _BlockW, s: Dict[str, torch.Tensor], x_out: torch.Tensor, M: int, B: int, L: int, st: int):
+        D, H, hd = w.dim, w.heads, w.hd
+        calls.mae_layernorm_fwd(_ptr(s["x_in"]), self.pf(w.n1w), self.pf(w.n1b), None, 0, 0, M, D, LN_EPS,
+                                _ptr(s["xn1"]), _ptr(s["mean1"]), _ptr(s["rstd1"]), st)
+        calls.mae_gemm_tn(_ptr(s["xn1"]), self.pw(w.qkvw), M, 3 * D, D, EPI_BF16, self.pf(w.qkvb), _ptr(s["qkv"]),
+                          None, None, st)
+        calls.mae_attention_fwd(_ptr(s["qkv"]), B, L, H, hd, _ptr(s["att"]), _ptr(s["lse"]), st)
+        calls.mae_gemm_tn(_ptr(s["att"]), self.pw(w.projw), M, D, D, EPI_RESID_F32, self.pf(w.projb),
+                          _ptr(s["x_mid"]), None, _ptr(s["x_in"]), st)
+        calls.mae_layernorm_fwd(_ptr(s["x_mid"]), self.pf(w.n2w), self.pf(w.n2b), None, 0, 0, M, D, LN_EPS,
+                                _ptr(s["xn2"]), _ptr(s["mean2"]), _ptr(s["rstd2"]), st)
+        calls.mae_gemm_tn(_ptr(s["xn2"]), self.pw(w.fc1w), M, 4 * D, D, EPI_GELU_BF16, self.pf(w.fc1b), _ptr(s["h"]),
+                          _ptr(s["pre"]), None, st)
+        calls.mae_gemm_tn(_ptr(s["h"]), self.pw(w.fc2w), M, D, 4 * D, EPI_RESID_F32, self.pf(w.fc2b), _ptr(x_out),
+                          None, _ptr(s["x_mid"]), st)
+
+    def forward(self, images: torch.Tensor, noise: Optional[torch.Tensor], mask_ratio: float,
+                want_target: bool = False, compute_loss: bool = True):
+        """mask -> encode kept tokens -> decode -> predict masked patches (-> fused MSE + dpred)."""
+        m = self.model
+        if not images.is_cuda:
+            raise RuntimeError("MaskedAutoencoder runs only on CUDA tensors (sm_100a kernels; no CPU fallback)")
+        if images.dtype != torch.float32 or images.dim() != 4 or images.shape[1] != m.in_chans or \
+                images.shape[2] != m.image_size or images.shape[3] != m.image_size:
+            raise ValueError(f"expected float32 images (B,{m.in_chans},{m.image_size},{m.image_size}), got "
+                             f"{tuple(images.shape)} {images.dtype}")
+        images = images.contiguous()
+        dev = images.device
+        B, L = images.shape[0], m.sequence_length
+        Lk = num_keep_tokens(L, mask_ratio)
+        if Lk < 2 or Lk >= L:
+            raise ValueError(f"mask_ratio {mask_ratio} keeps {Lk} of {L} tokens; need 2 <= keep < L")
+        self._ensure_flat(dev)
+        self._ensure_ws(B, Lk, dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        self._refresh_shadow(st)
+        ws, d = self.ws, self.dims
+        if noise is None:
+            noise = torch.rand(B, L, device=dev)  # same RNG call as lightly.random_token_mask
+        noise = noise.to(device=dev, dtype=torch.float32).contiguous()
+        if noise.shape != (B, L):
+            raise ValueError(f"noise must be ({B},{L})")
+        calls.mae_random_token_mask(noise.data_ptr(), B, L, Lk, _ptr(ws["idx_keep"]), _ptr(ws["idx_mask"]), st)
+        self._encode(images, ws["idx_keep"], st)
+        self._decode(st)
+        target = None
+        if compute_loss or want_target:
+            if want_target:
+                target = torch.empty((B, d["Lm"], d["pd"]), dtype=torch.float32, device=dev)
+            calls.mae_masked_mse(_ptr(ws["pred"]), images.data_ptr(), _ptr(ws["idx_mask"]), B, m.in_chans, m.image_size,
+                                 m.patch_size, d["Lm"], int(self.norm_pix_loss), _ptr(ws["loss"]),
+                                 _ptr(ws["loss_partials"]), _ptr(ws["dpred"]), _ptr(target), st)
+            calls.launches += 1
+        self._images = images
+        return ws["pred"], target, ws["loss"]
+
+    def _encode(self, images: torch.Tensor, idx_keep: torch.Tensor, st: int) -> None:
+        m, ws, d = self.model, self.ws, self.dims
+        B, Lk, De = d["B"], d["Lk"], d["De"]
+        o = self._o
+        calls.mae_gather_patches(images.data_ptr(), idx_keep.data_ptr(), B, m.in_chans, m.image_size, m.patch_size, Lk,
+                                 _ptr(ws["patches"]), st)
+        calls.mae_gemm_tn(_ptr(ws["patches"]), self.pw(o("encoder.vit.patch_embed.proj.weight")), B * (Lk - 1), De,
+                          d["pd"], EPI_BF16, self.pf(o("encoder.vit.patch_embed.proj.bias")), _ptr(ws["tok"]), None,
+                          None, st)
+        x0 = ws["enc"][0]["x_in"] if self.enc_blocks else ws["x_enc"]
+        calls.mae_assemble_tokens(_ptr(ws["tok"]), self.pf(o("encoder.vit.cls_token")), self.pf(o("encoder.vit.pos_embed")),
+                                  idx_keep.data_ptr(), B, Lk, De, _ptr(x0), st)
+        for i, w in enumerate(self.enc_blocks):
+            x_out = ws["enc"][i + 1]["x_in"] if i + 1 < len(self.enc_blocks) else ws["x_enc"]
+            self._block_fwd(w, ws["enc"][i], x_out, d["Me"], B, Lk, st)
+        calls.mae_layernorm_fwd(_ptr(ws["x_enc"]), self.pf(o("encoder.vit.norm.weight")), self.pf(o("encoder.vit.norm.bias")),
+                                None, 0, 0, d["Me"], De, LN_EPS, _ptr(ws["xnf"]), _ptr(ws["meanf"]), _ptr(ws["rstdf"]), st)
+
+    def _decode(self, st: int) -> None:
+        ws, d = self.ws, self.dims
+        B, L, Lk, Lm, De, Dd = d["B"], d["L"], d["Lk"], d["Lm"], d["De"], d["Dd"]
+        o = self._o
+        calls.mae_gemm_tn(_ptr(ws["xnf"]), self.pw(o("decoder.decoder_embed.weight")), d["Me"], Dd, De, EPI_BF16,
+                          self.pf(o("decoder.decoder_embed.bias")), _ptr(ws["emb"]), None, None, st)
+        x0 = ws["dec"][0]["x_in"] if self.dec_blocks else ws["x_dec"]
+        calls.mae_scatter_decoder_tokens(_ptr(ws["emb"]), self.pf(o("decoder.mask_token")),
+                                         self.pf(o("decoder.decoder_pos_embed")), _ptr(ws["idx_keep"]),
+                                         _ptr(ws["idx_mask"]), B, L, Lk, Dd, _ptr(x0), st)
+        for i, w in enumerate(self.dec_blocks):
+            x_out = ws["dec"][i + 1]["x_in"] if i + 1 < len(self.dec_blocks) else ws["x_dec"]
+            self._block_fwd(w, ws["dec"][i], x_out, d["Md"], B, L, st)
+        calls.mae_layernorm_fwd(_ptr(ws["x_dec"]), self.pf(o("decoder.decoder_norm.weight")),
+                                self.pf(o("decoder.decoder_norm.bias")), _ptr(ws["idx_mask"]), Lm, L, d["Mm"], Dd, LN_EPS,
+                                _ptr(ws["xnd"]), _ptr(ws["meand"]), _ptr(ws["rstdd"]), st)
+        calls.mae_gemm_tn(_ptr(ws["xnd"]), self.pw(o("decoder.decoder_pred.weight")), d["Mm"], d["pd"], Dd, EPI_BF16,
+                          self.pf(o("decoder.decoder_pred.bias")), _ptr(ws["pred"]), None, None, st)
+
+    # ---------------- backward ----------------
+    def _linear_bwd_w(self, dy: int, n_out: int, x: int, n_in: int, M: int, w_off: int, b_off: int, st: int) -> None:
+        """dW (n_out, n_in) += dY^T X and db += colsum(dY).  The wider operand rides the MMA M axis."""
+        if n_in <= 256 and n_in % 16 == 0:
+            calls.mae_gemm_wgrad(dy, n_out, x, n_in, M, self.pg(w_off), n_in, 1, st)
+        else:
+            calls.mae_gemm_wgrad(x, n_in, dy, n_out, M, self.pg(w_off), 1, n_in, st)
+        calls.mae_colsum_bf16(dy, M, n_out, self.pg(b_off), st)
+
+    def _block_bwd(self, w: _BlockW, s: Dict[str, torch.Tensor], dx: torch.Tensor, dxb: torch.Tensor,
+                   dx_out: torch.Tensor, dxb_out: torch.Tensor, M: int, B: int, L: int, st: int) -> None:
+        """dx/dxb: fp32 / bf16 gradient w.r.t. the block output; writes the gradient w.r.t. its input."""
+        ws = self.ws
+        D, H, hd = w.dim, w.heads, w.hd
+        # mlp.fc2
+        self._linear_bwd_w(_ptr(dxb), D, _ptr(s["h"]), 4 * D, M, w.fc2w, w.fc2b, st)
+        calls.mae_gemm_tn(_ptr(dxb), self.pwt(w.fc2w), M, 4 * D, D, EPI_DGELU_BF16, None, _ptr(ws["dh"]), None,
+                          _ptr(s["pre"]), st)
+        # mlp.fc1 + norm2
+        self._linear_bwd_w(_ptr(ws["dh"]), 4 * D, _ptr(s["xn2"]), D, M, w.fc1w, w.fc1b, st)
+        calls.mae_gemm_tn(_ptr(ws["dh"]), self.pwt(w.fc1w), M, D, 4 * D, EPI_BF16, None, _ptr(ws["g"]), None, None, st)
+        calls.mae_layernorm_bwd(_ptr(ws["g"]), _ptr(s["x_mid"]), _ptr(s["mean2"]), _ptr(s["rstd2"]), self.pf(w.n2w),
+                                _ptr(dx), None, 0, 0, M, D, _ptr(dx_out), _ptr(dxb_out), self.pg(w.n2w), self.pg(w.n2b), st)
+        # attn.proj
+        self._linear_bwd_w(_ptr(dxb_out), D, _ptr(s["att"]), D, M, w.projw, w.projb, st)
+        calls.mae_gemm_tn(_ptr(dxb_out), self.pwt(w.projw), M, D, D, EPI_BF16, None, _ptr(ws["datt"]), None, None, st)
+        calls.mae_attention_bwd(_ptr(s["qkv"]), _ptr(s["att"]), _ptr(ws["datt"]), _ptr(s["lse"]), B, L, H, hd,
+                                _ptr(ws["dqkv"]), st)
+        # attn.qkv + norm1
+        self._linear_bwd_w(_ptr(ws["dqkv"]), 3 * D, _ptr(s["xn1"]), D, M, w.qkvw, w.qkvb, st)
+        calls.mae_gemm_tn(_ptr(ws["dqkv"]), self.pwt(w.qkvw), M, D, 3 * D, EPI_BF16, None, _ptr(ws["g"]), None, None, st)
+        calls.mae_layernorm_bwd(_ptr(ws["g"]), _ptr(s["x_in"]), _ptr(s["mean1"]), _ptr(s["rstd1"]), self.pf(w.n1w),
+                                _ptr(dx_out), None, 0, 0, M, D, _ptr(dx_out), _ptr(dxb_out), self.pg(w.n1w),
+                                self.pg(w.n1b), st)
+
+    def backward(self, dpred: Optional[torch.Tensor] = None, bucket_cb=None) -> None:
+        """Gradients of all trainable parameters into ``self.grads`` (zeroed first).  ``dpred`` defaults to
+        the MSE gradient produced by the fused loss kernel in :meth:`forward`.  ``bucket_cb("decoder")`` /
+        ``bucket_cb("encoder")`` fire as soon as that half of the flat gradient buffer is complete (the
+        data-parallel trainer starts the bucket's all-reduce there, overlapping the rest of backward)."""
+        ws, d = self.ws, self.dims
+        B, L, Lk, Lm, De, Dd, pd = d["B"], d["L"], d["Lk"], d["Lm"], d["De"], d["Dd"], d["pd"]
+        Me, Md, Mm = d["Me"], d["Md"], d["Mm"]
+        o = self._o
+        dev = self.flat.device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        if dpred is None:
+            dpred = ws["dpred"]
+        else:
+            dpred = dpred.to(torch.bfloat16).contiguous()
+        self.grads.zero_()
+        dx_a, dx_b, dxb_a, dxb_b = ws["dx_a"], ws["dx_b"], ws["dxb_a"], ws["dxb_b"]
+        # decoder_pred + decoder_norm (gradient lands only on the masked rows of the decoder stream)
+        self._linear_bwd_w(_ptr(dpred), pd, _ptr(ws["xnd"]), Dd, Mm, o("decoder.decoder_pred.weight"),
+                           o("decoder.decoder_pred.bias"), st)
+        calls.mae_gemm_tn(_ptr(dpred), self.pwt(o("decoder.decoder_pred.weight")), Mm, Dd, pd, EPI_BF16, None,
+                          _ptr(ws["g"]), None, None, st)
+        dx_a[:Md * Dd].zero_()
+        dxb_a[:Md * Dd].zero_()
+        calls.mae_layernorm_bwd(_ptr(ws["g"]), _ptr(ws["x_dec"]), _ptr(ws["meand"]), _ptr(ws["rstdd"]),
+                                self.pf(o("decoder.decoder_norm.weight")), None, _ptr(ws["idx_mask"]), Lm, L, Mm, Dd,
+                                _ptr(dx_a), _ptr(dxb_a), self.pg(o("decoder.decoder_norm.weight")),
+                                self.pg(o("decoder.decoder_norm.bias")), st)
+        cur, curb, nxt, nxtb = dx_a, dxb_a, dx_b, dxb_b
+        for i in reversed(range(len(self.dec_blocks))):
+            self._block_bwd(self.dec_blocks[i], ws["dec"][i], cur, curb, nxt, nxtb, Md, B, L, st)
+            cur, curb, nxt, nxtb = nxt, nxtb, cur, curb
+        # decoder input = scatter(embed) / mask_token, + frozen pos
+        calls.mae_colsum_rows_f32(_ptr(cur), _ptr(ws["idx_mask"]), B, Lm, L, 0, Dd, self.pg(o("decoder.mask_token")), st)
+        calls.mae_gather_rows_bf16(_ptr(cur), _ptr(ws["idx_keep"]), B, Lk, L, 0, Dd, _ptr(ws["demb"]), st)
+        self._linear_bwd_w(_ptr(ws["demb"]), Dd, _ptr(ws["xnf"]), De, Me, o("decoder.decoder_embed.weight"),
+                           o("decoder.decoder_embed.bias"), st)
+        if bucket_cb is not None:
+            bucket_cb("decoder")
+        calls.mae_gemm_tn(_ptr(ws["demb"]), self.pwt(o("decoder.decoder_embed.weight")), Me, De, Dd, EPI_BF16, None,
+                          _ptr(ws["g"]), None, None, st)
+        calls.mae_layernorm_bwd(_ptr(ws["g"]), _ptr(ws["x_enc"]), _ptr(ws["meanf"]), _ptr(ws["rstdf"]),
+                                self.pf(o("encoder.vit.norm.weight")), None, None, 0, 0, Me, De, _ptr(nxt), _ptr(nxtb),
+                                self.pg(o("encoder.vit.norm.weight")), self.pg(o("encoder.vit.norm.bias")), st)
+        cur, curb, nxt, nxtb = nxt, nxtb, cur, curb
+        for i in reversed(range(len(self.enc_blocks))):
+            self._block_bwd(self.enc_blocks[i], ws["enc"][i], cur, curb, nxt, nxtb, Me, B, Lk, st)
+            cur, curb, nxt, nxtb = nxt, nxtb, cur, curb
+        # tokens = cat(cls, patch_embed(kept patches)) + frozen pos
+        calls.mae_colsum_rows_f32(_ptr(cur), None, B, 1, Lk, 0, De, self.pg(o("encoder.vit.cls_token")), st)
+        calls.mae_gather_rows_bf16(_ptr(cur), None, B, Lk - 1, Lk, 1, De, _ptr(ws["dtok"]), st)
+        self._linear_bwd_w(_ptr(ws["dtok"]), De, _ptr(ws["patches"]), pd, B * (Lk - 1),
+                           o("encoder.vit.patch_embed.proj.weight"), o("encoder.vit.patch_embed.proj.bias"), st)
+        if bucket_cb is not None:
+            bucket_cb("encoder")
+
+    # ---------------- optimizer ----------------
+    def clip_adamw(self, lr: float, weight_decay: float = 0.05, betas=(0.9, 0.999), eps: float = 1e-8,
+                   max_norm: float = 1.0) -> torch.Tensor:
+        """Lightning clip-by-norm + AdamW over the flat buffers; refreshes the bf16 shadows.  Returns the
+        (device) pre-clip gradient norm."""
+        st = torch.cuda.current_stream(self.flat.device).cuda_stream
+        self.step_count += 1
+        nparts = 1024
+        calls.mae_grad_sumsq(self.grads.data_ptr(), self.n_opt, self.partials.data_ptr(), nparts, st)
+        calls.mae_clip_adamw(self.flat.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(),
+                             self.exp_avg_sq.data_ptr(), self.flat_bf16.data_ptr(), self.n_opt, float(lr), betas[0],
+                             betas[1], eps, weight_decay, max_norm, self.step_count, self.partials.data_ptr(), nparts,
+                             self.grad_norm.data_ptr(), st)
+        calls.mae_transpose_cast_bf16(self.flat.data_ptr(), self.flat_bf16_t.data_ptr(), self.t_table.data_ptr(),
+                                      self.t_table.shape[0], st)
+        self._shadow_version = self.flat._version
+        return self.grad_norm
+
+    def named_grads(self) -> Dict[str, torch.Tensor]:
+        out = {}
+        for n, p in self._ordered_params():
+            o = self.offsets[n]
+            if o < self.n_opt:
+                out[n] = self.grads[o:o + p.numel()].view(p.shape)
+        return out
+
+
+class _MAEFunction(torch.autograd.Function):
+    """autograd bridge for the reference-style API: ``pred, target = model(images)`` followed by any loss."""
+
+    @staticmethod
+    def forward(ctx, engine: MAEEngine, images, noise, mask_ratio, *params):
+        pred, target, _ = engine.forward(images, noise, mask_ratio, want_target=True, compute_loss=False)
+        ctx.engine = engine
+        ctx.n_params = len(params)
+        ctx.mark_non_differentiable(target)
+        return pred.clone(), target
+
+    @staticmethod
+    def backward(ctx, dpred, _dtarget):
+        eng: MAEEngine = ctx.engine
+        eng.backward(dpred)
+        grads = eng.named_grads()
+        out = []
+        for n, p in eng._grad_order:
+            g = grads.get(n)
+            out.append(g.clone() if (g is not None and p.requires_grad) else None)
+        return (None, None, None, None, *out)
+
+
+class MaskedAutoencoder(nn.Module):
+    """Masked Autoencoder (MAE) with ViT backbone -- drop-in for reference ``src/models/mae.py``."""
+
+    def __init__(self, general_cfg: Dict[str, Any], encoder_cfg: Dict[str, Any], decoder_cfg: Dict[str, Any]):
+        super().__init__()
+        self.mask_ratio = general_cfg.get("mask_ratio", 0.75)
+        self.image_size = general_cfg.get("image_size", 96)
+        self.patch_size = general_cfg.get("patch_size", 6)
+        self.in_chans = general_cfg.get("in_chans", 3)
+        embed_dim = encoder_cfg.get("embed_dim", 384)
+        vit = _VisionTransformer(self.image_size, self.patch_size, self.in_chans, embed_dim,
+                                 encoder_cfg.get("depth", 12), encoder_cfg.get("num_heads", 6))
+        self.encoder = _MaskedViT(vit)
+        self.sequence_length = self.encoder.sequence_length
+        self.decoder = _MAEDecoder(vit.patch_embed.num_patches, self.patch_size, self.in_chans, embed_dim,
+                                   decoder_cfg.get("decoder_embed_dim", 512), decoder_cfg.get("decoder_depth", 4),
+                                   decoder_cfg.get("decoder_num_heads", 6))
+        object.__setattr__(self, "_engine", MAEEngine(self))
+        self._check_supported()
+
+    def _check_supported(self) -> None:
+        vit, dec = self.encoder.vit, self.decoder
+        pd = self.in_chans * self.patch_size**2
+        dims = [(vit.embed_dim, vit.num_heads)]
+        if len(dec.decoder_blocks):
+            dims.append((dec.decoder_embed.out_features, dec.decoder_blocks[0].attn.num_heads))
+        for D, H in dims:
+            if D % 16 or D > 256 or D // H not in (24, 32):
+                raise NotImplementedError(f"kernels cover embed dims <= 256 (mult. of 16) with head_dim 24/32; got {D}/{H}")
+        if pd % 16 or self.sequence_length > 160:
+            raise NotImplementedError("kernels cover patch_dim % 16 == 0 and sequence_length <= 160")
+
+    @property
+    def engine(self) -> MAEEngine:
+        return self._engine
+
+    # -- reference surface ---------------------------------------------------------------
+    def forward(self, images: torch.Tensor, *, mask_ratio: Optional[float] = None, noise: Optional[torch.Tensor] = None):
+        """``(x_pred (B,Lm,p*p*C) bf16, target (B,Lm,p*p*C) f32)`` exactly like reference ``forward``."""
+        eng = self._engine
+        eng._ensure_flat(images.device)
+        eng._grad_order = [(n, p) for n, p in self.named_parameters()]
+        params = [p for _, p in eng._grad_order]
+        r = self.mask_ratio if mask_ratio is None else mask_ratio
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _MAEFunction.apply(eng, images, noise, r, *params)
+        pred, target, _ = eng.forward(images, noise, r, want_target=True, compute_loss=False)
+        return pred.clone(), target
+
+    def forward_loss(self, images: torch.Tensor, mask_ratio: Optional[float] = None,
+                     noise: Optional[torch.Tensor] = None):
+        """Fused path: ``(loss (), pred, mask (B, num_patches) with 1 = masked)``; follow with
+        ``engine.backward()`` / ``engine.clip_adamw()``.  The loss stays on the device."""
+        r = self.mask_ratio if mask_ratio is None else mask_ratio
+        pred, _, loss = self._engine.forward(images, noise, r)
+        ws = self._engine.ws
+        mask = torch.ones(images.shape[0], self.sequence_length, device=images.device)
+        mask.scatter_(1, ws["idx_keep"], 0.0)
+        return loss[0], pred, mask[:, 1:]
+
+    @torch.no_grad()
+    def forward_encoder(self, images: torch.Tensor, idx_keep=None):
+        """``encoder.encode(images, idx_keep)``: LayerNorm-ed encoder tokens (B, num_keep, D) (inference only)."""
+        eng = self._engine
+        eng._ensure_flat(images.device)
+        B, L = images.shape[0], self.sequence_length
+        if idx_keep is None:
+            idx_keep = torch.arange(L, device=images.device).unsqueeze(0).expand(B, -1)
+        idx_keep = idx_keep.to(torch.int64).contiguous()
+        if idx_keep.shape[1] > 160:
+            raise NotImplementedError("sequence too long for the fused attention kernel")
+        eng._ensure_ws(B, idx_keep.shape[1], images.device)
+        st = torch.cuda.current_stream(images.device).cuda_stream
+        eng._refresh_shadow(st)
+        eng.ws["idx_keep"].copy_(idx_keep)
+        eng._encode(images.contiguous(), eng.ws["idx_keep"], st)
+        return eng.ws["xnf"].view(B, idx_keep.shape[1], -1).float()
+
+    @torch.no_grad()
+    def forward_decoder(self, x_encoded, idx_keep, idx_mask):
+        """``decoder.embed`` -> mask-token scatter -> ``decode`` -> gather ``idx_mask`` -> ``predict``."""
+        eng = self._engine
+        B = x_encoded.shape[0]
+        eng._ensure_flat(x_encoded.device)
+        eng._ensure_ws(B, idx_keep.shape[1], x_encoded.device)
+        st = torch.cuda.current_stream(x_encoded.device).cuda_stream
+        eng._refresh_shadow(st)
+        eng.ws["idx_keep"].copy_(idx_keep)
+        eng.ws["idx_mask"].copy_(idx_mask)
+        eng.ws["xnf"].copy_(x_encoded.reshape(eng.ws["xnf"].shape))
+        eng._decode(st)
+        return eng.ws["pred"].clone()

@@ -1,0 +1,192 @@
+"""Host-side mirror of the reference's ``src/training/mae.py`` plus the fused data-parallel step.
+
+``MAEPretrainModule`` keeps the reference constructor ``(model_cfg, training_cfg)``, attributes, and the
+``forward / training_step / validation_step / configure_optimizers / on_train_epoch_start`` methods
+(reference ``src/training/mae.py:14-83``).  When ``pytorch_lightning`` is importable it subclasses
+``pl.LightningModule`` exactly like the reference; this image does not ship it, so a tiny stand-in base
+with the handful of members the module touches (``save_hyperparameters``, ``log``, ``current_epoch``) is
+used instead.
+
+``FusedTrainer`` is the B200 fast path for the same step: forward + masked MSE + backward + (bucketed
+NCCL all-reduce overlapped with the encoder backward) + clip(1.0) + AdamW, all through the C ABI, with no
+autograd graph and no host synchronisation.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+from torch.optim import AdamW
+from torch.optim.lr_scheduler import LambdaLR
+
+from .mae import MaskedAutoencoder
+
+try:  # pragma: no cover - not installed in this image
+    import pytorch_lightning as pl
+
+    _Base = pl.LightningModule
+except Exception:  # noqa: BLE001
+
+    class _Base(torch.nn.Module):  # minimal LightningModule surface used by the reference module
+        def __init__(self):
+            super().__init__()
+            self.current_epoch = 0
+            self.logged: Dict[str, Any] = {}
+            self.hparams: Dict[str, Any] = {}
+
+        def save_hyperparameters(self, **kw):
+            import inspect
+
+            frame = inspect.currentframe().f_back
+            args = {k: v for k, v in frame.f_locals.items() if k not in ("self", "__class__")}
+            self.hparams = dict(args)
+
+        def log(self, name: str, value, **kw):
+            self.logged[name] = value
+
+
+def mask_ratio_for_epoch(epoch: int, start: float, end: float, ramp_epochs: int) -> float:
+    """reference ``src/training/mae.py:78-82``."""
+    progress = min(epoch / max(1, ramp_epochs - 1), 1.0)
+    return start + progress * (end - start)
+
+
+def lr_factor(epoch: int, warmup_epochs: int, total_epochs: int) -> float:
+    """reference ``src/training/mae.py:67-70``: linear warm-up x cosine, stepped once per epoch."""
+    warmup = (epoch + 1) / max(1, warmup_epochs)
+    cosine = 0.5 * (1 + math.cos(math.pi * epoch / total_epochs))
+    return min(warmup, 1.0) * cosine
+
+
+class MAEPretrainModule(_Base):
+    """Self-supervised pretraining for Masked Autoencoder (reference ``src/training/mae.py:14``)."""
+
+    def __init__(self, model_cfg: Dict[str, Any], training_cfg: Dict[str, Any]):
+        super().__init__()
+        self.save_hyperparameters()
+        self.model = MaskedAutoencoder(
+            general_cfg=model_cfg["general"], encoder_cfg=model_cfg["encoder"], decoder_cfg=model_cfg["decoder"])
+        self.mask_start = training_cfg.get("mask_ratio_start", 0.5)
+        self.mask_end = training_cfg.get("mask_ratio_end", 0.85)
+        self.ramp_epochs = training_cfg.get("mask_ramp_epochs", 200)
+        self.lr = float(training_cfg.get("base_learning_rate", 1.5e-4))
+        self.weight_decay = float(training_cfg.get("weight_decay", 0.05))
+        self.warmup_epochs = int(training_cfg.get("warmup_epochs", 20))
+        self.total_epochs = int(training_cfg.get("total_epochs", 200))
+        self.batch_size = int(training_cfg.get("batch_size", 512))
+        self.criterion = torch.nn.MSELoss()
+
+    def forward(self, x: torch.Tensor):
+        return self.model(x)
+
+    def training_step(self, batch, batch_idx):
+        imgs, _ = batch
+        preds, targets = self(imgs)
+        loss = self.criterion(preds.float(), targets)
+        self.log("train_loss", loss, prog_bar=True, on_epoch=True)
+        return loss
+
+    def validation_step(self, batch, batch_idx):
+        imgs, _ = batch
+        with torch.no_grad():
+            loss, _, _ = self.model.forward_loss(imgs)
+        self.log("val_loss", loss, prog_bar=True, on_epoch=True)
+        return loss
+
+    @property
+    def effective_lr(self) -> float:
+        return self.lr * self.batch_size / 256
+
+    def configure_optimizers(self):
+        optimizer = AdamW(self.parameters(), lr=self.effective_lr, weight_decay=self.weight_decay)
+        scheduler = LambdaLR(optimizer, lambda e: lr_factor(e, self.warmup_epochs, self.total_epochs))
+        return {"optimizer": optimizer, "lr_scheduler": {"scheduler": scheduler, "interval": "epoch", "name": "lr"}}
+
+    def on_train_epoch_start(self):
+        """Update mask ratio linearly over epochs."""
+        new_mask = mask_ratio_for_epoch(self.current_epoch, self.mask_start, self.mask_end, self.ramp_epochs)
+        self.model.mask_ratio = new_mask
+        self.log("mask_ratio", new_mask, prog_bar=True)
+
+
+class GradBuckets:
+    """Contiguous slices of one flat gradient buffer, all-reduced (averaged) one bucket at a time so a
+    bucket's collective can run while the backward pass still produces the next one.  Works on any
+    backend (NCCL on the GPUs; gloo in the CPU tests)."""
+
+    def __init__(self, flat: torch.Tensor, boundaries: List[int], group=None):
+        assert boundaries[0] == 0 and boundaries[-1] == flat.numel() and sorted(boundaries) == list(boundaries)
+        self.flat, self.boundaries, self.group = flat, list(boundaries), group
+        self.pending: List[Any] = []
+
+    @property
+    def n(self) -> int:
+        return len(self.boundaries) - 1
+
+    def launch(self, i: int) -> None:
+        import torch.distributed as dist
+
+        lo, hi = self.boundaries[i], self.boundaries[i + 1]
+        self._avg = dist.get_backend(self.group) == "nccl"  # gloo has no AVG: sum, then scale in finish()
+        if hi > lo:
+            op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+            self.pending.append(dist.all_reduce(self.flat[lo:hi], op=op, group=self.group, async_op=True))
+
+    def finish(self) -> None:
+        import torch.distributed as dist
+
+        for w in self.pending:
+            w.wait()
+        self.pending.clear()
+        if not getattr(self, "_avg", False):
+            self.flat.div_(dist.get_world_size(self.group))
+
+
+class FusedTrainer:
+    """fwd + masked-MSE + bwd + grad all-reduce + clip + AdamW on one stream through the C ABI.
+
+    One process per GPU; parameters are replicated, the batch is sharded, gradients are averaged.  The
+    learning rate follows the reference (``effective_lr = base_lr * batch_size / 256`` with the per-process
+    batch size from the YAML, ``src/training/mae.py:60``) times the per-epoch warm-up x cosine factor."""
+
+    def __init__(self, module: MAEPretrainModule, distributed: Optional[bool] = None, max_norm: float = 1.0):
+        import torch.distributed as dist
+
+        self.module = module
+        self.model = module.model
+        self.engine = module.model.engine
+        self.max_norm = max_norm
+        self.epoch = 0
+        self.distributed = (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) \
+            if distributed is None else distributed
+        self._buckets: Optional[GradBuckets] = None
+
+    def set_epoch(self, epoch: int) -> None:
+        self.epoch = epoch
+        self.module.current_epoch = epoch
+        self.module.on_train_epoch_start()
+
+    def current_lr(self) -> float:
+        return self.module.effective_lr * lr_factor(self.epoch, self.module.warmup_epochs, self.module.total_epochs)
+
+    def _ensure_buckets(self) -> GradBuckets:
+        eng = self.engine
+        if self._buckets is None or self._buckets.flat.data_ptr() != eng.grads.data_ptr():
+            split = eng.offsets["decoder.mask_token"]  # encoder params [0, split), decoder params [split, n_opt)
+            self._buckets = GradBuckets(eng.grads, [0, split, eng.n_opt])
+        return self._buckets
+
+    def train_step(self, images: torch.Tensor, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One optimisation step; returns the 0-dim device loss tensor (no host sync)."""
+        eng = self.engine
+        _, _, loss = eng.forward(images, noise, self.model.mask_ratio)
+        if self.distributed:
+            eng._ensure_flat(images.device)
+            buckets = self._ensure_buckets()
+            eng.backward(bucket_cb=lambda which: buckets.launch(1 if which == "decoder" else 0))
+            buckets.finish()
+        else:
+            eng.backward()
+        eng.clip_adamw(self.current_lr(), weight_decay=self.module.weight_decay, max_norm=self.max_norm)
+        return loss[0]
