@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""MAE pre-training step benchmark (BASELINE.json metric: images/sec, fwd+bwd+clip+AdamW, device-timed).
+
+  python bench.py --gpus N --steps K --warmup W            # this framework (sm_100a kernels via the C ABI)
+  python bench.py --impl reference ...                       # the reference's CPU path (oracle port) on host cores
+
+Workload at every N: configs/mae.yaml at batch 2000 per GPU (BASELINE.json configs[1]; weak scaling), synthetic
+STL-10-shaped fp32 images, mask 0.75, bf16 tensor-core GEMMs with fp32 accumulation / fp32 master weights.
+One JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_IMAGE = 1_124_504_064  # fwd+bwd, patch-embed on kept patches only, no patch-embed dgrad
+CFG = {
+    "general": {"image_size": 96, "patch_size": 8, "in_chans": 3},
+    "encoder": {"embed_dim": 144, "depth": 4, "num_heads": 6},
+    "decoder": {"decoder_embed_dim": 192, "decoder_depth": 2, "decoder_num_heads": 6},
+}
+PRETRAIN = {"mask_ratio_start": 0.75, "mask_ratio_end": 0.75, "mask_ramp_epochs": 5, "total_epochs": 800,
+            "warmup_epochs": 20, "batch_size": 2000, "base_learning_rate": 1.5e-4, "weight_decay": 0.05}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "tf_burst": p["bf16_tflops"], "tf_sustained": p["bf16_tflops_sustained"],
+                "source": "measured"}
+    except Exception:  # noqa: BLE001
+        return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], 0, set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # median of the upper half = clock while the GPU was busy (idle samples drag a plain median down)
+        busy = sm[len(sm) // 2:] if sm else []
+        med = busy[len(busy) // 2] if busy else None
+        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(steps: int, warmup: int, batch: int = 64, time_budget_s: float = 25.0):
+    """The reference's CPU implementation of the step (oracle port: identical ATen op sequence, fp32 "highest"),
+    on all host cores.  Returns (img/s, cores, ms_per_step, steps_done)."""
+    import torch
+
+    from oracle import mae_oracle as O
+
+    torch.set_float32_matmul_precision("highest")
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = O.build_mae(seed=73)
+    tr = O.OracleTrainer(model, batch_size=batch)
+    g = torch.Generator().manual_seed(73)
+    images = torch.randn(batch, 3, 96, 96, generator=g)
+    for _ in range(warmup):
+        tr.step(images)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        tr.step(images)
+        done += 1
+        if time.perf_counter() - t0 > time_budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return batch * done / dt, cores, 1000 * dt / done, done
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ips, cores, ms, done = cpu_reference_run(args.steps, max(args.warmup, 1), batch=64, time_budget_s=120.0)
+    line = {
+        "impl": "reference", "metric": "MAE pretrain images/sec (fwd+bwd+AdamW)", "value": ips, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": done, "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs/mae.yaml MAE pretrain step, mask 0.75; CPU sample = batch 64 per step"},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{done} steps of batch 64 (oracle port of src/models/mae.py + lightly/timm, fp32 highest)"},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def kernel_breakdown(trainer, images, noise, pk):
+    """One instrumented step: CUDA events around every C-ABI call -> time share per kernel family and the
+    roofline of the dominant one (gemm_tn: algorithmic FLOPs of its launches / their summed duration)."""
+    import torch
+
+    from ssrl_vit_mae_jepa_b200._lib import calls
+
+    lib_calls = calls
+    records = []
+    orig = {}
+
+    def wrap(name):
+        fn = getattr(lib_calls, name)
+
+        def timed(*a):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn(*a)
+            e.record()
+            records.append((name, s, e, a))
+
+        return fn, timed
+
+    from ssrl_vit_mae_jepa_b200 import _lib
+    for name in _lib.SIGNATURES:
+        orig[name], t = wrap(name)
+        setattr(lib_calls, name, t)
+    try:
+        trainer.train_step(images, noise)
+        torch.cuda.synchronize()
+    finally:
+        for name, fn in orig.items():
+            setattr(lib_calls, name, fn)
+    fam = {}
+    gemm_flops = 0.0
+    wgrad_flops = 0.0
+    for name, s, e, a in records:
+        ms = s.elapsed_time(e)
+        d = fam.setdefault(name, [0.0, 0])
+        d[0] += ms; d[1] += 1
+        if name == "mae_gemm_tn":
+            gemm_flops += 2.0 * a[2] * a[3] * a[4]
+        if name == "mae_gemm_wgrad":
+            wgrad_flops += 2.0 * a[1] * a[3] * a[4]
+    total = sum(v[0] for v in fam.values())
+    share = {k: {"ms": round(v[0], 4), "launches": v[1], "share": round(v[0] / total, 4)} for k, v in
+             sorted(fam.items(), key=lambda kv: -kv[1][0])}
+    g_ms = fam.get("mae_gemm_tn", [0.0, 0])[0]
+    roof = None
+    if g_ms > 0:
+        ach = gemm_flops / (g_ms * 1e-3) / 1e12
+        roof = {"kernel": "gemm_tn_kernel (tcgen05, all forward/dgrad GEMMs of one step)", "bound": "tensor",
+                "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+                "traffic": None, "peak_source": pk["source"] + " (sustained: timed inside a long step)",
+                "flops_per_step": gemm_flops, "ms_per_step": g_ms}
+    w_ms = fam.get("mae_gemm_wgrad", [0.0, 0])[0]
+    extra = {"gemm_wgrad_tflops": (wgrad_flops / (w_ms * 1e-3) / 1e12) if w_ms > 0 else None,
+             "instrumented_step_ms": total}
+    return share, roof, extra
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import ssrl_vit_mae_jepa_b200 as P
+    from ssrl_vit_mae_jepa_b200._lib import calls
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the MAE hot path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    torch.manual_seed(73 + rank)  # rank-distinct noise / data streams
+    mod = P.MAEPretrainModule(CFG, dict(PRETRAIN, batch_size=B)).to(dev)
+    if world > 1:  # identical replicas
+        for p in mod.parameters():
+            dist.broadcast(p.data, 0)
+    tr = P.FusedTrainer(mod)
+    tr.set_epoch(0)
+    pool = [torch.randn(B, 3, 96, 96, device=dev) for _ in range(3)]  # 221 MB each: > 126 MB L2 between reuses
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        tr.train_step(pool[i % len(pool)])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = calls.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        loss = tr.train_step(pool[i % len(pool)])
+    ev1.record()
+    barrier()
+    launches = calls.launches - l0
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # end to end through the public API: pinned host batch -> H2D -> step -> D2H of the loss, every step
+    host = [torch.randn(B, 3, 96, 96).pin_memory() for _ in range(2)]
+    stage = torch.empty(B, 3, 96, 96, device=dev)
+    for i in range(2):
+        stage.copy_(host[i % 2], non_blocking=True)
+        tr.train_step(stage).item()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    ev0.record()
+    for i in range(e2e_steps):
+        stage.copy_(host[i % 2], non_blocking=True)
+        lv = tr.train_step(stage).item()
+    ev1.record()
+    barrier()
+    e_ms = max(ev0.elapsed_time(ev1), 1e3 * (time.perf_counter() - t0) * 0)  # device-timed (events bracket the copies)
+    t = torch.tensor([e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / (t.item() * 1e-3)
+
+    if rank == 0:
+        pk = peaks()
+        share, roof, extra = kernel_breakdown(tr, pool[0], None, pk)
+        step_tf = value / world * FLOPS_PER_IMAGE / 1e12
+        line = {
+            "metric": "MAE pretrain images/sec (fwd+bwd+AdamW, device-timed)", "value": value, "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "configs/mae.yaml MAE pretrain step (96px, 8px patches, 144-d x4 enc, 192-d x2 dec), "
+                                   f"batch {B}/GPU, mask 0.75, fwd+bwd+clip+AdamW", "global_batch": B * world,
+                       "parallelism": f"dp{world}", "l2_policy": "3 rotating 221 MB input batches (> 126 MB L2)"},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 96 * 96 * 4,
+                    "d2h_bytes_per_step": 4, "steps": e2e_steps},
+            "gpu_launches": launches, "clocks": clocks, "final_loss": float(loss.item()),
+            "roofline": roof,
+            "step_roofline": {"bound": "tensor", "achieved": step_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                              "frac": step_tf / pk["tf_sustained"], "flops_per_image": FLOPS_PER_IMAGE,
+                              "peak_source": pk["source"]},
+            "kernel_share": share, "extra": extra,
+        }
+        if world == 1 and not args.no_cpu:
+            ips, cores, cms, done = cpu_reference_run(10, 2, batch=64, time_budget_s=20.0)
+            line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                                    "sample": f"{done} steps of batch 64, oracle port, fp32 highest, {cms:.0f} ms/step"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=2000)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

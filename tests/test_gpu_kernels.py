@@ -1,0 +1,310 @@
+"""-m gpu: every kernel of libmae_b200.so, called through the C ABI, against the oracle (integer paths,
+bit-exact) or a plain fp32 torch computation of the same op on the same inputs (floating point; tolerances
+written at each assert).  bf16-output kernels are compared after rounding the reference to bf16 where that is
+the op's contract."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import mae_oracle as O
+from ssrl_vit_mae_jepa_b200._lib import calls
+from tests.gpu_util import bf, cos_sim, gemm_tn, gemm_wgrad, max_err, p, rel_err, report, stream
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+
+
+def _mask(noise, L, Lk):
+    B = noise.shape[0]
+    k = torch.empty(B, Lk, dtype=torch.int64, device=dev)
+    m = torch.empty(B, L - Lk, dtype=torch.int64, device=dev)
+    calls.mae_random_token_mask(p(noise), B, L, Lk, p(k), p(m), stream())
+    return k, m
+
+
+@pytest.mark.parametrize("B,L,ratio", [(4, 145, 0.75), (257, 145, 0.75), (33, 197, 0.75), (5, 17, 0.6), (3, 256, 0.5),
+                                       (2, 145, 0.5), (1, 145, 0.85)])
+def test_token_mask_bit_exact(B, L, ratio):
+    g = torch.Generator().manual_seed(B * 1000 + L)
+    noise = torch.rand(B, L, generator=g)
+    Lk = O.num_keep_tokens(L, ratio)
+    k, m = _mask(noise.to(dev), L, Lk)
+    rk, rm = O.random_token_mask_numpy(noise.numpy(), ratio)
+    assert np.array_equal(k.cpu().numpy(), rk) and np.array_equal(m.cpu().numpy(), rm)
+
+
+def test_token_mask_golden_and_ties(golden):
+    k, m = _mask(torch.from_numpy(golden["noise"]).to(dev), 145, 36)
+    assert np.array_equal(k.cpu().numpy(), golden["idx_keep"]) and np.array_equal(m.cpu().numpy(), golden["idx_mask"])
+    k, m = _mask(torch.from_numpy(golden["tie_noise"]).to(dev), 145, 36)
+    assert np.array_equal(k.cpu().numpy(), golden["tie_idx_keep"]) and np.array_equal(m.cpu().numpy(), golden["tie_idx_mask"])
+    # heavy ties: noise quantised to 8 levels, and signed zeros
+    g = torch.Generator().manual_seed(5)
+    noise = (torch.rand(64, 145, generator=g) * 8).floor() / 8
+    noise[:, 7] = -0.0
+    k, m = _mask(noise.to(dev), 145, 36)
+    rk, rm = O.random_token_mask_numpy(noise.numpy(), 0.75)
+    assert np.array_equal(k.cpu().numpy(), rk) and np.array_equal(m.cpu().numpy(), rm)
+
+
+def test_token_mask_full_size_permutation_property():
+    noise = torch.rand(2000, 145, device=dev)
+    k, m = _mask(noise, 145, 36)
+    allidx = torch.cat([k, m], 1)
+    assert (allidx.sort(1).values == torch.arange(145, device=dev)).all() and (k[:, 0] == 0).all()
+    n = noise.clone(); n[:, 0] = -1
+    s = torch.gather(n, 1, allidx)
+    assert (s[:, 1:] >= s[:, :-1]).all()  # sortedness
+    assert calls.mae_random_token_mask.__name__  # symbol exists
+    with pytest.raises(RuntimeError):
+        calls.mae_random_token_mask(p(noise), 4, 300, 10, p(k), p(m), stream())  # L > 256 -> MAE_ERR_SHAPE
+
+
+def test_gather_patches_and_assemble():
+    B, Lk, D = 7, 36, 144
+    g = torch.Generator().manual_seed(1)
+    images = torch.randn(B, 3, 96, 96, generator=g).to(dev)
+    noise = torch.rand(B, 145, generator=g)
+    k, _ = O.random_token_mask_from_noise(noise, 0.75)
+    k = k.to(dev)
+    patches = torch.empty(B * (Lk - 1), 192, dtype=torch.bfloat16, device=dev)
+    calls.mae_gather_patches(p(images), p(k), B, 3, 96, 8, Lk, p(patches), stream())
+    # conv-weight order (c,py,px): unfold gives exactly that
+    unf = F.unfold(images, kernel_size=8, stride=8).transpose(1, 2)  # (B,144,192)
+    ref = torch.gather(unf, 1, (k[:, 1:] - 1).unsqueeze(-1).expand(-1, -1, 192)).reshape(-1, 192)
+    assert torch.equal(patches, bf(ref))
+    tok = bf(torch.randn(B * (Lk - 1), D, generator=g)).to(dev)
+    cls, pos = torch.randn(D, generator=g).to(dev), torch.randn(145, D, generator=g).to(dev)
+    x = torch.empty(B, Lk, D, device=dev)
+    calls.mae_assemble_tokens(p(tok), p(cls), p(pos), p(k), B, Lk, D, p(x), stream())
+    full = torch.cat([cls.expand(B, 1, D), tok.float().view(B, Lk - 1, D)], 1) + pos[k]
+    assert max_err(x, full) < 1e-6
+
+
+@pytest.mark.parametrize("rows,D", [(1000, 144), (777, 192), (5, 16), (300, 256)])
+def test_layernorm_fwd_bwd(rows, D):
+    g = torch.Generator().manual_seed(rows)
+    x = (torch.randn(rows, D, generator=g) * 2 + 0.5).to(dev)
+    gamma, beta = (torch.rand(D, generator=g) + 0.5).to(dev), torch.randn(D, generator=g).to(dev)
+    xn = torch.empty(rows, D, dtype=torch.bfloat16, device=dev)
+    mean, rstd = torch.empty(rows, device=dev), torch.empty(rows, device=dev)
+    calls.mae_layernorm_fwd(p(x), p(gamma), p(beta), None, 0, 0, rows, D, 1e-6, p(xn), p(mean), p(rstd), stream())
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (D,), gr, br, 1e-6)
+    assert max_err(xn, ref) <= 2 ** -7 * ref.abs().max().item() + 1e-6  # bf16 rounding of the output
+    assert max_err(mean, x.mean(1)) < 1e-5 and rel_err(rstd, 1 / torch.sqrt(x.var(1, unbiased=False) + 1e-6)) < 1e-5
+    dy = bf(torch.randn(rows, D, generator=g)).to(dev)
+    dx_in = torch.randn(rows, D, generator=g).to(dev)
+    ref.backward(dy.float())
+    dx = torch.empty(rows, D, device=dev)
+    dxb = torch.empty(rows, D, dtype=torch.bfloat16, device=dev)
+    dg, db = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+    calls.mae_layernorm_bwd(p(dy), p(x), p(mean), p(rstd), p(gamma), p(dx_in), None, 0, 0, rows, D, p(dx), p(dxb), p(dg), p(db), stream())
+    e1, e2, e3 = max_err(dx, xr.grad + dx_in), rel_err(dg, gr.grad), rel_err(db, br.grad)
+    report("layernorm", rows=rows, D=D, dx_max=e1, dgamma_rel=e2, dbeta_rel=e3)
+    assert e1 < 1e-4 and e2 < 1e-4 and e3 < 1e-4  # fp32 kernel vs fp32 torch
+    assert torch.equal(dxb, bf(dx))
+
+
+def test_layernorm_gather_variants():
+    B, L, n_sel, D = 6, 145, 109, 192
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B * L, D, generator=g).to(dev)
+    idx = torch.stack([torch.randperm(L, generator=g)[:n_sel] for _ in range(B)]).to(dev)
+    gamma, beta = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+    rows = B * n_sel
+    xn = torch.empty(rows, D, dtype=torch.bfloat16, device=dev)
+    mean, rstd = torch.empty(rows, device=dev), torch.empty(rows, device=dev)
+    calls.mae_layernorm_fwd(p(x), p(gamma), p(beta), p(idx), n_sel, L, rows, D, 1e-6, p(xn), p(mean), p(rstd), stream())
+    sel = torch.gather(x.view(B, L, D), 1, idx.unsqueeze(-1).expand(-1, -1, D)).reshape(rows, D)
+    assert max_err(xn, F.layer_norm(sel, (D,), eps=1e-6)) < 0.04
+    dy = bf(torch.randn(rows, D, generator=g)).to(dev)
+    dx = torch.zeros(B * L, D, device=dev)
+    dg, db = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+    calls.mae_layernorm_bwd(p(dy), p(x), p(mean), p(rstd), p(gamma), None, p(idx), n_sel, L, rows, D, p(dx), None, p(dg), p(db), stream())
+    xr = x.clone().view(B, L, D).requires_grad_(True)
+    F.layer_norm(torch.gather(xr, 1, idx.unsqueeze(-1).expand(-1, -1, D)), (D,), eps=1e-6).backward(dy.float().view(B, n_sel, D))
+    assert max_err(dx.view(B, L, D), xr.grad) < 1e-4
+
+
+GEMM_SHAPES = [(128, 64, 64), (128, 144, 144), (300, 432, 144), (1000, 576, 192), (777, 144, 576), (517, 192, 768),
+               (128, 768, 192), (2500, 192, 192), (64, 144, 192), (40000, 576, 192)]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_tn_bias_bf16(M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    A, B = bf(torch.randn(M, K, generator=g)).to(dev), bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    out, _ = gemm_tn(A, B, 0, bias)
+    ref = A.float() @ B.float().t() + bias
+    e = max_err(out, ref)
+    report("gemm_tn", M=M, N=N, K=K, max_err=e, rel=rel_err(out, ref))
+    assert e <= 2 ** -7 * ref.abs().max().item()  # one bf16 ulp of the largest output
+    out2, _ = gemm_tn(A, B, 0, None)
+    assert max_err(out2, A.float() @ B.float().t()) <= 2 ** -7 * ref.abs().max().item()
+
+
+def test_gemm_tn_epilogues():
+    M, D = 1000, 192
+    g = torch.Generator().manual_seed(9)
+    x = bf(torch.randn(M, D, generator=g)).to(dev)
+    W1, b1 = bf(torch.randn(4 * D, D, generator=g) / math.sqrt(D)).to(dev), torch.randn(4 * D, generator=g).to(dev)
+    h, pre = gemm_tn(x, W1, 1, b1)
+    pre_ref = x.float() @ W1.float().t() + b1
+    assert max_err(pre, pre_ref) <= 2 ** -7 * pre_ref.abs().max().item()
+    assert max_err(h, F.gelu(pre.float())) <= 2 ** -7 * pre_ref.abs().max().item()  # gelu of the bf16-rounded pre
+    W2, b2 = bf(torch.randn(D, 4 * D, generator=g) / math.sqrt(4 * D)).to(dev), torch.randn(D, generator=g).to(dev)
+    resid = torch.randn(M, D, generator=g).to(dev)
+    y, _ = gemm_tn(h, W2, 2, b2, aux=resid)
+    y_ref = resid + h.float() @ W2.float().t() + b2
+    e = max_err(y, y_ref)
+    report("gemm_tn_resid", max_err=e)
+    assert y.dtype == torch.float32 and e < 2e-4 * max(1.0, y_ref.abs().max().item())  # fp32 out, fp32 accumulate
+    dy = bf(torch.randn(M, D, generator=g)).to(dev)
+    W2t = bf(W2.float().t())  # (4D, D): B operand of the dgrad
+    dh, _ = gemm_tn(dy, W2t, 4, None, aux=pre)
+    pf = pre.float().requires_grad_(True)
+    F.gelu(pf).backward(dy.float() @ W2.float())
+    e = max_err(dh, pf.grad)
+    report("gemm_tn_dgelu", max_err=e)
+    assert e <= 2 ** -6 * pf.grad.abs().max().item()
+
+
+WGRAD_SHAPES = [(64, 128, 64), (1000, 432, 144), (1000, 144, 144), (5000, 768, 192), (70000, 576, 144), (333, 192, 192),
+                (218000, 192, 192)]
+
+
+@pytest.mark.parametrize("M,Pc,Qc", WGRAD_SHAPES)
+def test_gemm_wgrad(M, Pc, Qc):
+    g = torch.Generator().manual_seed(M + Pc)
+    P, Q = bf(torch.randn(M, Pc, generator=g)).to(dev), bf(torch.randn(M, Qc, generator=g)).to(dev)
+    out = torch.zeros(Pc, Qc, device=dev)
+    gemm_wgrad(P, Q, out, Qc, 1)
+    ref = (P.double().t() @ Q.double()).float()
+    e = rel_err(out, ref)
+    report("gemm_wgrad", M=M, Pc=Pc, Qc=Qc, rel=e, max_err=max_err(out, ref))
+    assert e < 1e-5  # exact bf16 products, fp32 accumulation
+    outT = torch.ones(Qc, Pc, device=dev)  # accumulate semantics + transposed strides
+    gemm_wgrad(P, Q, outT, 1, Pc)
+    assert rel_err(outT - 1, ref.t()) < 1e-5 + 1e-6 * M ** 0.5
+
+
+@pytest.mark.parametrize("B,L,H,hd", [(3, 36, 6, 24), (2, 145, 6, 32), (2, 145, 6, 24), (5, 17, 2, 32), (2, 73, 6, 24),
+                                      (1, 160, 1, 32), (1, 1, 1, 24)])
+def test_attention_fwd_bwd(B, L, H, hd):
+    D = H * hd
+    g = torch.Generator().manual_seed(L * 7 + hd)
+    qkv = bf(torch.randn(B, L, 3, H, hd, generator=g)).to(dev)
+    out = torch.empty(B, L, D, dtype=torch.bfloat16, device=dev)
+    lse = torch.empty(B, H, L, device=dev)
+    calls.mae_attention_fwd(p(qkv), B, L, H, hd, p(out), p(lse), stream())
+    qf = qkv.float().requires_grad_(True)
+    q, k, v = qf.permute(2, 0, 3, 1, 4).unbind(0)
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, L, D)
+    s = (q @ k.transpose(-1, -2)) * hd ** -0.5
+    e = max_err(out, ref)
+    report("attn_fwd", L=L, hd=hd, max_err=e, lse_err=max_err(lse, torch.logsumexp(s, -1)))
+    assert e < 2e-2 and max_err(lse, torch.logsumexp(s, -1)) < 1e-3  # P rounded to bf16, bf16 output
+    dout = bf(torch.randn(B, L, D, generator=g)).to(dev)
+    ref.backward(dout.float())
+    dqkv = torch.empty_like(qkv)
+    calls.mae_attention_bwd(p(qkv), p(out), p(dout), p(lse), B, L, H, hd, p(dqkv), stream())
+    for i, name in enumerate("qkv"):
+        c = cos_sim(dqkv[:, :, i], qf.grad[:, :, i])
+        r = rel_err(dqkv[:, :, i], qf.grad[:, :, i])
+        report("attn_bwd", L=L, hd=hd, which=name, cos=c, rel=r)
+        if L > 1:
+            assert c > 0.999 and r < 3e-2  # bf16 P / dS operands
+        else:
+            assert max_err(dqkv[:, :, i], qf.grad[:, :, i]) < 2e-2
+
+
+def test_scatter_decoder_and_row_ops():
+    B, L, Lk, D = 5, 145, 36, 192
+    g = torch.Generator().manual_seed(11)
+    noise = torch.rand(B, L, generator=g)
+    k, m = [t.to(dev) for t in O.random_token_mask_from_noise(noise, 0.75)]
+    emb = bf(torch.randn(B * Lk, D, generator=g)).to(dev)
+    mt, pos = torch.randn(D, generator=g).to(dev), torch.randn(L, D, generator=g).to(dev)
+    x = torch.empty(B, L, D, device=dev)
+    calls.mae_scatter_decoder_tokens(p(emb), p(mt), p(pos), p(k), p(m), B, L, Lk, D, p(x), stream())
+    ref = O.set_at_index(O.repeat_token(mt.view(1, 1, D), (B, L)), k, emb.float().view(B, Lk, D)) + pos
+    assert max_err(x, ref) < 1e-6
+    src = torch.randn(B, L, D, generator=g).to(dev)
+    out = torch.empty(B * Lk, D, dtype=torch.bfloat16, device=dev)
+    calls.mae_gather_rows_bf16(p(src), p(k), B, Lk, L, 0, D, p(out), stream())
+    assert torch.equal(out, bf(O.get_at_index(src, k).reshape(-1, D)))
+    out2 = torch.empty(B * (L - 1), D, dtype=torch.bfloat16, device=dev)
+    calls.mae_gather_rows_bf16(p(src), None, B, L - 1, L, 1, D, p(out2), stream())
+    assert torch.equal(out2, bf(src[:, 1:].reshape(-1, D)))
+    acc = torch.zeros(D, device=dev)
+    calls.mae_colsum_rows_f32(p(src), p(m), B, L - Lk, L, 0, D, p(acc), stream())
+    assert max_err(acc, O.get_at_index(src, m).sum((0, 1))) < 1e-3
+    acc.zero_()
+    calls.mae_colsum_rows_f32(p(src), None, B, 1, L, 0, D, p(acc), stream())
+    assert max_err(acc, src[:, 0].sum(0)) < 1e-4
+    xb = bf(torch.randn(3001, 432, generator=g)).to(dev)
+    cs = torch.zeros(432, device=dev)
+    calls.mae_colsum_bf16(p(xb), 3001, 432, p(cs), stream())
+    assert rel_err(cs, xb.float().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("norm_pix", [0, 1])
+def test_masked_mse(norm_pix):
+    B, L, Lk = 9, 145, 36
+    g = torch.Generator().manual_seed(21)
+    images = torch.randn(B, 3, 96, 96, generator=g).to(dev)
+    _, m = O.random_token_mask_from_noise(torch.rand(B, L, generator=g), 0.75)
+    m = m.to(dev)
+    Lm = L - Lk
+    pred = bf(torch.randn(B, Lm, 192, generator=g)).to(dev)
+    loss, parts = torch.zeros(1, device=dev), torch.empty(4096, device=dev)
+    dpred = torch.empty_like(pred)
+    target = torch.empty(B, Lm, 192, device=dev)
+    calls.mae_masked_mse(p(pred), p(images), p(m), B, 3, 96, 8, Lm, norm_pix, p(loss), p(parts), p(dpred), p(target), stream())
+    t_ref = O.get_at_index(O.patchify(images, 8), torch.clamp(m - 1, min=0))
+    if norm_pix:
+        t_ref = (t_ref - t_ref.mean(-1, keepdim=True)) / (t_ref.var(-1, keepdim=True) + 1e-6) ** 0.5
+        assert max_err(target, t_ref) < 1e-4
+    else:
+        assert torch.equal(target, t_ref)  # pure data movement: exact
+    pr = pred.float().requires_grad_(True)
+    l_ref = F.mse_loss(pr, t_ref)
+    l_ref.backward()
+    assert abs(loss.item() - l_ref.item()) < 1e-5 * l_ref.item() + 1e-7
+    assert max_err(dpred, pr.grad) <= 2 ** -8 * pr.grad.abs().max().item()
+
+
+def test_casts_and_clip_adamw():
+    g = torch.Generator().manual_seed(31)
+    n = 100_003
+    src = torch.randn(n, generator=g).to(dev)
+    dst = torch.empty(n, dtype=torch.bfloat16, device=dev)
+    calls.mae_cast_bf16(p(src), p(dst), n, stream())
+    assert torch.equal(dst, bf(src))
+    flat = torch.randn(4096 + 432 * 144 + 64, generator=g).to(dev)
+    tbl = torch.tensor([[0, 48, 64, 0], [4096, 432, 144, 4096]], dtype=torch.int64, device=dev)
+    dt = torch.zeros(flat.numel(), dtype=torch.bfloat16, device=dev)
+    calls.mae_transpose_cast_bf16(p(flat), p(dt), p(tbl), 2, stream())
+    assert torch.equal(dt[:48 * 64].view(64, 48), bf(flat[:48 * 64].view(48, 64).t()))
+    assert torch.equal(dt[4096:4096 + 432 * 144].view(144, 432), bf(flat[4096:4096 + 432 * 144].view(432, 144).t()))
+    # clip + AdamW, three steps, against the oracle's explicit restatement
+    pr = torch.randn(n, generator=g)
+    gr = torch.randn(n, generator=g) * 0.01
+    pd_, m_, v_ = pr.clone().to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    shadow = torch.empty(n, dtype=torch.bfloat16, device=dev)
+    parts, gn = torch.zeros(1024, device=dev), torch.zeros(1, device=dev)
+    rp, rm_, rv = [pr.clone()], [torch.zeros(n)], [torch.zeros(n)]
+    for step in (1, 2, 3):
+        gstep = gr * step * 40  # crosses the clip threshold
+        gd = gstep.to(dev)
+        calls.mae_grad_sumsq(p(gd), n, p(parts), 1024, stream())
+        calls.mae_clip_adamw(p(pd_), p(gd), p(m_), p(v_), p(shadow), n, 1e-3, 0.9, 0.999, 1e-8, 0.05, 1.0, step, p(parts), 1024, p(gn), stream())
+        total = O.clip_adamw_reference(rp, [gstep], rm_, rv, step, lr=1e-3)
+        assert abs(gn.item() - total.item()) < 1e-4 * total.item()
+    assert max_err(pd_, rp[0]) < 1e-6 and torch.equal(shadow, bf(pd_))
