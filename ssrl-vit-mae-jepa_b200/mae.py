@@ -605,7 +605,7 @@ class MaskedAutoencoder(nn.Module):
         ws = self._engine.ws
         mask = torch.ones(images.shape[0], self.sequence_length, device=images.device)
         mask.scatter_(1, ws["idx_keep"], 0.0)
-        return loss[0], pred, mask[:, 1:]
+        return loss[0].clone(), pred, mask[:, 1:]
 
     @torch.no_grad()
     def forward_encoder(self, images: torch.Tensor, idx_keep=None):

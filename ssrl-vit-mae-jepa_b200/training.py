@@ -189,4 +189,4 @@ class FusedTrainer:
         else:
             eng.backward()
         eng.clip_adamw(self.current_lr(), weight_decay=self.module.weight_decay, max_norm=self.max_norm)
-        return loss[0]
+        return loss[0].clone()  # the workspace scalar is overwritten by the next step

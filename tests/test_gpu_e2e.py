@@ -32,7 +32,7 @@ def check_grads(tag, mine, ref):
     for n in sorted(ref):
         a, b = mine[n].detach().float().cpu(), ref[n]
         c, r, nb = cos_sim(a, b), rel_err(a, b), b.norm().item()
-        report(tag, name=n, cos=c, rel=r, ref_norm=nb)
+        report(tag, tensor=n, cos=c, rel=r, ref_norm=nb)
         if nb < 1e-3:
             assert max_err(a, b) < 1e-4, n
         else:

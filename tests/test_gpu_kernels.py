@@ -307,4 +307,5 @@ def test_casts_and_clip_adamw():
         calls.mae_clip_adamw(p(pd_), p(gd), p(m_), p(v_), p(shadow), n, 1e-3, 0.9, 0.999, 1e-8, 0.05, 1.0, step, p(parts), 1024, p(gn), stream())
         total = O.clip_adamw_reference(rp, [gstep], rm_, rv, step, lr=1e-3)
         assert abs(gn.item() - total.item()) < 1e-4 * total.item()
-    assert max_err(pd_, rp[0]) < 1e-6 and torch.equal(shadow, bf(pd_))
+        torch.cuda.synchronize()
+    assert max_err(pd_.cpu(), rp[0]) < 1e-6 and torch.equal(shadow, bf(pd_))
