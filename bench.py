@@ -243,22 +243,20 @@ def run_ours(args):
     ms = t.item()
     value = world * B * args.steps / (ms * 1e-3)
 
-    # end to end through the public API: pinned host batch -> H2D -> step -> D2H of the loss, every step
+    # end to end through the public API: pinned host batches -> (prefetching) H2D -> step -> D2H of the loss,
+    # every step.  The copy of batch i+1 overlaps step i on a side stream; it is still inside the timed region.
     host = [torch.randn(B, 3, 96, 96).pin_memory() for _ in range(2)]
-    stage = torch.empty(B, 3, 96, 96, device=dev)
-    for i in range(2):
-        stage.copy_(host[i % 2], non_blocking=True)
-        tr.train_step(stage).item()
-    barrier()
     e2e_steps = max(3, min(args.steps, 10))
-    t0 = time.perf_counter()
+    pf = P.training.DevicePrefetcher((host[i % 2] for i in range(e2e_steps + 2)), dev)
+    for _ in range(2):
+        tr.train_step(next(pf)).item()
+    barrier()
     ev0.record()
-    for i in range(e2e_steps):
-        stage.copy_(host[i % 2], non_blocking=True)
-        lv = tr.train_step(stage).item()
+    for _ in range(e2e_steps):
+        lv = tr.train_step(next(pf)).item()
     ev1.record()
     barrier()
-    e_ms = max(ev0.elapsed_time(ev1), 1e3 * (time.perf_counter() - t0) * 0)  # device-timed (events bracket the copies)
+    e_ms = ev0.elapsed_time(ev1)
     t = torch.tensor([e_ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

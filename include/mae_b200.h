@@ -84,9 +84,11 @@ int mae_gemm_tn(const void* A_bf16, const void* B_bf16, int M, int N, int K, int
                 void* pre_out_bf16, const void* aux, mae_stream_t stream);
 
 /* out[p*so_p + q*so_q] += sum_m P[m,p] * Q[m,q]: weight gradients (autograd of the Linears above).
- * P bf16 (M,Pc), Q bf16 (M,Qc), Qc <= 256, Qc % 16 == 0, Pc % 8 == 0.  fp32 atomics: zero `out` first. */
+ * P bf16 (M,Pc), Q bf16 (M,Qc), Qc <= 256, Qc % 16 == 0, Pc % 8 == 0.  fp32 atomics: zero `out` first.
+ * If colsum != NULL the same launch also accumulates the bias gradient: colsum[c] += sum_m P[m,c]
+ * (colsum_of_q == 0) or sum_m Q[m,c] (colsum_of_q != 0), read from the tiles already staged in shared memory. */
 int mae_gemm_wgrad(const void* P_bf16, int Pc, const void* Q_bf16, int Qc, int M, float* out, long long so_p,
-                   long long so_q, mae_stream_t stream);
+                   long long so_q, float* colsum, int colsum_of_q, mae_stream_t stream);
 
 /* timm Attention core: F.scaled_dot_product_attention on qkv (B,L,3,H,hd) bf16 -> out (B,L,H*hd) bf16,
  * scale hd^-0.5, plus lse (B,H,L) f32 for the backward.  hd in {24,32}; L <= 160. */

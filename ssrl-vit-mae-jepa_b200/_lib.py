@@ -22,7 +22,7 @@ SIGNATURES = {
     "mae_layernorm_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp],
     "mae_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "mae_gemm_tn": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
-    "mae_gemm_wgrad": [_vp, _i, _vp, _i, _i, _vp, _ll, _ll, _vp],
+    "mae_gemm_wgrad": [_vp, _i, _vp, _i, _i, _vp, _ll, _ll, _vp, _i, _vp],
     "mae_attention_fwd": [_vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "mae_attention_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "mae_scatter_decoder_tokens": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],

@@ -1,11 +1,14 @@
 // Fused small-sequence attention (timm Attention core = F.scaled_dot_product_attention, no mask, no dropout).
-// One CTA per (sample, head); the whole Q/K/V tile of that head lives in shared memory; one warp owns a
-// 16-row slab.  L <= 160 (encoder 36, decoder 145), head_dim 24 or 32 (24 is zero-padded to 32 for Q.K^T).
-// Tensor work uses warp-level mma.sync m16n8k16 (bf16 in, fp32 accumulate): each (sample, head) problem is
-// 36..145 rows, far below a 128-row tcgen05 tile, and S/P never leave registers.
+// One CTA per (sample, head); the whole Q/K/V tile of that head lives in shared memory (row-major, padded
+// rows); one warp owns a 16-row slab.  L <= 160 (encoder 36, decoder 145), head_dim 24 or 32 (24 is zero-padded
+// to 32).  Tensor work uses warp-level mma.sync m16n8k16 (bf16 in, fp32 accumulate) fed by ldmatrix: each
+// (sample, head) problem is 36..145 rows, far below a 128-row tcgen05 tile, and S/P never leave registers.
 //
-// Backward recomputes S twice, once per orientation, so that every gradient is produced by the warp that
-// owns its rows (no cross-warp reduction, no atomics, no P/dS round trip through shared memory):
+// Register pressure is kept low so that several CTAs are resident per SM (the load phase of one overlaps the
+// math of another): the forward makes two passes over the keys (pass 1: online row max / sum, pass 2: recompute
+// S per 16-key block, P = exp(S - max), O += P.V); the backward uses the saved log-sum-exp, so every 16-wide
+// block of P is recomputed independently.  Backward recomputes S once per orientation so that every gradient
+// is produced by the warp that owns its rows (no cross-warp reduction, no atomics, no smem round trip for P/dS):
 //   phase A (warp = 16 queries): P, dP = dO.V^T, dS = P o (dP - delta), dQ = dS.K
 //   phase B (warp = 16 keys):    P^T, dP^T = V.dO^T, dS^T,  dV = P^T.dO, dK = dS^T.Q
 #include "mae_internal.h"
@@ -13,104 +16,139 @@
 
 namespace mae {
 
-static constexpr int ST = 40;  // smem row stride (bf16) of [row][d] tiles: 32 data + 8 pad -> conflict-free frags
+static constexpr int ST = 40;  // smem row stride (bf16): 32 data + 8 pad -> 80-byte rows, conflict-free ldmatrix
 
-__device__ __forceinline__ uint32_t ld32(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const __nv_bfloat16* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const __nv_bfloat16* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
 
-// A fragment (16 rows x 16 k) of a row-major [row][k] smem tile
-__device__ __forceinline__ void load_a_frag(uint32_t (&a)[4], const __nv_bfloat16* tile, int row0, int k0, int g, int t) {
-  a[0] = ld32(tile + (row0 + g) * ST + k0 + t * 2);
-  a[1] = ld32(tile + (row0 + g + 8) * ST + k0 + t * 2);
-  a[2] = ld32(tile + (row0 + g) * ST + k0 + 8 + t * 2);
-  a[3] = ld32(tile + (row0 + g + 8) * ST + k0 + 8 + t * 2);
+// A fragment: 16 rows [row0, +16) x 16 k [k0, +16) of a row-major tile.
+__device__ __forceinline__ void frag_a(uint32_t (&a)[4], const __nv_bfloat16* tile, int row0, int k0, int lane) {
+  ldsm_x4(a, tile + (row0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ST + k0 + (lane >> 4) * 8);
+}
+// B fragments for  D[m][n] += A[m][k] * X[n][k]  (X row-major [n][k], k = the 32 padded head-dim columns):
+// {b[0], b[1]} serve k-step 0, {b[2], b[3]} k-step 1, for the 8 rows n0..n0+7 of X.
+__device__ __forceinline__ void frag_b_rows(uint32_t (&b)[4], const __nv_bfloat16* tile, int n0, int lane) {
+  ldsm_x4(b, tile + (n0 + (lane & 7)) * ST + (lane >> 3) * 8);
+}
+// B fragments for  D[m][n] += A[m][k] * X[k][n]  (X row-major [k][n]): 16 k-rows k0.., 16 n-columns d0..:
+// {b[0], b[1]} serve n-tile d0, {b[2], b[3]} n-tile d0 + 8.
+__device__ __forceinline__ void frag_b_cols(uint32_t (&b)[4], const __nv_bfloat16* tile, int k0, int d0, int lane) {
+  ldsm_x4_t(b, tile + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ST + d0 + (lane >> 4) * 8);
+}
+
+template <int NARR>
+__device__ __forceinline__ void load_tiles(const __nv_bfloat16* const (&src)[NARR], const int (&ld)[NARR],
+                                           __nv_bfloat16* const (&dst)[NARR], int L, int Lp, int chunks, int tid,
+                                           int nthreads) {
+  for (int i = tid; i < Lp * 4; i += nthreads) {
+    const int r = i >> 2, c = i & 3;
+    const bool ok = r < L && c < chunks;
+#pragma unroll
+    for (int a = 0; a < NARR; ++a) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (ok) v = *reinterpret_cast<const uint4*>(src[a] + size_t(r) * ld[a] + c * 8);
+      *reinterpret_cast<uint4*>(dst[a] + r * ST + c * 8) = v;
+    }
+  }
 }
 
 template <int HD, int NT>
 __global__ void __launch_bounds__(NT * 16) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                            __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
                                                            int L, int H, float scale) {
-  constexpr int Lp = NT * 8, LpP = Lp + 8, CH = HD / 8, DN = HD / 8;
+  constexpr int Lp = NT * 8, DN = HD / 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
   __nv_bfloat16* sK = sQ + Lp * ST;
-  __nv_bfloat16* sVt = sK + Lp * ST;  // [32][LpP]
+  __nv_bfloat16* sV = sK + Lp * ST;
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int D = H * HD;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
-
-  for (int i = tid; i < Lp * 4; i += NT * 16) {
-    const int r = i >> 2, c = i & 3;
-    uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q;
-    if (r < L && c < CH) {
-      const __nv_bfloat16* base = qkv + (size_t(b) * L + r) * 3 * D + h * HD + c * 8;
-      q = *reinterpret_cast<const uint4*>(base);
-      k = *reinterpret_cast<const uint4*>(base + D);
-      v = *reinterpret_cast<const uint4*>(base + 2 * D);
-    }
-    *reinterpret_cast<uint4*>(sQ + r * ST + c * 8) = q;
-    *reinterpret_cast<uint4*>(sK + r * ST + c * 8) = k;
-    const __nv_bfloat16* vv = reinterpret_cast<const __nv_bfloat16*>(&v);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) sVt[(c * 8 + e) * LpP + r] = vv[e];
+  {
+    const __nv_bfloat16* base = qkv + size_t(b) * L * 3 * D + h * HD;
+    const __nv_bfloat16* const src[3] = {base, base + D, base + 2 * D};
+    const int ld[3] = {3 * D, 3 * D, 3 * D};
+    __nv_bfloat16* const dst[3] = {sQ, sK, sV};
+    load_tiles<3>(src, ld, dst, L, Lp, HD / 8, tid, NT * 16);
   }
   __syncthreads();
 
   const int q0 = w * 16;
   uint32_t aq[2][4];
-  load_a_frag(aq[0], sQ, q0, 0, g, t);
-  load_a_frag(aq[1], sQ, q0, 16, g, t);
-  float s[NT][4];
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      const __nv_bfloat16* kr = sK + (nt * 8 + g) * ST + ks * 16 + t * 2;
-      mma_16816(s[nt], aq[ks], ld32(kr), ld32(kr + 8));
-    }
-  }
+  frag_a(aq[0], sQ, q0, 0, lane);
+  frag_a(aq[1], sQ, q0, 16, lane);
   const float sl2 = scale * 1.4426950408889634f;
-  float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int col = nt * 8 + t * 2 + (i & 1);
-      if (col >= L) s[nt][i] = -INFINITY;
-    }
-    m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
-    m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
-  }
-  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-  float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    s[nt][0] = exp2f((s[nt][0] - m0) * sl2); s[nt][1] = exp2f((s[nt][1] - m0) * sl2);
-    s[nt][2] = exp2f((s[nt][2] - m1) * sl2); s[nt][3] = exp2f((s[nt][3] - m1) * sl2);
-    sum0 += s[nt][0] + s[nt][1];
-    sum1 += s[nt][2] + s[nt][3];
-  }
-  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
 
-  float o[DN][4];
+  // pass 1: row max only (no exponentials); key columns >= L exist only in the last tiles, so only those mask
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll 2
+  for (int nt = 0; nt < NT; ++nt) {
+    uint32_t bk[4];
+    frag_b_rows(bk, sK, nt * 8, lane);
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_16816(s, aq[0], bk[0], bk[1]);
+    mma_16816(s, aq[1], bk[2], bk[3]);
+    if (nt * 8 + 8 > L) {  // warp-uniform
+      const int c = nt * 8 + t * 2;
+      if (c >= L) { s[0] = -INFINITY; s[2] = -INFINITY; }
+      if (c + 1 >= L) { s[1] = -INFINITY; s[3] = -INFINITY; }
+    }
+    m0 = fmaxf(m0, fmaxf(s[0], s[1]));
+    m1 = fmaxf(m1, fmaxf(s[2], s[3]));
+  }
+  float M0 = m0, M1 = m1;
+  M0 = fmaxf(M0, __shfl_xor_sync(0xffffffffu, M0, 1)); M0 = fmaxf(M0, __shfl_xor_sync(0xffffffffu, M0, 2));
+  M1 = fmaxf(M1, __shfl_xor_sync(0xffffffffu, M1, 1)); M1 = fmaxf(M1, __shfl_xor_sync(0xffffffffu, M1, 2));
+
+  // pass 2: recompute S per 16-key block, P = exp(S - max), row sums and O += P.V; normalised at the end
+  float o[4][4];
 #pragma unroll
-  for (int dn = 0; dn < DN; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
-#pragma unroll
+  for (int dn = 0; dn < 4; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
+  const float ms0 = M0 * sl2, ms1 = M1 * sl2;
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll 2
   for (int kk = 0; kk < NT / 2; ++kk) {
-    uint32_t a[4];
-    a[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
-    a[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
-    a[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-    a[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+    float p[2][4];
 #pragma unroll
-    for (int dn = 0; dn < DN; ++dn) {
-      const __nv_bfloat16* vr = sVt + (dn * 8 + g) * LpP + kk * 16 + t * 2;
-      mma_16816(o[dn], a, ld32(vr), ld32(vr + 8));
+    for (int hf = 0; hf < 2; ++hf) {
+      const int nt = 2 * kk + hf;
+      uint32_t bk[4];
+      frag_b_rows(bk, sK, nt * 8, lane);
+      p[hf][0] = p[hf][1] = p[hf][2] = p[hf][3] = 0.f;
+      mma_16816(p[hf], aq[0], bk[0], bk[1]);
+      mma_16816(p[hf], aq[1], bk[2], bk[3]);
+      p[hf][0] = exp2f(p[hf][0] * sl2 - ms0); p[hf][1] = exp2f(p[hf][1] * sl2 - ms0);
+      p[hf][2] = exp2f(p[hf][2] * sl2 - ms1); p[hf][3] = exp2f(p[hf][3] * sl2 - ms1);
+      if (nt * 8 + 8 > L) {  // warp-uniform
+        const int c = nt * 8 + t * 2;
+        if (c >= L) { p[hf][0] = 0.f; p[hf][2] = 0.f; }
+        if (c + 1 >= L) { p[hf][1] = 0.f; p[hf][3] = 0.f; }
+      }
+      l0 += p[hf][0] + p[hf][1];
+      l1 += p[hf][2] + p[hf][3];
+    }
+    uint32_t a[4];
+    a[0] = pack_bf16x2(p[0][0], p[0][1]); a[1] = pack_bf16x2(p[0][2], p[0][3]);
+    a[2] = pack_bf16x2(p[1][0], p[1][1]); a[3] = pack_bf16x2(p[1][2], p[1][3]);
+#pragma unroll
+    for (int dp = 0; dp < 2; ++dp) {
+      uint32_t bv[4];
+      frag_b_cols(bv, sV, kk * 16, dp * 16, lane);
+      mma_16816(o[2 * dp], a, bv[0], bv[1]);
+      if (2 * dp + 1 < DN) mma_16816(o[2 * dp + 1], a, bv[2], bv[3]);
     }
   }
-  const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
   const int r0 = q0 + g, r1 = q0 + g + 8;
 #pragma unroll
   for (int dn = 0; dn < DN; ++dn) {
@@ -119,8 +157,8 @@ __global__ void __launch_bounds__(NT * 16) attn_fwd_kernel(const __nv_bfloat16* 
     if (r1 < L) *reinterpret_cast<uint32_t*>(out + (size_t(b) * L + r1) * D + d) = pack_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1);
   }
   if (t == 0) {
-    if (r0 < L) lse[(size_t(b) * H + h) * L + r0] = m0 * scale + logf(sum0);
-    if (r1 < L) lse[(size_t(b) * H + h) * L + r1] = m1 * scale + logf(sum1);
+    if (r0 < L) lse[(size_t(b) * H + h) * L + r0] = M0 * scale + logf(l0);
+    if (r1 < L) lse[(size_t(b) * H + h) * L + r1] = M1 * scale + logf(l1);
   }
 }
 
@@ -130,110 +168,90 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
                                                            const __nv_bfloat16* __restrict__ dout,
                                                            const float* __restrict__ lse,
                                                            __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale) {
-  constexpr int Lp = NT * 8, LpP = Lp + 8, CH = HD / 8, DN = HD / 8;
+  constexpr int Lp = NT * 8, DN = HD / 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
   __nv_bfloat16* sK = sQ + Lp * ST;
   __nv_bfloat16* sV = sK + Lp * ST;
   __nv_bfloat16* sdO = sV + Lp * ST;
-  __nv_bfloat16* sQt = sdO + Lp * ST;  // [32][LpP]
-  __nv_bfloat16* sKt = sQt + 32 * LpP;
-  __nv_bfloat16* sdOt = sKt + 32 * LpP;
-  float* sLse = reinterpret_cast<float*>(sdOt + 32 * LpP);
+  float* sLse = reinterpret_cast<float*>(sdO + Lp * ST);  // pre-multiplied by log2(e)
   float* sDelta = sLse + Lp;
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int D = H * HD;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
-
-  for (int i = tid; i < Lp * 4; i += NT * 16) {  // Lp*4 == 2 * blockDim: every lane runs both iterations
+  const float l2e = 1.4426950408889634f;
+  {
+    const __nv_bfloat16* base = qkv + size_t(b) * L * 3 * D + h * HD;
+    const __nv_bfloat16* const src[4] = {base, base + D, base + 2 * D, dout + size_t(b) * L * D + h * HD};
+    const int ld[4] = {3 * D, 3 * D, 3 * D, D};
+    __nv_bfloat16* const dst[4] = {sQ, sK, sV, sdO};
+    load_tiles<4>(src, ld, dst, L, Lp, HD / 8, tid, NT * 16);
+  }
+  // delta[q] = sum_d dO[q,d] * O[q,d];  Lp*4 == 2 * blockDim, so every lane runs both iterations (full-warp shuffles)
+  for (int i = tid; i < Lp * 4; i += NT * 16) {
     const int r = i >> 2, c = i & 3;
-    uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q, d_o = q, oo = q;
-    if (r < L && c < CH) {
-      const __nv_bfloat16* base = qkv + (size_t(b) * L + r) * 3 * D + h * HD + c * 8;
-      q = *reinterpret_cast<const uint4*>(base);
-      k = *reinterpret_cast<const uint4*>(base + D);
-      v = *reinterpret_cast<const uint4*>(base + 2 * D);
-      const size_t ob = (size_t(b) * L + r) * D + h * HD + c * 8;
-      d_o = *reinterpret_cast<const uint4*>(dout + ob);
-      oo = *reinterpret_cast<const uint4*>(out + ob);
-    }
-    *reinterpret_cast<uint4*>(sQ + r * ST + c * 8) = q;
-    *reinterpret_cast<uint4*>(sK + r * ST + c * 8) = k;
-    *reinterpret_cast<uint4*>(sV + r * ST + c * 8) = v;
-    *reinterpret_cast<uint4*>(sdO + r * ST + c * 8) = d_o;
-    const __nv_bfloat16* qq = reinterpret_cast<const __nv_bfloat16*>(&q);
-    const __nv_bfloat16* kk2 = reinterpret_cast<const __nv_bfloat16*>(&k);
-    const __nv_bfloat16* dd = reinterpret_cast<const __nv_bfloat16*>(&d_o);
-    const __nv_bfloat16* op = reinterpret_cast<const __nv_bfloat16*>(&oo);
     float part = 0.f;
+    if (r < L && c < HD / 8) {
+      const size_t ob = (size_t(b) * L + r) * D + h * HD + c * 8;
+      const uint4 d_o = *reinterpret_cast<const uint4*>(dout + ob);
+      const uint4 oo = *reinterpret_cast<const uint4*>(out + ob);
+      const uint32_t dw[4] = {d_o.x, d_o.y, d_o.z, d_o.w}, ow[4] = {oo.x, oo.y, oo.z, oo.w};
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      sQt[(c * 8 + e) * LpP + r] = qq[e];
-      sKt[(c * 8 + e) * LpP + r] = kk2[e];
-      sdOt[(c * 8 + e) * LpP + r] = dd[e];
-      part += __bfloat162float(dd[e]) * __bfloat162float(op[e]);
+      for (int e = 0; e < 4; ++e) part += bf16_lo(dw[e]) * bf16_lo(ow[e]) + bf16_hi(dw[e]) * bf16_hi(ow[e]);
     }
     part += __shfl_xor_sync(0xffffffffu, part, 1);
     part += __shfl_xor_sync(0xffffffffu, part, 2);
     if (c == 0) {
       sDelta[r] = part;
-      sLse[r] = (r < L) ? lse[(size_t(b) * H + h) * L + r] : 0.f;
+      sLse[r] = (r < L) ? lse[(size_t(b) * H + h) * L + r] * l2e : 0.f;
     }
   }
   __syncthreads();
 
-  const float sl2 = scale * 1.4426950408889634f;
-  const float l2e = 1.4426950408889634f;
+  const float sl2 = scale * l2e;
   const int x0 = w * 16;  // first row of this warp's slab (queries in phase A, keys in phase B)
   const int r0 = x0 + g, r1 = x0 + g + 8;
 
   // ------------------------------ phase A: dQ ------------------------------
   {
     uint32_t aq[2][4], ado[2][4];
-    load_a_frag(aq[0], sQ, x0, 0, g, t);  load_a_frag(aq[1], sQ, x0, 16, g, t);
-    load_a_frag(ado[0], sdO, x0, 0, g, t); load_a_frag(ado[1], sdO, x0, 16, g, t);
-    float s[NT][4];
-    const float l0 = sLse[r0] * l2e, l1 = sLse[r1] * l2e;
+    frag_a(aq[0], sQ, x0, 0, lane);   frag_a(aq[1], sQ, x0, 16, lane);
+    frag_a(ado[0], sdO, x0, 0, lane); frag_a(ado[1], sdO, x0, 16, lane);
+    const float l0 = sLse[r0], l1 = sLse[r1], d0 = sDelta[r0], d1 = sDelta[r1];
+    float dq[4][4];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        const __nv_bfloat16* kr = sK + (nt * 8 + g) * ST + ks * 16 + t * 2;
-        mma_16816(s[nt], aq[ks], ld32(kr), ld32(kr + 8));
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int col = nt * 8 + t * 2 + (i & 1);
-        s[nt][i] = (col < L) ? exp2f(s[nt][i] * sl2 - (i < 2 ? l0 : l1)) : 0.f;
-      }
-    }
-    const float d0 = sDelta[r0], d1 = sDelta[r1];
-    float dq[DN][4];
-#pragma unroll
-    for (int dn = 0; dn < DN; ++dn) dq[dn][0] = dq[dn][1] = dq[dn][2] = dq[dn][3] = 0.f;
-#pragma unroll
+    for (int dn = 0; dn < 4; ++dn) dq[dn][0] = dq[dn][1] = dq[dn][2] = dq[dn][3] = 0.f;
+#pragma unroll 2
     for (int kk = 0; kk < NT / 2; ++kk) {
-      float dp[2][4];
+      float ds[2][4];
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        dp[hf][0] = dp[hf][1] = dp[hf][2] = dp[hf][3] = 0.f;
         const int nt = 2 * kk + hf;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const __nv_bfloat16* vr = sV + (nt * 8 + g) * ST + ks * 16 + t * 2;
-          mma_16816(dp[hf], ado[ks], ld32(vr), ld32(vr + 8));
+        uint32_t bk[4], bv[4];
+        frag_b_rows(bk, sK, nt * 8, lane);
+        frag_b_rows(bv, sV, nt * 8, lane);
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_16816(s, aq[0], bk[0], bk[1]);   mma_16816(s, aq[1], bk[2], bk[3]);
+        mma_16816(dp, ado[0], bv[0], bv[1]); mma_16816(dp, ado[1], bv[2], bv[3]);
+        float p0 = exp2f(s[0] * sl2 - l0), p1 = exp2f(s[1] * sl2 - l0);
+        float p2 = exp2f(s[2] * sl2 - l1), p3 = exp2f(s[3] * sl2 - l1);
+        if (nt * 8 + 8 > L) {  // warp-uniform: only the tail tiles hold padded keys (s = 0 there, exp(-lse) may overflow)
+          const int c = nt * 8 + t * 2;
+          if (c >= L) { p0 = 0.f; p2 = 0.f; }
+          if (c + 1 >= L) { p1 = 0.f; p3 = 0.f; }
         }
-        dp[hf][0] = s[nt][0] * (dp[hf][0] - d0); dp[hf][1] = s[nt][1] * (dp[hf][1] - d0);
-        dp[hf][2] = s[nt][2] * (dp[hf][2] - d1); dp[hf][3] = s[nt][3] * (dp[hf][3] - d1);
+        ds[hf][0] = p0 * (dp[0] - d0); ds[hf][1] = p1 * (dp[1] - d0);
+        ds[hf][2] = p2 * (dp[2] - d1); ds[hf][3] = p3 * (dp[3] - d1);
       }
       uint32_t a[4];
-      a[0] = pack_bf16x2(dp[0][0], dp[0][1]); a[1] = pack_bf16x2(dp[0][2], dp[0][3]);
-      a[2] = pack_bf16x2(dp[1][0], dp[1][1]); a[3] = pack_bf16x2(dp[1][2], dp[1][3]);
+      a[0] = pack_bf16x2(ds[0][0], ds[0][1]); a[1] = pack_bf16x2(ds[0][2], ds[0][3]);
+      a[2] = pack_bf16x2(ds[1][0], ds[1][1]); a[3] = pack_bf16x2(ds[1][2], ds[1][3]);
 #pragma unroll
-      for (int dn = 0; dn < DN; ++dn) {
-        const __nv_bfloat16* kr = sKt + (dn * 8 + g) * LpP + kk * 16 + t * 2;
-        mma_16816(dq[dn], a, ld32(kr), ld32(kr + 8));
+      for (int dp2 = 0; dp2 < 2; ++dp2) {
+        uint32_t kt[4];
+        frag_b_cols(kt, sK, kk * 16, dp2 * 16, lane);
+        mma_16816(dq[2 * dp2], a, kt[0], kt[1]);
+        if (2 * dp2 + 1 < DN) mma_16816(dq[2 * dp2 + 1], a, kt[2], kt[3]);
       }
     }
 #pragma unroll
@@ -247,68 +265,66 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
   // ------------------------------ phase B: dK, dV ------------------------------
   {
     uint32_t ak[2][4], av[2][4];
-    load_a_frag(ak[0], sK, x0, 0, g, t); load_a_frag(ak[1], sK, x0, 16, g, t);
-    load_a_frag(av[0], sV, x0, 0, g, t); load_a_frag(av[1], sV, x0, 16, g, t);
-    float s[NT][4];
+    frag_a(ak[0], sK, x0, 0, lane); frag_a(ak[1], sK, x0, 16, lane);
+    frag_a(av[0], sV, x0, 0, lane); frag_a(av[1], sV, x0, 16, lane);
+    float dk[4][4], dv[4][4];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        const __nv_bfloat16* qr = sQ + (nt * 8 + g) * ST + ks * 16 + t * 2;
-        mma_16816(s[nt], ak[ks], ld32(qr), ld32(qr + 8));
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int qc = nt * 8 + t * 2 + (i & 1);
-        const int kr = (i < 2) ? r0 : r1;
-        s[nt][i] = (qc < L && kr < L) ? exp2f(s[nt][i] * sl2 - sLse[qc] * l2e) : 0.f;
-      }
-    }
-    float dk[DN][4], dv[DN][4];
-#pragma unroll
-    for (int dn = 0; dn < DN; ++dn) {
+    for (int dn = 0; dn < 4; ++dn) {
       dk[dn][0] = dk[dn][1] = dk[dn][2] = dk[dn][3] = 0.f;
       dv[dn][0] = dv[dn][1] = dv[dn][2] = dv[dn][3] = 0.f;
     }
-#pragma unroll
+    const bool k0ok = r0 < L, k1ok = r1 < L;
+#pragma unroll 2
     for (int kk = 0; kk < NT / 2; ++kk) {
-      float ds[2][4];
+      float pt[2][4], ds[2][4];
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        ds[hf][0] = ds[hf][1] = ds[hf][2] = ds[hf][3] = 0.f;
         const int nt = 2 * kk + hf;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const __nv_bfloat16* dr = sdO + (nt * 8 + g) * ST + ks * 16 + t * 2;
-          mma_16816(ds[hf], av[ks], ld32(dr), ld32(dr + 8));
-        }
-        const float dl0 = sDelta[nt * 8 + t * 2], dl1 = sDelta[nt * 8 + t * 2 + 1];
-        ds[hf][0] = s[nt][0] * (ds[hf][0] - dl0); ds[hf][1] = s[nt][1] * (ds[hf][1] - dl1);
-        ds[hf][2] = s[nt][2] * (ds[hf][2] - dl0); ds[hf][3] = s[nt][3] * (ds[hf][3] - dl1);
+        uint32_t bq[4], bd[4];
+        frag_b_rows(bq, sQ, nt * 8, lane);
+        frag_b_rows(bd, sdO, nt * 8, lane);
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_16816(s, ak[0], bq[0], bq[1]);  mma_16816(s, ak[1], bq[2], bq[3]);
+        mma_16816(dp, av[0], bd[0], bd[1]); mma_16816(dp, av[1], bd[2], bd[3]);
+        // no masks needed: for query >= L the Q and dO rows are exactly zero (P^T there meets zero dO / Q rows,
+        // sLse/sDelta are 0), and key rows >= L only feed dK/dV rows that are never stored
+        const int c = nt * 8 + t * 2;  // query column
+        const float2 lq = *reinterpret_cast<const float2*>(sLse + c), dl = *reinterpret_cast<const float2*>(sDelta + c);
+        const float lq0 = lq.x, lq1 = lq.y, dl0 = dl.x, dl1 = dl.y;
+        pt[hf][0] = exp2f(s[0] * sl2 - lq0);
+        pt[hf][1] = exp2f(s[1] * sl2 - lq1);
+        pt[hf][2] = exp2f(s[2] * sl2 - lq0);
+        pt[hf][3] = exp2f(s[3] * sl2 - lq1);
+        ds[hf][0] = pt[hf][0] * (dp[0] - dl0); ds[hf][1] = pt[hf][1] * (dp[1] - dl1);
+        ds[hf][2] = pt[hf][2] * (dp[2] - dl0); ds[hf][3] = pt[hf][3] * (dp[3] - dl1);
       }
       uint32_t ap[4], as_[4];
-      ap[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);         ap[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
-      ap[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]); ap[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      ap[0] = pack_bf16x2(pt[0][0], pt[0][1]); ap[1] = pack_bf16x2(pt[0][2], pt[0][3]);
+      ap[2] = pack_bf16x2(pt[1][0], pt[1][1]); ap[3] = pack_bf16x2(pt[1][2], pt[1][3]);
       as_[0] = pack_bf16x2(ds[0][0], ds[0][1]); as_[1] = pack_bf16x2(ds[0][2], ds[0][3]);
       as_[2] = pack_bf16x2(ds[1][0], ds[1][1]); as_[3] = pack_bf16x2(ds[1][2], ds[1][3]);
 #pragma unroll
-      for (int dn = 0; dn < DN; ++dn) {
-        const __nv_bfloat16* dor = sdOt + (dn * 8 + g) * LpP + kk * 16 + t * 2;
-        mma_16816(dv[dn], ap, ld32(dor), ld32(dor + 8));
-        const __nv_bfloat16* qr = sQt + (dn * 8 + g) * LpP + kk * 16 + t * 2;
-        mma_16816(dk[dn], as_, ld32(qr), ld32(qr + 8));
+      for (int dp2 = 0; dp2 < 2; ++dp2) {
+        uint32_t dot[4], qt[4];
+        frag_b_cols(dot, sdO, kk * 16, dp2 * 16, lane);
+        frag_b_cols(qt, sQ, kk * 16, dp2 * 16, lane);
+        mma_16816(dv[2 * dp2], ap, dot[0], dot[1]);
+        mma_16816(dk[2 * dp2], as_, qt[0], qt[1]);
+        if (2 * dp2 + 1 < DN) {
+          mma_16816(dv[2 * dp2 + 1], ap, dot[2], dot[3]);
+          mma_16816(dk[2 * dp2 + 1], as_, qt[2], qt[3]);
+        }
       }
     }
 #pragma unroll
     for (int dn = 0; dn < DN; ++dn) {
       const int d = h * HD + dn * 8 + t * 2;
-      if (r0 < L) {
+      if (k0ok) {
         __nv_bfloat16* base = dqkv + (size_t(b) * L + r0) * 3 * D + d;
         *reinterpret_cast<uint32_t*>(base + D) = pack_bf16x2(dk[dn][0] * scale, dk[dn][1] * scale);
         *reinterpret_cast<uint32_t*>(base + 2 * D) = pack_bf16x2(dv[dn][0], dv[dn][1]);
       }
-      if (r1 < L) {
+      if (k1ok) {
         __nv_bfloat16* base = dqkv + (size_t(b) * L + r1) * 3 * D + d;
         *reinterpret_cast<uint32_t*>(base + D) = pack_bf16x2(dk[dn][2] * scale, dk[dn][3] * scale);
         *reinterpret_cast<uint32_t*>(base + 2 * D) = pack_bf16x2(dv[dn][2], dv[dn][3]);
@@ -319,8 +335,8 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
 
 template <int HD, int NT>
 static int launch_fwd(const void* qkv, int B, int L, int H, void* out, float* lse, cudaStream_t st) {
-  constexpr int Lp = NT * 8, LpP = Lp + 8;
-  const size_t smem = size_t(2 * Lp * ST + 32 * LpP) * 2;
+  constexpr int Lp = NT * 8;
+  const size_t smem = size_t(3 * Lp * ST) * 2;
   static bool done = false;
   if (!done) {
     if (cudaFuncSetAttribute(attn_fwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
@@ -336,8 +352,8 @@ static int launch_fwd(const void* qkv, int B, int L, int H, void* out, float* ls
 template <int HD, int NT>
 static int launch_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int B, int L, int H,
                       void* dqkv, cudaStream_t st) {
-  constexpr int Lp = NT * 8, LpP = Lp + 8;
-  const size_t smem = size_t(4 * Lp * ST + 3 * 32 * LpP) * 2 + size_t(2 * Lp) * 4;
+  constexpr int Lp = NT * 8;
+  const size_t smem = size_t(4 * Lp * ST) * 2 + size_t(2 * Lp) * 4;
   static bool done = false;
   if (!done) {
     if (cudaFuncSetAttribute(attn_bwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)

@@ -558,7 +558,7 @@ extern "C" int mae_layernorm_bwd(const void* g, const float* x, const float* mea
   if (rows <= 0) return MAE_OK;
   if (!g || !x || !mean || !rstd || !gamma || !dx_out || !dgamma || !dbeta) return MAE_ERR_NULL;
   if (D > 256 || (D % 4) || (gather_idx && (n_sel <= 0 || L_src <= 0))) return MAE_ERR_SHAPE;
-  layernorm_bwd_kernel<<<grid_for(rows, 8, 148 * 4), 256, 0, stream>>>(
+  layernorm_bwd_kernel<<<grid_for(rows, 8, 148 * 8), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(g), x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out,
       reinterpret_cast<__nv_bfloat16*>(dx_out_bf16), dgamma, dbeta);
   return MAE_CHECK_LAUNCH();

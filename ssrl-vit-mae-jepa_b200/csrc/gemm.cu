@@ -3,8 +3,9 @@
 //   gemm_tn     C[M,N]  = epi( A[M,K] * B[N,K]^T )      forward linears and dgrads (both operands K-major)
 //   gemm_wgrad  O[P,Q] += sum_m  P[m,:]^T Q[m,:]        weight gradients (both operands MN-major)
 //
-// Shared structure: 6 warps.  warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer (one
-// lane), warps 2..5 = epilogue (TMEM -> registers -> global).  Operand tiles are staged by TMA with the
+// Shared structure: warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer (one lane), the
+// remaining warps = epilogue (TMEM -> registers -> global).  gemm_tn runs 16 epilogue warps: a warp may only
+// read the TMEM lane quarter (warp_id % 4), so the four warps of a quarter interleave the 16-column chunks.  Operand tiles are staged by TMA with the
 // 128-byte swizzle in a 4-deep mbarrier ring; accumulators live in TMEM (fp32), double buffered for
 // gemm_tn so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "mae_internal.h"
@@ -13,7 +14,9 @@
 namespace mae {
 
 static constexpr int kStages = 4;
-static constexpr int kGemmThreads = 192;
+static constexpr int kEpiGroups = 4;                               // epilogue warps per TMEM lane quarter
+static constexpr int kGemmThreads = 64 + 4 * kEpiGroups * 32;       // gemm_tn: TMA + MMA + 16 epilogue warps
+static constexpr int kWgradThreads = 192;                            // gemm_wgrad: TMA + MMA + 4 epilogue warps
 static constexpr int BM = 128;  // UMMA M
 static constexpr int BK = 64;   // one 128-byte swizzle span of bf16
 
@@ -72,6 +75,7 @@ struct GemmTnParams {
   int nchunks;  // N / bn
   int mtiles;   // ceil(M / 128)
   int nkb;      // ceil(K / 64)
+  int nstages;  // TMA ring depth (3 or 4, whatever fits next to the epilogue staging tiles)
   const float* bias;          // [N] or null
   void* out;                  // bf16 [M,N] (EPI 0,1,3,4)  or  f32 [M,N] (EPI 2)
   __nv_bfloat16* pre_out;     // EPI 1: bf16 [M,N] pre-activation
@@ -86,52 +90,155 @@ struct GemmSmemHdr {
   uint32_t tmem_base;
 };
 
-template <int EPI>
-__device__ __forceinline__ void epilogue16(const GemmTnParams& p, int row, int col, float (&v)[16]) {
-  if (p.bias != nullptr) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + col + i);
+// ---------------------------------------------------------------------------------------------
+// Epilogue.  An epilogue warp owns TMEM lanes [32q, 32q+32) = 32 output rows, one row per thread.  To keep
+// every global access a full 128-byte line, a warp works in units of 128 output bytes per row (64 bf16 or 32
+// fp32 columns): the row-per-thread values go through a private padded staging tile in shared memory and
+// leave (or, for aux inputs, arrive) with 8 lanes covering one row, i.e. 4 complete rows per instruction.
+// ---------------------------------------------------------------------------------------------
+static constexpr int kStgRow = 144;                 // 128 data bytes + 16 pad: conflict-free 16-byte accesses
+static constexpr int kStgBytes = 32 * kStgRow;      // per epilogue warp
+
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Coalesced move of a [32 rows x row_bytes] tile between global memory (row pitch gpitch bytes) and the staging
+// tile.  row_bytes is a multiple of 16 and <= 128.  Rows >= rows_valid are skipped.
+template <bool TO_GLOBAL>
+__device__ __forceinline__ void stg_copy(uint8_t* stg, uint8_t* gbase, size_t gpitch, int row_bytes, int rows_valid,
+                                         int lane) {
+  const int lpr = row_bytes >> 4;            // lanes per row (1..8)
+  const int rpi = 32 / lpr;                  // rows per instruction
+  const int rr = lane / lpr, ch = lane % lpr;
+  if (rr < rpi) {
+    for (int r0 = 0; r0 < 32; r0 += rpi) {
+      const int r = r0 + rr;
+      if (r < rows_valid && r < 32) {
+        uint4* sp = reinterpret_cast<uint4*>(stg + r * kStgRow + ch * 16);
+        uint4* gp = reinterpret_cast<uint4*>(gbase + size_t(r) * gpitch + ch * 16);
+        if (TO_GLOBAL) *gp = *sp; else *sp = *gp;
+      }
+    }
   }
-  const size_t off = size_t(row) * p.N + col;
-  if constexpr (EPI == MAE_EPI_BF16) {
-    uint4 o0, o1;
-    o0.x = pack_bf16x2(v[0], v[1]);  o0.y = pack_bf16x2(v[2], v[3]);
-    o0.z = pack_bf16x2(v[4], v[5]);  o0.w = pack_bf16x2(v[6], v[7]);
-    o1.x = pack_bf16x2(v[8], v[9]);  o1.y = pack_bf16x2(v[10], v[11]);
-    o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
-    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
-    dst[0] = o0; dst[1] = o1;
-  } else if constexpr (EPI == MAE_EPI_GELU_BF16) {
-    // autocast semantics: the linear's output is rounded to bf16, GELU reads that bf16 value
-    uint32_t pr[8], hr[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      pr[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-      hr[i] = pack_bf16x2(gelu_erf(bf16_lo(pr[i])), gelu_erf(bf16_hi(pr[i])));
+}
+
+// fp32 variant with the residual added on the way out: out = staged + resid
+__device__ __forceinline__ void stg_flush_add_f32(const uint8_t* stg, const uint8_t* rbase, uint8_t* obase,
+                                                  size_t gpitch, int row_bytes, int rows_valid, int lane) {
+  const int lpr = row_bytes >> 4, rpi = 32 / lpr;
+  const int rr = lane / lpr, ch = lane % lpr;
+  if (rr < rpi) {
+    for (int r0 = 0; r0 < 32; r0 += rpi) {
+      const int r = r0 + rr;
+      if (r < rows_valid && r < 32) {
+        const float4 a = *reinterpret_cast<const float4*>(stg + r * kStgRow + ch * 16);
+        const float4 x = *reinterpret_cast<const float4*>(rbase + size_t(r) * gpitch + ch * 16);
+        *reinterpret_cast<float4*>(obase + size_t(r) * gpitch + ch * 16) =
+            make_float4(a.x + x.x, a.y + x.y, a.z + x.z, a.w + x.w);
+      }
     }
-    uint4* d0 = reinterpret_cast<uint4*>(p.pre_out + off);
-    uint4* d1 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
-    d0[0] = make_uint4(pr[0], pr[1], pr[2], pr[3]); d0[1] = make_uint4(pr[4], pr[5], pr[6], pr[7]);
-    d1[0] = make_uint4(hr[0], hr[1], hr[2], hr[3]); d1[1] = make_uint4(hr[4], hr[5], hr[6], hr[7]);
-  } else if constexpr (EPI == MAE_EPI_RESID_F32) {
-    const float4* r = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.aux) + off);
-    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float4 x = r[i];
-      x.x += v[4 * i]; x.y += v[4 * i + 1]; x.z += v[4 * i + 2]; x.w += v[4 * i + 3];
-      dst[i] = x;
+  }
+}
+
+// One work item (128 x bn accumulator tile) for one epilogue warp.  row0 = first global row of this warp's 32.
+template <int EPI>
+__device__ __forceinline__ void epilogue_item(const GemmTnParams& p, uint32_t taddr, int row0, int col_base, int grp,
+                                              uint8_t* stg, int lane) {
+  constexpr bool F32 = (EPI == MAE_EPI_RESID_F32);
+  constexpr int UC = F32 ? 32 : 64;          // columns per 128-byte unit
+  constexpr int SB = F32 ? 64 : 32;          // bytes per 16-column sub-chunk
+  constexpr int ES = F32 ? 4 : 2;            // output element size
+  const int rows_valid = p.M - row0;         // may be <= 0 or > 32
+  const int units = (p.bn + UC - 1) / UC;
+  for (int u = grp; u < units; u += kEpiGroups) {
+    const int c0 = u * UC;
+    int nsub = (p.bn - c0) >> 4;
+    if (nsub > UC / 16) nsub = UC / 16;
+    const int row_bytes = nsub * SB;
+    const int gcol = col_base + c0;
+    const size_t gpitch = size_t(p.N) * ES;
+    if constexpr (EPI == MAE_EPI_DGELU_BF16) {  // bring the pre-activation tile in, coalesced
+      uint8_t* abase = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(p.aux)) + (size_t(row0) * p.N + gcol) * 2;
+      stg_copy<false>(stg, abase, gpitch, row_bytes, rows_valid, lane);
+      __syncwarp();
     }
-  } else if constexpr (EPI == MAE_EPI_DGELU_BF16) {
-    const uint4* pp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux) + off);
-    uint4 a = pp[0], b = pp[1];
-    const uint32_t pr[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    uint32_t o[8];
+    uint32_t hkeep[UC / 16][8];  // EPI_GELU: second output (h) parked in registers while `pre` is flushed
+    for (int sidx = 0; sidx < nsub; ++sidx) {
+      uint32_t raw[16];
+      tmem_ld16_issue(taddr + c0 + sidx * 16, raw);
+      float bia[16];
+      if (p.bias != nullptr) {
+        const float4* bp = reinterpret_cast<const float4*>(p.bias + gcol + sidx * 16);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      o[i] = pack_bf16x2(v[2 * i] * gelu_erf_grad(bf16_lo(pr[i])), v[2 * i + 1] * gelu_erf_grad(bf16_hi(pr[i])));
-    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off);
-    dst[0] = make_uint4(o[0], o[1], o[2], o[3]); dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        for (int i = 0; i < 4; ++i) {
+          const float4 t4 = __ldg(bp + i);
+          bia[4 * i] = t4.x; bia[4 * i + 1] = t4.y; bia[4 * i + 2] = t4.z; bia[4 * i + 3] = t4.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bia[i] = 0.f;
+      }
+      uint8_t* my = stg + lane * kStgRow + sidx * SB;
+      uint32_t pr[8];
+      if constexpr (EPI == MAE_EPI_DGELU_BF16) {
+        const uint4 a = *reinterpret_cast<const uint4*>(my), b = *reinterpret_cast<const uint4*>(my + 16);
+        pr[0] = a.x; pr[1] = a.y; pr[2] = a.z; pr[3] = a.w; pr[4] = b.x; pr[5] = b.y; pr[6] = b.z; pr[7] = b.w;
+      }
+      tmem_ld_wait();
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) + bia[i];
+      if constexpr (F32) {
+        float4* d = reinterpret_cast<float4*>(my);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      } else {
+        uint32_t o[8];
+        if constexpr (EPI == MAE_EPI_BF16) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        } else if constexpr (EPI == MAE_EPI_GELU_BF16) {
+          // autocast semantics: the linear's output is rounded to bf16, GELU reads that bf16 value
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            hkeep[sidx][i] = pack_bf16x2(gelu_fast(bf16_lo(o[i])), gelu_fast(bf16_hi(o[i])));
+          }
+        } else {  // DGELU
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            o[i] = pack_bf16x2(v[2 * i] * gelu_fast_grad(bf16_lo(pr[i])), v[2 * i + 1] * gelu_fast_grad(bf16_hi(pr[i])));
+        }
+        uint4* d = reinterpret_cast<uint4*>(my);
+        d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+    }
+    __syncwarp();
+    const size_t goff = (size_t(row0) * p.N + gcol) * ES;
+    if constexpr (F32) {
+      stg_flush_add_f32(stg, reinterpret_cast<const uint8_t*>(p.aux) + goff, reinterpret_cast<uint8_t*>(p.out) + goff,
+                        gpitch, row_bytes, rows_valid, lane);
+    } else if constexpr (EPI == MAE_EPI_GELU_BF16) {
+      stg_copy<true>(stg, reinterpret_cast<uint8_t*>(p.pre_out) + goff, gpitch, row_bytes, rows_valid, lane);
+      __syncwarp();
+      for (int sidx = 0; sidx < nsub; ++sidx) {
+        uint4* d = reinterpret_cast<uint4*>(stg + lane * kStgRow + sidx * SB);
+        d[0] = make_uint4(hkeep[sidx][0], hkeep[sidx][1], hkeep[sidx][2], hkeep[sidx][3]);
+        d[1] = make_uint4(hkeep[sidx][4], hkeep[sidx][5], hkeep[sidx][6], hkeep[sidx][7]);
+      }
+      __syncwarp();
+      stg_copy<true>(stg, reinterpret_cast<uint8_t*>(p.out) + goff, gpitch, row_bytes, rows_valid, lane);
+    } else {
+      stg_copy<true>(stg, reinterpret_cast<uint8_t*>(p.out) + goff, gpitch, row_bytes, rows_valid, lane);
+    }
+    __syncwarp();
   }
 }
 
@@ -144,7 +251,9 @@ gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, c
   const uint32_t a_bytes = BM * BK * 2;             // 16 KB
   const uint32_t b_bytes = uint32_t(p.bn) * BK * 2;  // bn rows x 128 B
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  GemmSmemHdr* hdr = reinterpret_cast<GemmSmemHdr*>(smem + kStages * stage_bytes);
+  const int nst = p.nstages;
+  uint8_t* stg_all = smem + nst * stage_bytes;
+  GemmSmemHdr* hdr = reinterpret_cast<GemmSmemHdr*>(stg_all + 4 * kEpiGroups * kStgBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -153,8 +262,8 @@ gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
-    for (int s = 0; s < kStages; ++s) { mbar_init(&hdr->full[s], 1); mbar_init(&hdr->empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&hdr->tfull[a], 1); mbar_init(&hdr->tempty[a], 4); }
+    for (int s = 0; s < nst; ++s) { mbar_init(&hdr->full[s], 1); mbar_init(&hdr->empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&hdr->tfull[a], 1); mbar_init(&hdr->tempty[a], 4 * kEpiGroups); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(&hdr->tmem_base, 512);
@@ -174,7 +283,7 @@ gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, c
           mbar_expect_tx(&hdr->full[stage], stage_bytes);
           tma_load_2d(sa, &mapA, &hdr->full[stage], kb * BK, mt * BM);
           tma_load_2d(sa + a_bytes, &mapB, &hdr->full[stage], kb * BK, nc * p.bn);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -200,26 +309,23 @@ gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, c
             umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
           }
           umma_commit(&hdr->empty[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
         }
         umma_commit(&hdr->tfull[acc]);
         acc ^= 1; if (acc == 0) accphase ^= 1;
       }
     }
   } else {
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;  // which of the quarter's kEpiGroups warps: takes units grp, grp+4, ...
+    uint8_t* stg = stg_all + (warp - 2) * kStgBytes;
     int acc = 0; uint32_t accphase = 0;
     for (int item = blockIdx.x; item < total; item += gridDim.x) {
       const int mt = item / p.nchunks, nc = item % p.nchunks;
       mbar_wait(&hdr->tfull[acc], accphase);
       tc_fence_after();
-      const int row = mt * BM + q * 32 + lane;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc) * 256u;
-      for (int c0 = 0; c0 < p.bn; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + c0, v);
-        if (row < p.M) epilogue16<EPI>(p, row, nc * p.bn + c0, v);
-      }
+      epilogue_item<EPI>(p, taddr, mt * BM + q * 32, nc * p.bn, grp, stg, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&hdr->tempty[acc]);
@@ -239,7 +345,8 @@ static int pick_bn(int N) {
 
 template <int EPI>
 static int launch_gemm_tn(const GemmTnParams& p, const CUtensorMap& ma, const CUtensorMap& mb, cudaStream_t st) {
-  const size_t smem = size_t(kStages) * (BM * BK * 2 + p.bn * BK * 2) + sizeof(GemmSmemHdr) + 1024;
+  const size_t smem = size_t(p.nstages) * (BM * BK * 2 + p.bn * BK * 2) + 4 * kEpiGroups * kStgBytes +
+                      sizeof(GemmSmemHdr) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -267,6 +374,11 @@ extern "C" int mae_gemm_tn(const void* A, const void* B, int M, int N, int K, in
   p.nchunks = N / p.bn;
   p.mtiles = (M + BM - 1) / BM;
   p.nkb = (K + BK - 1) / BK;
+  {
+    const size_t fixed = 4 * kEpiGroups * kStgBytes + sizeof(GemmSmemHdr) + 1024;
+    const size_t per_stage = BM * BK * 2 + size_t(p.bn) * BK * 2;
+    p.nstages = (fixed + 4 * per_stage <= 227 * 1024) ? 4 : 3;
+  }
   p.bias = bias; p.out = out; p.pre_out = reinterpret_cast<__nv_bfloat16*>(pre_out); p.aux = aux;
   if (!A || !B || !out) return MAE_ERR_NULL;
   if (epi == MAE_EPI_GELU_BF16 && !pre_out) return MAE_ERR_NULL;
@@ -301,9 +413,17 @@ struct WgradParams {
   int rows_per_cta; // multiple of WR
   float* out;
   long long so_p, so_q;
+  float* colsum;    // optional: += column sums of P (colsum_of_q == 0) or of Q (== 1): the bias gradient
+  int colsum_of_q;
 };
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// bf16 element (row r, col c) of a [64 rows x 64 cols] TMA box written with the 128-byte swizzle
+__device__ __forceinline__ float swz_box_elem(const uint8_t* box, int r, int c) {
+  const uint32_t off = uint32_t(r) * 128u + ((uint32_t(c >> 3) ^ uint32_t(r & 7)) << 4) + uint32_t(c & 7) * 2u;
+  return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(box + off));
+}
+
+__global__ void __launch_bounds__(kWgradThreads, 1)
 gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapQ) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -324,7 +444,8 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapP);
     tma_prefetch_desc(&mapQ);
-    for (int s = 0; s < kStages; ++s) { mbar_init(&hdr->full[s], 1); mbar_init(&hdr->empty[s], 1); }
+    // a stage is released by the MMA commit and, when column sums are fused, by the 4 epilogue warps too
+    for (int s = 0; s < kStages; ++s) { mbar_init(&hdr->full[s], 1); mbar_init(&hdr->empty[s], p.colsum ? 5 : 1); }
     mbar_init(&hdr->tfull[0], 1);
     fence_mbar_init();
   }
@@ -373,6 +494,63 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
       }
     } else {
       const int q = warp & 3;
+      if (p.colsum != nullptr) {
+        // The epilogue warps are idle during the main loop: they add up the columns of the staged dY tile
+        // (bias gradient) straight from shared memory, so dY is read from HBM exactly once.
+        // Thread t of 128: box (t>>6), 16-byte column chunk cc = t&7, row group rg = (t>>3)&7 -> rows rg+8i.
+        // Within a 128B-swizzled box the chunk of row r sits at (cc ^ (r&7)) = (cc ^ rg): constant per thread.
+        const int t = (warp - 2) * 32 + lane;
+        const bool of_q = p.colsum_of_q != 0;
+        const bool active = !of_q || blockIdx.x == 0;
+        const int nbox = of_q ? p.nqb : 2;
+        const uint32_t tile_off = of_q ? p_bytes : 0u;
+        const int cc = t & 7, rg = (t >> 3) & 7;
+        const uint32_t thr_off = uint32_t(rg) * 128u + (uint32_t(cc ^ rg) << 4);
+        float acc[2][8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
+        int stage = 0; uint32_t phase = 0;
+        for (int mb = 0; mb < nmb; ++mb) {
+          mbar_wait(&hdr->full[stage], phase);
+          if (active) {
+            const uint8_t* sp = smem + stage * stage_bytes + tile_off;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int box = (t >> 6) + 2 * j;
+              if (box < nbox) {
+                const uint8_t* bp = sp + box * box_bytes + thr_off;
+#pragma unroll
+                for (int i = 0; i < WR / 8; ++i) {
+                  const uint4 v = *reinterpret_cast<const uint4*>(bp + i * 1024);
+                  acc[j][0] += bf16_lo(v.x); acc[j][1] += bf16_hi(v.x); acc[j][2] += bf16_lo(v.y); acc[j][3] += bf16_hi(v.y);
+                  acc[j][4] += bf16_lo(v.z); acc[j][5] += bf16_hi(v.z); acc[j][6] += bf16_lo(v.w); acc[j][7] += bf16_hi(v.w);
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&hdr->empty[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (active) {
+          const int col_base = of_q ? 0 : pc * 128;
+          const int ncols = of_q ? p.Qc : p.Pc;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int box = (t >> 6) + 2 * j;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float v = acc[j][e];
+              v += __shfl_xor_sync(0xffffffffu, v, 8);   // lanes differing in rg bits 0,1
+              v += __shfl_xor_sync(0xffffffffu, v, 16);
+              const int c = col_base + box * 64 + cc * 8 + e;
+              if ((lane >> 3) == 0 && box < nbox && c < ncols) atomicAdd(p.colsum + c, v);
+            }
+          }
+        }
+      }
       mbar_wait(&hdr->tfull[0], 0);
       tc_fence_after();
       const int prow = pc * 128 + q * 32 + lane;
@@ -396,7 +574,7 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
 }  // namespace mae
 
 extern "C" int mae_gemm_wgrad(const void* P, int Pc, const void* Q, int Qc, int M, float* out, long long so_p,
-                              long long so_q, cudaStream_t stream) {
+                              long long so_q, float* colsum, int colsum_of_q, cudaStream_t stream) {
   if (M <= 0) return MAE_OK;
   if (!P || !Q || !out) return MAE_ERR_NULL;
   if (Pc <= 0 || Qc <= 0 || Qc > 256 || (Qc % 16) || (Pc % 8)) return MAE_ERR_SHAPE;
@@ -404,6 +582,7 @@ extern "C" int mae_gemm_wgrad(const void* P, int Pc, const void* Q, int Qc, int 
   p.M = M; p.Pc = Pc; p.Qc = Qc;
   p.nqb = (Qc + 63) / 64;
   p.out = out; p.so_p = so_p; p.so_q = so_q;
+  p.colsum = colsum; p.colsum_of_q = colsum_of_q;
   const int pchunks = (Pc + 127) / 128;
   int msplit = num_sms() / pchunks;
   if (msplit < 1) msplit = 1;
@@ -423,6 +602,6 @@ extern "C" int mae_gemm_wgrad(const void* P, int Pc, const void* Q, int Qc, int 
       return MAE_ERR_LAUNCH;
     attr_done = true;
   }
-  gemm_wgrad_kernel<<<dim3(pchunks, msplit), kGemmThreads, smem, stream>>>(p, mp, mq);
+  gemm_wgrad_kernel<<<dim3(pchunks, msplit), kWgradThreads, smem, stream>>>(p, mp, mq);
   return cudaGetLastError() == cudaSuccess ? MAE_OK : MAE_ERR_LAUNCH;
 }

@@ -44,6 +44,40 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
+// Fast erf-GELU for bf16 outputs: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below a bf16 ulp),
+// one ex2 + one rcp instead of erff's long polynomial.  exp(-u^2) with u = x/sqrt(2) is shared with the pdf.
+__device__ __forceinline__ float rcp_approx(float x) {  // single MUFU.RCP, no IEEE fix-up / slow path
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {  // single MUFU.EX2
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& e) {
+  const float u = fabsf(x) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, u, 1.0f));
+  e = ex2_approx(u * u * -1.4426950408889634f);  // exp(-u^2)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * e;          // erf(|x|/sqrt2)
+  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float cdf, e;
+  gelu_parts(x, cdf, e);
+  return x * cdf;
+}
+__device__ __forceinline__ float gelu_fast_grad(float x) {
+  float cdf, e;
+  gelu_parts(x, cdf, e);
+  return fmaf(x * 0.3989422804014327f, e, cdf);
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier (shared::cta).  Waits are bounded: a wedged pipeline traps (-> CUDA launch error)
 // instead of hanging the GPU.

@@ -410,10 +410,9 @@ class MAEEngine:
     def _linear_bwd_w(self, dy: int, n_out: int, x: int, n_in: int, M: int, w_off: int, b_off: int, st: int) -> None:
         """dW (n_out, n_in) += dY^T X and db += colsum(dY).  The wider operand rides the MMA M axis."""
         if n_in <= 256 and n_in % 16 == 0:
-            calls.mae_gemm_wgrad(dy, n_out, x, n_in, M, self.pg(w_off), n_in, 1, st)
+            calls.mae_gemm_wgrad(dy, n_out, x, n_in, M, self.pg(w_off), n_in, 1, self.pg(b_off), 0, st)
         else:
-            calls.mae_gemm_wgrad(x, n_in, dy, n_out, M, self.pg(w_off), 1, n_in, st)
-        calls.mae_colsum_bf16(dy, M, n_out, self.pg(b_off), st)
+            calls.mae_gemm_wgrad(x, n_in, dy, n_out, M, self.pg(w_off), 1, n_in, self.pg(b_off), 1, st)
 
     def _block_bwd(self, w: _BlockW, s: Dict[str, torch.Tensor], dx: torch.Tensor, dxb: torch.Tensor,
                    dx_out: torch.Tensor, dxb_out: torch.Tensor, M: int, B: int, L: int, st: int) -> None:

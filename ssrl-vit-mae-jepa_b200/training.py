@@ -190,3 +190,52 @@ class FusedTrainer:
             eng.backward()
         eng.clip_adamw(self.current_lr(), weight_decay=self.module.weight_decay, max_norm=self.max_norm)
         return loss[0].clone()  # the workspace scalar is overwritten by the next step
+
+
+class DevicePrefetcher:
+    """Pinned-host -> device input pipeline: the H2D copy of batch i+1 runs on a side stream while step i
+    computes (two device staging buffers).  Iterating yields device tensors that stay valid until the next
+    ``next()``.  This is the piece of Lightning's batch transfer the hot path needs (reference
+    ``scripts/training/pretrain_mae.py:128`` -> ``trainer.fit`` moves each batch to the GPU before
+    ``training_step``), made asynchronous."""
+
+    def __init__(self, host_batches, device):
+        self.it = iter(host_batches)
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self.bufs: List[Optional[torch.Tensor]] = [None, None]
+        self.k = 0
+        self.ready: Optional[torch.cuda.Event] = None
+        self.cur: Optional[torch.Tensor] = None
+        self._preload()
+
+    def _preload(self) -> None:
+        try:
+            host = next(self.it)
+        except StopIteration:
+            self.nxt = None
+            return
+        if isinstance(host, (tuple, list)):
+            host = host[0]
+        slot = self.k % 2
+        self.k += 1
+        if self.bufs[slot] is None or self.bufs[slot].shape != host.shape:
+            self.bufs[slot] = torch.empty(host.shape, dtype=host.dtype, device=self.device)
+        # everything enqueued so far on the compute stream (incl. the step that last read this slot) goes first
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.bufs[slot].copy_(host, non_blocking=True)
+            self.ready = torch.cuda.Event()
+            self.ready.record(self.stream)
+        self.nxt = self.bufs[slot]
+
+    def __iter__(self):
+        return self
+
+    def __next__(self) -> torch.Tensor:
+        if self.nxt is None:
+            raise StopIteration
+        torch.cuda.current_stream(self.device).wait_event(self.ready)
+        self.cur = self.nxt
+        self._preload()
+        return self.cur

@@ -53,5 +53,6 @@ def gemm_tn(A, B, epi, bias=None, aux=None):
     return out, pre
 
 
-def gemm_wgrad(P, Q, out, so_p, so_q):
-    calls.mae_gemm_wgrad(p(P), P.shape[1], p(Q), Q.shape[1], P.shape[0], p(out), so_p, so_q, stream())
+def gemm_wgrad(P, Q, out, so_p, so_q, colsum=None, colsum_of_q=0):
+    calls.mae_gemm_wgrad(p(P), P.shape[1], p(Q), Q.shape[1], P.shape[0], p(out), so_p, so_q, p(colsum), colsum_of_q,
+                         stream())

@@ -189,9 +189,15 @@ def test_gemm_wgrad(M, Pc, Qc):
     e = rel_err(out, ref)
     report("gemm_wgrad", M=M, Pc=Pc, Qc=Qc, rel=e, max_err=max_err(out, ref))
     assert e < 1e-5  # exact bf16 products, fp32 accumulation
-    outT = torch.ones(Qc, Pc, device=dev)  # accumulate semantics + transposed strides
-    gemm_wgrad(P, Q, outT, 1, Pc)
+    outT = torch.ones(Qc, Pc, device=dev)  # accumulate semantics + transposed strides + fused bias gradient (of P)
+    cs = torch.zeros(Pc, device=dev)
+    gemm_wgrad(P, Q, outT, 1, Pc, cs, 0)
     assert rel_err(outT - 1, ref.t()) < 1e-5 + 1e-6 * M ** 0.5
+    assert max_err(cs, P.double().sum(0).float()) < 1e-3 * M ** 0.5
+    csq = torch.zeros(Qc, device=dev)  # ... and of Q
+    out2 = torch.zeros(Pc, Qc, device=dev)
+    gemm_wgrad(P, Q, out2, Qc, 1, csq, 1)
+    assert rel_err(out2, ref) < 1e-5 and max_err(csq, Q.double().sum(0).float()) < 1e-3 * M ** 0.5
 
 
 @pytest.mark.parametrize("B,L,H,hd", [(3, 36, 6, 24), (2, 145, 6, 32), (2, 145, 6, 24), (5, 17, 2, 32), (2, 73, 6, 24),
