@@ -391,17 +391,26 @@ __global__ void __launch_bounds__(256) gather_rows_bf16_kernel(const float* __re
 
 __global__ void __launch_bounds__(256) colsum_rows_f32_kernel(const float* __restrict__ src,
                                                              const int64_t* __restrict__ idx, int B, int n_sel,
-                                                             int L_src, int row_offset, int D, int rows_per_block,
+                                                             int L_src, int row_offset, int D,
                                                              float* __restrict__ out) {
-  const int d = threadIdx.x;
-  if (d >= D) return;
+  // one warp per row (grid-stride), lane owns columns {4*lane..} and {128+4*lane..}; block-level smem reduce
+  __shared__ float s_acc[256];
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int c0 = lane * 4, c1 = 128 + lane * 4;
+  const bool h0 = c0 < D, h1 = c1 < D;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
   const long long nrows = (long long)B * n_sel;
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
-  long long r1 = r0 + rows_per_block;
-  if (r1 > nrows) r1 = nrows;
-  float a = 0.f;
-  for (long long r = r0; r < r1; ++r) a += src[sel_row(r, idx, n_sel, L_src, row_offset) * D + d];
-  atomicAdd(out + d, a);
+  for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < nrows; r += (long long)gridDim.x * wpb) {
+    const float* row = src + sel_row(r, idx, n_sel, L_src, row_offset) * D;
+    if (h0) { const float4 v = *reinterpret_cast<const float4*>(row + c0); a0.x += v.x; a0.y += v.y; a0.z += v.z; a0.w += v.w; }
+    if (h1) { const float4 v = *reinterpret_cast<const float4*>(row + c1); a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w; }
+  }
+  if (h0) { atomicAdd(&s_acc[c0], a0.x); atomicAdd(&s_acc[c0 + 1], a0.y); atomicAdd(&s_acc[c0 + 2], a0.z); atomicAdd(&s_acc[c0 + 3], a0.w); }
+  if (h1) { atomicAdd(&s_acc[c1], a1.x); atomicAdd(&s_acc[c1 + 1], a1.y); atomicAdd(&s_acc[c1 + 2], a1.z); atomicAdd(&s_acc[c1 + 3], a1.w); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) atomicAdd(out + i, s_acc[i]);
 }
 
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
@@ -621,13 +630,9 @@ extern "C" int mae_colsum_rows_f32(const float* src, const int64_t* idx, int B, 
                                    int D, float* out, cudaStream_t stream) {
   if (B <= 0 || n_sel <= 0) return MAE_OK;
   if (!src || !out) return MAE_ERR_NULL;
-  if (D > 256) return MAE_ERR_SHAPE;
+  if (D > 256 || (D % 4)) return MAE_ERR_SHAPE;
   const long long nrows = (long long)B * n_sel;
-  int nb = 148 * 4;
-  long long rpb = (nrows + nb - 1) / nb;
-  if (rpb < 8) rpb = 8;
-  nb = int((nrows + rpb - 1) / rpb);
-  colsum_rows_f32_kernel<<<nb, 256, 0, stream>>>(src, idx, B, n_sel, L_src, row_offset, D, int(rpb), out);
+  colsum_rows_f32_kernel<<<grid_for(nrows, 8, 148 * 4), 256, 0, stream>>>(src, idx, B, n_sel, L_src, row_offset, D, out);
   return MAE_CHECK_LAUNCH();
 }
 

@@ -109,21 +109,36 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Coalesced move of a [32 rows x row_bytes] tile between global memory (row pitch gpitch bytes) and the staging
-// tile.  row_bytes is a multiple of 16 and <= 128.  Rows >= rows_valid are skipped.
+// tile.  row_bytes is a multiple of 16 and <= 128: (row_bytes/16) lanes cover one row, so one instruction moves
+// 32/(row_bytes/16) >= 4 complete rows.  Rows >= rows_valid are skipped.  All global loads of a tile are issued
+// before the first use (fixed 8-way unroll) so their latencies overlap instead of serialising.
 template <bool TO_GLOBAL>
 __device__ __forceinline__ void stg_copy(uint8_t* stg, uint8_t* gbase, size_t gpitch, int row_bytes, int rows_valid,
                                          int lane) {
   const int lpr = row_bytes >> 4;            // lanes per row (1..8)
-  const int rpi = 32 / lpr;                  // rows per instruction
+  const int rpi = 32 / lpr;                  // rows per instruction (>= 4)
   const int rr = lane / lpr, ch = lane % lpr;
-  if (rr < rpi) {
-    for (int r0 = 0; r0 < 32; r0 += rpi) {
-      const int r = r0 + rr;
-      if (r < rows_valid && r < 32) {
-        uint4* sp = reinterpret_cast<uint4*>(stg + r * kStgRow + ch * 16);
-        uint4* gp = reinterpret_cast<uint4*>(gbase + size_t(r) * gpitch + ch * 16);
-        if (TO_GLOBAL) *gp = *sp; else *sp = *gp;
-      }
+  const bool lane_ok = rr < rpi;
+  if (TO_GLOBAL) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * rpi + rr;
+      if (lane_ok && r < 32 && r < rows_valid)
+        *reinterpret_cast<uint4*>(gbase + size_t(r) * gpitch + ch * 16) =
+            *reinterpret_cast<const uint4*>(stg + r * kStgRow + ch * 16);
+    }
+  } else {
+    uint4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * rpi + rr;
+      v[i] = make_uint4(0, 0, 0, 0);
+      if (lane_ok && r < 32 && r < rows_valid) v[i] = *reinterpret_cast<const uint4*>(gbase + size_t(r) * gpitch + ch * 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * rpi + rr;
+      if (lane_ok && r < 32) *reinterpret_cast<uint4*>(stg + r * kStgRow + ch * 16) = v[i];
     }
   }
 }
@@ -133,15 +148,21 @@ __device__ __forceinline__ void stg_flush_add_f32(const uint8_t* stg, const uint
                                                   size_t gpitch, int row_bytes, int rows_valid, int lane) {
   const int lpr = row_bytes >> 4, rpi = 32 / lpr;
   const int rr = lane / lpr, ch = lane % lpr;
-  if (rr < rpi) {
-    for (int r0 = 0; r0 < 32; r0 += rpi) {
-      const int r = r0 + rr;
-      if (r < rows_valid && r < 32) {
-        const float4 a = *reinterpret_cast<const float4*>(stg + r * kStgRow + ch * 16);
-        const float4 x = *reinterpret_cast<const float4*>(rbase + size_t(r) * gpitch + ch * 16);
-        *reinterpret_cast<float4*>(obase + size_t(r) * gpitch + ch * 16) =
-            make_float4(a.x + x.x, a.y + x.y, a.z + x.z, a.w + x.w);
-      }
+  const bool lane_ok = rr < rpi;
+  float4 x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * rpi + rr;
+    x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane_ok && r < 32 && r < rows_valid) x[i] = *reinterpret_cast<const float4*>(rbase + size_t(r) * gpitch + ch * 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * rpi + rr;
+    if (lane_ok && r < 32 && r < rows_valid) {
+      const float4 a = *reinterpret_cast<const float4*>(stg + r * kStgRow + ch * 16);
+      *reinterpret_cast<float4*>(obase + size_t(r) * gpitch + ch * 16) =
+          make_float4(a.x + x[i].x, a.y + x[i].y, a.z + x[i].z, a.w + x[i].w);
     }
   }
 }

@@ -1,0 +1,12 @@
+#!/bin/bash
+# quick check: full gpu test-suite + bench summary
+TAG=${1:-q}
+timeout 900 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/t_all.log 2>&1; echo "tests rc=$?"; tail -n 4 gpurun_out/t_all.log
+timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/bench_$TAG.log 2>&1; echo "bench rc=$?"
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/bench_$TAG.log").read().strip().splitlines()[-1])
+print("img/s",round(d["value"]),"ms",round(d["ms_per_step"],3),"e2e",round(d["e2e"]["value"]))
+print({k.replace("mae_",""):v["ms"] for k,v in d["kernel_share"].items() if v["ms"]>0.03})
+print("gemm_tn TF",round(d["roofline"]["achieved"],1),d["extra"])
+PY
