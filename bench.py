@@ -156,10 +156,13 @@ def kernel_breakdown(trainer, images, noise, pk):
     for name in _lib.SIGNATURES:
         orig[name], t = wrap(name)
         setattr(lib_calls, name, t)
+    was_distributed = trainer.distributed
+    trainer.distributed = False  # rank-0-only diagnostic step: it must not enter a collective
     try:
         trainer.train_step(images, noise)
         torch.cuda.synchronize()
     finally:
+        trainer.distributed = was_distributed
         for name, fn in orig.items():
             setattr(lib_calls, name, fn)
     fam = {}
