@@ -64,6 +64,7 @@ template <int HD, int NT>
 __global__ void __launch_bounds__(NT * 16) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                            __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
                                                            int L, int H, float scale) {
+  pdl_trigger();
   constexpr int Lp = NT * 8, DN = HD / 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(NT * 16) attn_fwd_kernel(const __nv_bfloat16* 
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int D = H * HD;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+  pdl_wait();
   {
     const __nv_bfloat16* base = qkv + size_t(b) * L * 3 * D + h * HD;
     const __nv_bfloat16* const src[3] = {base, base + D, base + 2 * D};
@@ -168,6 +170,7 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
                                                            const __nv_bfloat16* __restrict__ dout,
                                                            const float* __restrict__ lse,
                                                            __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale) {
+  pdl_trigger();
   constexpr int Lp = NT * 8, DN = HD / 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
@@ -179,6 +182,7 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int D = H * HD;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+  pdl_wait();
   const float l2e = 1.4426950408889634f;
   {
     const __nv_bfloat16* base = qkv + size_t(b) * L * 3 * D + h * HD;
@@ -343,7 +347,7 @@ static int launch_fwd(const void* qkv, int B, int L, int H, void* out, float* ls
       return MAE_ERR_LAUNCH;
     done = true;
   }
-  attn_fwd_kernel<HD, NT><<<B * H, NT * 16, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+  mae_launch(attn_fwd_kernel<HD, NT>, dim3(B * H), dim3(NT * 16), smem, st, reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                         reinterpret_cast<__nv_bfloat16*>(out), lse, L, H,
                                                         1.0f / sqrtf(float(HD)));
   return MAE_CHECK_LAUNCH();
@@ -360,8 +364,7 @@ static int launch_bwd(const void* qkv, const void* out, const void* dout, const 
       return MAE_ERR_LAUNCH;
     done = true;
   }
-  attn_bwd_kernel<HD, NT><<<B * H, NT * 16, smem, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(out),
+  mae_launch(attn_bwd_kernel<HD, NT>, dim3(B * H), dim3(NT * 16), smem, st, reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(out),
       reinterpret_cast<const __nv_bfloat16*>(dout), lse, reinterpret_cast<__nv_bfloat16*>(dqkv), L, H,
       1.0f / sqrtf(float(HD)));
   return MAE_CHECK_LAUNCH();

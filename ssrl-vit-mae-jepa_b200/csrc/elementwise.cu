@@ -19,6 +19,8 @@ __device__ __forceinline__ uint32_t float_to_ordered(float x) {
 __global__ void __launch_bounds__(128) token_mask_kernel(const float* __restrict__ noise, int B, int L, int num_keep,
                                                         int64_t* __restrict__ idx_keep,
                                                         int64_t* __restrict__ idx_mask) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
   const int lane = threadIdx.x & 31;
@@ -80,6 +82,8 @@ __global__ void __launch_bounds__(256) gather_patches_kernel(const float* __rest
                                                             const int64_t* __restrict__ idx_keep, int B, int C,
                                                             int img, int patch, int num_keep,
                                                             __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int nk = num_keep - 1;
   const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= (long long)B * nk) return;
@@ -102,6 +106,8 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const __nv_bfloat1
                                                              const float* __restrict__ pos,
                                                              const int64_t* __restrict__ idx_keep, int B,
                                                              int num_keep, int D, float* __restrict__ x) {
+  pdl_trigger();
+  pdl_wait();
   const long long n = (long long)B * num_keep * D;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int d = int(i % D);
@@ -130,6 +136,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                            int L_src, int rows, int D, float eps,
                                                            __nv_bfloat16* __restrict__ xn, float* __restrict__ mean,
                                                            float* __restrict__ rstd) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int c0 = lane * 4, c1 = 128 + lane * 4;
@@ -170,6 +178,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dx_in,
     const int64_t* __restrict__ gather_idx, int n_sel, int L_src, int rows, int D, float* __restrict__ dx_out,
     __nv_bfloat16* __restrict__ dx_out_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_dg[256], s_db[256];
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -253,6 +263,8 @@ __global__ void __launch_bounds__(256) scatter_decoder_kernel(const __nv_bfloat1
                                                              const int64_t* __restrict__ idx_keep,
                                                              const int64_t* __restrict__ idx_mask, int B, int L,
                                                              int num_keep, int D, float* __restrict__ x_dec) {
+  pdl_trigger();
+  pdl_wait();
   const int D4 = D >> 2;
   const long long n = (long long)B * L * D4;
   const int n_mask = L - num_keep;
@@ -289,6 +301,8 @@ __global__ void __launch_bounds__(256) masked_mse_kernel(const __nv_bfloat16* __
                                                         float* __restrict__ partials,
                                                         __nv_bfloat16* __restrict__ dpred,
                                                         float* __restrict__ target) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_t[];  // per warp: patch_dim floats (target in (py,px,c) order)
   __shared__ float s_red[8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -339,6 +353,8 @@ __global__ void __launch_bounds__(256) masked_mse_kernel(const __nv_bfloat16* __
 
 __global__ void __launch_bounds__(256) finalize_loss_kernel(const float* __restrict__ partials, int n, float scale,
                                                            float* __restrict__ loss) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s[256];
   float t = 0.f;
   for (int i = threadIdx.x; i < n; i += 256) t += partials[i];
@@ -356,6 +372,8 @@ __global__ void __launch_bounds__(256) finalize_loss_kernel(const float* __restr
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int M, int N,
                                                          int rows_per_block, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int col = (blockIdx.y * 128 + threadIdx.x) * 2;
   if (col >= N) return;
   const int m0 = blockIdx.x * rows_per_block;
@@ -379,6 +397,8 @@ __global__ void __launch_bounds__(256) gather_rows_bf16_kernel(const float* __re
                                                               const int64_t* __restrict__ idx, int B, int n_sel,
                                                               int L_src, int row_offset, int D,
                                                               __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int D4 = D >> 2;
   const long long n = (long long)B * n_sel * D4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -393,6 +413,8 @@ __global__ void __launch_bounds__(256) colsum_rows_f32_kernel(const float* __res
                                                              const int64_t* __restrict__ idx, int B, int n_sel,
                                                              int L_src, int row_offset, int D,
                                                              float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   // one warp per row (grid-stride), lane owns columns {4*lane..} and {128+4*lane..}; block-level smem reduce
   __shared__ float s_acc[256];
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -415,6 +437,8 @@ __global__ void __launch_bounds__(256) colsum_rows_f32_kernel(const float* __res
 
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                        long long n) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = __float2bfloat16_rn(src[i]);
 }
@@ -422,6 +446,8 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __restrict__ src,
                                                             __nv_bfloat16* __restrict__ dst,
                                                             const long long* __restrict__ table) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][33];
   const long long* t = table + size_t(blockIdx.z) * 4;
   const long long src_off = t[0], dst_off = t[2 + 1];
@@ -445,6 +471,8 @@ __global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __rest
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) grad_sumsq_kernel(const float* __restrict__ g, long long n,
                                                         float* __restrict__ partials) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s[8];
   float t = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -468,6 +496,8 @@ __global__ void __launch_bounds__(256) clip_adamw_kernel(float* __restrict__ p, 
                                                         float inv_bc1, float inv_sqrt_bc2,
                                                         const float* __restrict__ partials, int n_partials,
                                                         float* __restrict__ grad_norm_out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s[256];
   // every block reduces the same partials in the same order -> identical, deterministic norm
   float t = 0.f;
@@ -525,7 +555,7 @@ extern "C" int mae_random_token_mask(const float* noise, int B, int L, int num_k
   if (B <= 0) return MAE_OK;
   if (!noise || !idx_keep || (!idx_mask && num_keep < L)) return MAE_ERR_NULL;
   if (L < 1 || L > 256 || num_keep < 1 || num_keep > L) return MAE_ERR_SHAPE;
-  token_mask_kernel<<<(B + 3) / 4, 128, 0, stream>>>(noise, B, L, num_keep, idx_keep, idx_mask);
+  mae_launch(token_mask_kernel, dim3((B + 3) / 4), dim3(128), 0, stream, noise, B, L, num_keep, idx_keep, idx_mask);
   return MAE_CHECK_LAUNCH();
 }
 
@@ -535,7 +565,7 @@ extern "C" int mae_gather_patches(const float* images, const int64_t* idx_keep, 
   if (!images || !idx_keep || !patches) return MAE_ERR_NULL;
   if (patch <= 0 || img % patch) return MAE_ERR_SHAPE;
   const long long warps = (long long)B * (num_keep - 1);
-  gather_patches_kernel<<<unsigned((warps + 7) / 8), 256, 0, stream>>>(images, idx_keep, B, C, img, patch, num_keep,
+  mae_launch(gather_patches_kernel, dim3(unsigned((warps + 7) / 8)), dim3(256), 0, stream, images, idx_keep, B, C, img, patch, num_keep,
                                                                        reinterpret_cast<__nv_bfloat16*>(patches));
   return MAE_CHECK_LAUNCH();
 }
@@ -544,8 +574,7 @@ extern "C" int mae_assemble_tokens(const void* tok, const float* cls, const floa
                                    int num_keep, int D, float* x, cudaStream_t stream) {
   if (B <= 0) return MAE_OK;
   if (!tok || !cls || !pos || !idx_keep || !x) return MAE_ERR_NULL;
-  assemble_tokens_kernel<<<grid_for((long long)B * num_keep * D, 256), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(tok), cls, pos, idx_keep, B, num_keep, D, x);
+  mae_launch(assemble_tokens_kernel, dim3(grid_for((long long)B * num_keep * D, 256)), dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(tok), cls, pos, idx_keep, B, num_keep, D, x);
   return MAE_CHECK_LAUNCH();
 }
 
@@ -555,7 +584,7 @@ extern "C" int mae_layernorm_fwd(const float* x, const float* gamma, const float
   if (rows <= 0) return MAE_OK;
   if (!x || !gamma || !beta || !xn || !mean || !rstd) return MAE_ERR_NULL;
   if (D > 256 || (D % 4) || (gather_idx && (n_sel <= 0 || L_src <= 0))) return MAE_ERR_SHAPE;
-  layernorm_fwd_kernel<<<grid_for(rows, 8), 256, 0, stream>>>(x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps,
+  mae_launch(layernorm_fwd_kernel, dim3(grid_for(rows, 8)), dim3(256), 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps,
                                                              reinterpret_cast<__nv_bfloat16*>(xn), mean, rstd);
   return MAE_CHECK_LAUNCH();
 }
@@ -567,8 +596,7 @@ extern "C" int mae_layernorm_bwd(const void* g, const float* x, const float* mea
   if (rows <= 0) return MAE_OK;
   if (!g || !x || !mean || !rstd || !gamma || !dx_out || !dgamma || !dbeta) return MAE_ERR_NULL;
   if (D > 256 || (D % 4) || (gather_idx && (n_sel <= 0 || L_src <= 0))) return MAE_ERR_SHAPE;
-  layernorm_bwd_kernel<<<grid_for(rows, 8, 148 * 8), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(g), x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out,
+  mae_launch(layernorm_bwd_kernel, dim3(grid_for(rows, 8, 148 * 8)), dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(g), x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out,
       reinterpret_cast<__nv_bfloat16*>(dx_out_bf16), dgamma, dbeta);
   return MAE_CHECK_LAUNCH();
 }
@@ -579,8 +607,7 @@ extern "C" int mae_scatter_decoder_tokens(const void* emb, const float* mask_tok
   if (B <= 0) return MAE_OK;
   if (!emb || !mask_token || !dec_pos || !idx_keep || !idx_mask || !x_dec) return MAE_ERR_NULL;
   if (D % 4 || num_keep < 1 || num_keep > L) return MAE_ERR_SHAPE;
-  scatter_decoder_kernel<<<grid_for((long long)B * L * (D / 4), 256), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(emb), mask_token, dec_pos, idx_keep, idx_mask, B, L, num_keep, D, x_dec);
+  mae_launch(scatter_decoder_kernel, dim3(grid_for((long long)B * L * (D / 4), 256)), dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(emb), mask_token, dec_pos, idx_keep, idx_mask, B, L, num_keep, D, x_dec);
   return MAE_CHECK_LAUNCH();
 }
 
@@ -595,11 +622,10 @@ extern "C" int mae_masked_mse(const void* pred, const float* images, const int64
   int grid = int((nrows + 7) / 8);
   if (grid > kMsePartials) grid = kMsePartials;
   const float inv_numel = 1.0f / (float(nrows) * float(pd));
-  masked_mse_kernel<<<grid, 256, 8 * pd * sizeof(float), stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(pred), images, idx_mask, B, C, img, patch, n_mask, norm_pix, inv_numel,
+  mae_launch(masked_mse_kernel, dim3(grid), dim3(256), 8 * pd * sizeof(float), stream, reinterpret_cast<const __nv_bfloat16*>(pred), images, idx_mask, B, C, img, patch, n_mask, norm_pix, inv_numel,
       partials, reinterpret_cast<__nv_bfloat16*>(dpred), target);
   if (cudaGetLastError() != cudaSuccess) return MAE_ERR_LAUNCH;
-  finalize_loss_kernel<<<1, 256, 0, stream>>>(partials, grid, inv_numel, loss);
+  mae_launch(finalize_loss_kernel, dim3(1), dim3(256), 0, stream, partials, grid, inv_numel, loss);
   return MAE_CHECK_LAUNCH();
 }
 
@@ -612,7 +638,7 @@ extern "C" int mae_colsum_bf16(const void* x, int M, int N, float* out, cudaStre
   int rpb = (M + nx - 1) / nx;
   if (rpb < 16) rpb = 16;
   nx = (M + rpb - 1) / rpb;
-  colsum_bf16_kernel<<<dim3(nx, ny), 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), M, N, rpb, out);
+  mae_launch(colsum_bf16_kernel, dim3(dim3(nx, ny)), dim3(128), 0, stream, reinterpret_cast<const __nv_bfloat16*>(x), M, N, rpb, out);
   return MAE_CHECK_LAUNCH();
 }
 
@@ -621,8 +647,7 @@ extern "C" int mae_gather_rows_bf16(const float* src, const int64_t* idx, int B,
   if (B <= 0 || n_sel <= 0) return MAE_OK;
   if (!src || !out) return MAE_ERR_NULL;
   if (D % 4) return MAE_ERR_SHAPE;
-  gather_rows_bf16_kernel<<<grid_for((long long)B * n_sel * (D / 4), 256), 256, 0, stream>>>(
-      src, idx, B, n_sel, L_src, row_offset, D, reinterpret_cast<__nv_bfloat16*>(out));
+  mae_launch(gather_rows_bf16_kernel, dim3(grid_for((long long)B * n_sel * (D / 4), 256)), dim3(256), 0, stream, src, idx, B, n_sel, L_src, row_offset, D, reinterpret_cast<__nv_bfloat16*>(out));
   return MAE_CHECK_LAUNCH();
 }
 
@@ -632,14 +657,14 @@ extern "C" int mae_colsum_rows_f32(const float* src, const int64_t* idx, int B, 
   if (!src || !out) return MAE_ERR_NULL;
   if (D > 256 || (D % 4)) return MAE_ERR_SHAPE;
   const long long nrows = (long long)B * n_sel;
-  colsum_rows_f32_kernel<<<grid_for(nrows, 8, 148 * 4), 256, 0, stream>>>(src, idx, B, n_sel, L_src, row_offset, D, out);
+  mae_launch(colsum_rows_f32_kernel, dim3(grid_for(nrows, 8, 148 * 4)), dim3(256), 0, stream, src, idx, B, n_sel, L_src, row_offset, D, out);
   return MAE_CHECK_LAUNCH();
 }
 
 extern "C" int mae_cast_bf16(const float* src, void* dst, long long n, cudaStream_t stream) {
   if (n <= 0) return MAE_OK;
   if (!src || !dst) return MAE_ERR_NULL;
-  cast_bf16_kernel<<<grid_for(n, 256), 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  mae_launch(cast_bf16_kernel, dim3(grid_for(n, 256)), dim3(256), 0, stream, src, reinterpret_cast<__nv_bfloat16*>(dst), n);
   return MAE_CHECK_LAUNCH();
 }
 
@@ -648,14 +673,14 @@ extern "C" int mae_transpose_cast_bf16(const float* src, void* dst, const long l
   if (n_entries <= 0) return MAE_OK;
   if (!src || !dst || !table) return MAE_ERR_NULL;
   // grid covers the largest weight (<= 1024 x 1024); smaller entries exit early
-  transpose_cast_kernel<<<dim3(32, 32, n_entries), 256, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), table);
+  mae_launch(transpose_cast_kernel, dim3(dim3(32, 32, n_entries)), dim3(256), 0, stream, src, reinterpret_cast<__nv_bfloat16*>(dst), table);
   return MAE_CHECK_LAUNCH();
 }
 
 extern "C" int mae_grad_sumsq(const float* g, long long n, float* partials, int max_partials, cudaStream_t stream) {
   if (!g || !partials) return MAE_ERR_NULL;
   if (n <= 0 || max_partials <= 0) return MAE_ERR_SHAPE;
-  grad_sumsq_kernel<<<max_partials, 256, 0, stream>>>(g, n, partials);
+  mae_launch(grad_sumsq_kernel, dim3(max_partials), dim3(256), 0, stream, g, n, partials);
   return MAE_CHECK_LAUNCH();
 }
 
@@ -666,8 +691,7 @@ extern "C" int mae_clip_adamw(float* p, const float* g, float* m, float* v, void
   if (n <= 0 || step < 1 || n_partials < 1) return MAE_ERR_SHAPE;
   const double bc1 = 1.0 - pow(double(beta1), double(step));
   const double bc2 = 1.0 - pow(double(beta2), double(step));
-  clip_adamw_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, stream>>>(
-      p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n, lr, beta1, beta2, eps, weight_decay, max_norm,
+  mae_launch(clip_adamw_kernel, dim3(grid_for(n, 256, 148 * 8)), dim3(256), 0, stream, p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n, lr, beta1, beta2, eps, weight_decay, max_norm,
       float(1.0 / bc1), float(1.0 / sqrt(bc2)), partials, n_partials, grad_norm_out);
   return MAE_CHECK_LAUNCH();
 }

@@ -266,6 +266,7 @@ __device__ __forceinline__ void epilogue_item(const GemmTnParams& p, uint32_t ta
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128-byte swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -292,6 +293,7 @@ gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     if (lane == 0) {
@@ -376,7 +378,7 @@ static int launch_gemm_tn(const GemmTnParams& p, const CUtensorMap& ma, const CU
   }
   const int total = p.mtiles * p.nchunks;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_tn_kernel<EPI><<<grid, kGemmThreads, smem, st>>>(p, ma, mb);
+  mae_launch(gemm_tn_kernel<EPI>, dim3(grid), dim3(kGemmThreads), smem, st, p, ma, mb);
   return cudaGetLastError() == cudaSuccess ? MAE_OK : MAE_ERR_LAUNCH;
 }
 
@@ -446,6 +448,7 @@ __device__ __forceinline__ float swz_box_elem(const uint8_t* box, int r, int c) 
 
 __global__ void __launch_bounds__(kWgradThreads, 1)
 gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP, const __grid_constant__ CUtensorMap mapQ) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t box_bytes = WR * 128;  // one [64 rows x 64 cols] bf16 box = 8 KB
@@ -475,6 +478,7 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
   if (nmb > 0) {
     if (warp == 0) {
       if (lane == 0) {
@@ -623,6 +627,6 @@ extern "C" int mae_gemm_wgrad(const void* P, int Pc, const void* Q, int Qc, int 
       return MAE_ERR_LAUNCH;
     attr_done = true;
   }
-  gemm_wgrad_kernel<<<dim3(pchunks, msplit), kWgradThreads, smem, stream>>>(p, mp, mq);
+  mae_launch(gemm_wgrad_kernel, dim3(dim3(pchunks, msplit)), dim3(kWgradThreads), smem, stream, p, mp, mq);
   return cudaGetLastError() == cudaSuccess ? MAE_OK : MAE_ERR_LAUNCH;
 }

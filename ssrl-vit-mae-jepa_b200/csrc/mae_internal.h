@@ -12,4 +12,21 @@ namespace mae {
 int make_tmap_bf16(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows);
 }
 
+// Launch with the programmatic-dependent-launch attribute (see ptx.cuh: pdl_trigger / pdl_wait).
+template <typename... KArgs, typename... Args>
+inline cudaError_t mae_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 #define MAE_CHECK_LAUNCH() (cudaGetLastError() == cudaSuccess ? MAE_OK : MAE_ERR_LAUNCH)

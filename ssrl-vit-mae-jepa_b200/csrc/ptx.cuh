@@ -10,6 +10,15 @@
 namespace mae {
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel is launched with programmaticStreamSerialization, lets its
+// successor start scheduling immediately (pdl_trigger) and blocks before its first global access until the
+// predecessor grid has completed and flushed (pdl_wait).  Launch latency and prologues (barrier init, TMEM
+// alloc, descriptor prefetch) then overlap the predecessor's tail.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
 // misc
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
