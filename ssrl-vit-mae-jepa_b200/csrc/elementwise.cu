@@ -146,34 +146,52 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   if (h0) { g0 = *reinterpret_cast<const float4*>(gamma + c0); b0 = *reinterpret_cast<const float4*>(beta + c0); }
   if (h1) { g1 = *reinterpret_cast<const float4*>(gamma + c1); b1 = *reinterpret_cast<const float4*>(beta + c1); }
   const float invD = 1.0f / D;
-  for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * wpb) {
-    const float* src = x + map_row(r, gather_idx, n_sel, L_src) * D;
-    float4 v0 = make_float4(0, 0, 0, 0), v1 = v0;
-    if (h0) v0 = *reinterpret_cast<const float4*>(src + c0);
-    if (h1) v1 = *reinterpret_cast<const float4*>(src + c1);
-    const float mu = warp_sum(v0.x + v0.y + v0.z + v0.w + v1.x + v1.y + v1.z + v1.w) * invD;
-    float sq = 0.f;
-    if (h0) { float a = v0.x - mu, b = v0.y - mu, c = v0.z - mu, d = v0.w - mu; sq += a * a + b * b + c * c + d * d; }
-    if (h1) { float a = v1.x - mu, b = v1.y - mu, c = v1.z - mu, d = v1.w - mu; sq += a * a + b * b + c * c + d * d; }
-    const float rs = rsqrtf(warp_sum(sq) * invD + eps);
-    __nv_bfloat16* dst = xn + r * D;
-    if (h0) {
-      uint2 o;
-      o.x = pack_bf16x2((v0.x - mu) * rs * g0.x + b0.x, (v0.y - mu) * rs * g0.y + b0.y);
-      o.y = pack_bf16x2((v0.z - mu) * rs * g0.z + b0.z, (v0.w - mu) * rs * g0.w + b0.w);
-      *reinterpret_cast<uint2*>(dst + c0) = o;
+  const long long stride = (long long)gridDim.x * wpb;
+  // two rows per iteration: both rows' loads are in flight before the first reduction
+  for (long long ra = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); ra < rows; ra += 2 * stride) {
+    float4 v[2][2];
+    long long rr[2] = {ra, ra + stride};
+    bool ok[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      ok[k] = rr[k] < rows;
+      if (!ok[k]) rr[k] = ra;
+      const float* src = x + map_row(rr[k], gather_idx, n_sel, L_src) * D;
+      v[k][0] = v[k][1] = make_float4(0, 0, 0, 0);
+      if (h0) v[k][0] = *reinterpret_cast<const float4*>(src + c0);
+      if (h1) v[k][1] = *reinterpret_cast<const float4*>(src + c1);
     }
-    if (h1) {
-      uint2 o;
-      o.x = pack_bf16x2((v1.x - mu) * rs * g1.x + b1.x, (v1.y - mu) * rs * g1.y + b1.y);
-      o.y = pack_bf16x2((v1.z - mu) * rs * g1.z + b1.z, (v1.w - mu) * rs * g1.w + b1.w);
-      *reinterpret_cast<uint2*>(dst + c1) = o;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float4 v0 = v[k][0], v1 = v[k][1];
+      const float mu = warp_sum(v0.x + v0.y + v0.z + v0.w + v1.x + v1.y + v1.z + v1.w) * invD;
+      float sq = 0.f;
+      if (h0) { float a = v0.x - mu, b = v0.y - mu, c = v0.z - mu, d = v0.w - mu; sq += a * a + b * b + c * c + d * d; }
+      if (h1) { float a = v1.x - mu, b = v1.y - mu, c = v1.z - mu, d = v1.w - mu; sq += a * a + b * b + c * c + d * d; }
+      const float rs = rsqrtf(warp_sum(sq) * invD + eps);
+      if (!ok[k]) continue;
+      const long long r = rr[k];
+      __nv_bfloat16* dst = xn + r * D;
+      if (h0) {
+        uint2 o;
+        o.x = pack_bf16x2((v0.x - mu) * rs * g0.x + b0.x, (v0.y - mu) * rs * g0.y + b0.y);
+        o.y = pack_bf16x2((v0.z - mu) * rs * g0.z + b0.z, (v0.w - mu) * rs * g0.w + b0.w);
+        *reinterpret_cast<uint2*>(dst + c0) = o;
+      }
+      if (h1) {
+        uint2 o;
+        o.x = pack_bf16x2((v1.x - mu) * rs * g1.x + b1.x, (v1.y - mu) * rs * g1.y + b1.y);
+        o.y = pack_bf16x2((v1.z - mu) * rs * g1.z + b1.z, (v1.w - mu) * rs * g1.w + b1.w);
+        *reinterpret_cast<uint2*>(dst + c1) = o;
+      }
+      if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
     }
-    if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
   }
 }
 
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(
+// Two rows per warp iteration: all 12 loads of both rows are issued before the first reduction, doubling the
+// bytes in flight per warp (the kernel is a pure HBM stream: ~3 KB per row in + out).
+__global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(
     const __nv_bfloat16* __restrict__ g, const float* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dx_in,
     const int64_t* __restrict__ gather_idx, int n_sel, int L_src, int rows, int D, float* __restrict__ dx_out,
@@ -190,56 +208,74 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
   float4 w0 = make_float4(0, 0, 0, 0), w1 = w0;
   if (h0) w0 = *reinterpret_cast<const float4*>(gamma + c0);
   if (h1) w1 = *reinterpret_cast<const float4*>(gamma + c1);
+  const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
   float dg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, db[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const float invD = 1.0f / D;
-  for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * wpb) {
-    const long long xr = map_row(r, gather_idx, n_sel, L_src);
-    const float mu = mean[r], rs = rstd[r];
-    float gv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, xh[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (h0) {
-      const uint2 gg = *reinterpret_cast<const uint2*>(g + r * D + c0);
-      const float4 xv = *reinterpret_cast<const float4*>(x + xr * D + c0);
-      gv[0] = bf16_lo(gg.x); gv[1] = bf16_hi(gg.x); gv[2] = bf16_lo(gg.y); gv[3] = bf16_hi(gg.y);
-      xh[0] = (xv.x - mu) * rs; xh[1] = (xv.y - mu) * rs; xh[2] = (xv.z - mu) * rs; xh[3] = (xv.w - mu) * rs;
-    }
-    if (h1) {
-      const uint2 gg = *reinterpret_cast<const uint2*>(g + r * D + c1);
-      const float4 xv = *reinterpret_cast<const float4*>(x + xr * D + c1);
-      gv[4] = bf16_lo(gg.x); gv[5] = bf16_hi(gg.x); gv[6] = bf16_lo(gg.y); gv[7] = bf16_hi(gg.y);
-      xh[4] = (xv.x - mu) * rs; xh[5] = (xv.y - mu) * rs; xh[6] = (xv.z - mu) * rs; xh[7] = (xv.w - mu) * rs;
-    }
-    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-    float s1 = 0.f, s2 = 0.f, dxh[8];
+  const long long stride = (long long)gridDim.x * wpb;
+  for (long long ra = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); ra < rows; ra += 2 * stride) {
+    long long rrow[2] = {ra, ra + stride};
+    long long xr[2];
+    bool ok[2];
+    uint2 gg[2][2];
+    float4 xv[2][2], di[2][2];
+    float mu[2], rs[2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      dg[i] += gv[i] * xh[i];
-      db[i] += gv[i];
-      dxh[i] = gv[i] * wv[i];
-      s1 += dxh[i];
-      s2 += dxh[i] * xh[i];
+    for (int k = 0; k < 2; ++k) {
+      ok[k] = rrow[k] < rows;
+      if (!ok[k]) rrow[k] = ra;
+      xr[k] = map_row(rrow[k], gather_idx, n_sel, L_src);
+      mu[k] = mean[rrow[k]]; rs[k] = rstd[rrow[k]];
+      gg[k][0] = gg[k][1] = make_uint2(0, 0);
+      xv[k][0] = xv[k][1] = di[k][0] = di[k][1] = make_float4(0, 0, 0, 0);
+      if (h0) {
+        gg[k][0] = *reinterpret_cast<const uint2*>(g + rrow[k] * D + c0);
+        xv[k][0] = *reinterpret_cast<const float4*>(x + xr[k] * D + c0);
+        if (dx_in) di[k][0] = *reinterpret_cast<const float4*>(dx_in + xr[k] * D + c0);
+      }
+      if (h1) {
+        gg[k][1] = *reinterpret_cast<const uint2*>(g + rrow[k] * D + c1);
+        xv[k][1] = *reinterpret_cast<const float4*>(x + xr[k] * D + c1);
+        if (dx_in) di[k][1] = *reinterpret_cast<const float4*>(dx_in + xr[k] * D + c1);
+      }
     }
-    s1 = warp_sum(s1) * invD;
-    s2 = warp_sum(s2) * invD;
-    float o[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = rs * (dxh[i] - s1 - xh[i] * s2);
-    if (h0) {
-      if (dx_in) {
-        const float4 a = *reinterpret_cast<const float4*>(dx_in + xr * D + c0);
-        o[0] += a.x; o[1] += a.y; o[2] += a.z; o[3] += a.w;
+    for (int k = 0; k < 2; ++k) {
+      const float gv[8] = {bf16_lo(gg[k][0].x), bf16_hi(gg[k][0].x), bf16_lo(gg[k][0].y), bf16_hi(gg[k][0].y),
+                           bf16_lo(gg[k][1].x), bf16_hi(gg[k][1].x), bf16_lo(gg[k][1].y), bf16_hi(gg[k][1].y)};
+      float xh[8] = {(xv[k][0].x - mu[k]) * rs[k], (xv[k][0].y - mu[k]) * rs[k], (xv[k][0].z - mu[k]) * rs[k],
+                     (xv[k][0].w - mu[k]) * rs[k], (xv[k][1].x - mu[k]) * rs[k], (xv[k][1].y - mu[k]) * rs[k],
+                     (xv[k][1].z - mu[k]) * rs[k], (xv[k][1].w - mu[k]) * rs[k]};
+      if (!h0) { xh[0] = xh[1] = xh[2] = xh[3] = 0.f; }
+      if (!h1) { xh[4] = xh[5] = xh[6] = xh[7] = 0.f; }
+      float s1 = 0.f, s2 = 0.f, dxh[8];
+      const float live = ok[k] ? 1.f : 0.f;  // the duplicate row of a ragged tail must not count twice
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        dg[i] += live * gv[i] * xh[i];
+        db[i] += live * gv[i];
+        dxh[i] = gv[i] * wv[i];
+        s1 += dxh[i];
+        s2 += dxh[i] * xh[i];
       }
-      *reinterpret_cast<float4*>(dx_out + xr * D + c0) = make_float4(o[0], o[1], o[2], o[3]);
-      if (dx_out_bf16)
-        *reinterpret_cast<uint2*>(dx_out_bf16 + xr * D + c0) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
-    }
-    if (h1) {
-      if (dx_in) {
-        const float4 a = *reinterpret_cast<const float4*>(dx_in + xr * D + c1);
-        o[4] += a.x; o[5] += a.y; o[6] += a.z; o[7] += a.w;
+      s1 = warp_sum(s1) * invD;
+      s2 = warp_sum(s2) * invD;
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = rs[k] * (dxh[i] - s1 - xh[i] * s2);
+      o[0] += di[k][0].x; o[1] += di[k][0].y; o[2] += di[k][0].z; o[3] += di[k][0].w;
+      o[4] += di[k][1].x; o[5] += di[k][1].y; o[6] += di[k][1].z; o[7] += di[k][1].w;
+      if (ok[k]) {
+        if (h0) {
+          *reinterpret_cast<float4*>(dx_out + xr[k] * D + c0) = make_float4(o[0], o[1], o[2], o[3]);
+          if (dx_out_bf16)
+            *reinterpret_cast<uint2*>(dx_out_bf16 + xr[k] * D + c0) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+        }
+        if (h1) {
+          *reinterpret_cast<float4*>(dx_out + xr[k] * D + c1) = make_float4(o[4], o[5], o[6], o[7]);
+          if (dx_out_bf16)
+            *reinterpret_cast<uint2*>(dx_out_bf16 + xr[k] * D + c1) = make_uint2(pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+        }
       }
-      *reinterpret_cast<float4*>(dx_out + xr * D + c1) = make_float4(o[4], o[5], o[6], o[7]);
-      if (dx_out_bf16)
-        *reinterpret_cast<uint2*>(dx_out_bf16 + xr * D + c1) = make_uint2(pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
     }
   }
 #pragma unroll
@@ -317,11 +353,23 @@ __global__ void __launch_bounds__(256) masked_mse_kernel(const __nv_bfloat16* __
     const int pr = pidx / grid, pcn = pidx % grid;
     const float* src = images + size_t(b) * C * img * img;
     float s = 0.f, ss = 0.f;
-    for (int q = lane; q < pd; q += 32) {  // q in image order (c,py,px): 32-byte runs
-      const int c = q / pp, py = (q % pp) / patch, px = q % patch;
-      const float v = src[(size_t(c) * img + pr * patch + py) * img + pcn * patch + px];
-      st[(py * patch + px) * C + c] = v;
-      s += v; ss += v * v;
+    if ((patch & 3) == 0) {
+      // vector path: one float4 = 4 consecutive px of one (c, py) image row
+      const int p4 = patch >> 2, nq = pd >> 2;
+      for (int q = lane; q < nq; q += 32) {
+        const int c = q / (patch * p4), py = (q / p4) % patch, px = (q % p4) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(src + (size_t(c) * img + pr * patch + py) * img + pcn * patch + px);
+        float* d = st + (py * patch + px) * C + c;
+        d[0] = v.x; d[C] = v.y; d[2 * C] = v.z; d[3 * C] = v.w;
+        s += v.x + v.y + v.z + v.w; ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      }
+    } else {
+      for (int q = lane; q < pd; q += 32) {  // q in image order (c,py,px): 32-byte runs
+        const int c = q / pp, py = (q % pp) / patch, px = q % patch;
+        const float v = src[(size_t(c) * img + pr * patch + py) * img + pcn * patch + px];
+        st[(py * patch + px) * C + c] = v;
+        s += v; ss += v * v;
+      }
     }
     __syncwarp();
     float mu = 0.f, rsd = 1.f;
@@ -332,12 +380,13 @@ __global__ void __launch_bounds__(256) masked_mse_kernel(const __nv_bfloat16* __
       rsd = rsqrtf(var + 1e-6f);
     }
     const __nv_bfloat16* pr_row = pred + r * pd;
-    for (int e = lane; e < pd; e += 32) {
-      const float t = (st[e] - mu) * rsd;
-      const float d = __bfloat162float(pr_row[e]) - t;
-      acc += d * d;
-      if (dpred) dpred[r * pd + e] = __float2bfloat16_rn(2.0f * d * inv_numel);
-      if (target) target[r * pd + e] = t;
+    for (int e = lane * 2; e < pd; e += 64) {  // pd is even: bf16x2 per lane, coalesced
+      const uint32_t pv = *reinterpret_cast<const uint32_t*>(pr_row + e);
+      const float t0 = (st[e] - mu) * rsd, t1 = (st[e + 1] - mu) * rsd;
+      const float d0 = bf16_lo(pv) - t0, d1 = bf16_hi(pv) - t1;
+      acc += d0 * d0 + d1 * d1;
+      if (dpred) *reinterpret_cast<uint32_t*>(dpred + r * pd + e) = pack_bf16x2(2.0f * d0 * inv_numel, 2.0f * d1 * inv_numel);
+      if (target) *reinterpret_cast<float2*>(target + r * pd + e) = make_float2(t0, t1);
     }
     __syncwarp();
   }

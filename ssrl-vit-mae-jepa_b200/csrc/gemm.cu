@@ -585,8 +585,17 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
         tmem_ld16(taddr + c0, v);
         if (prow < p.Pc) {
           float* o = p.out + (long long)prow * p.so_p + (long long)c0 * p.so_q;
+          if (p.so_q == 1 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+            // 16 consecutive floats of one dW row: four 16-byte vector reductions instead of 16 scalar ones
 #pragma unroll
-          for (int i = 0; i < 16; ++i) atomicAdd(o + (long long)i * p.so_q, v[i]);
+            for (int i = 0; i < 16; i += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + i), "f"(v[i]), "f"(v[i + 1]),
+                           "f"(v[i + 2]), "f"(v[i + 3])
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(o + (long long)i * p.so_q, v[i]);
+          }
         }
       }
     }
