@@ -36,9 +36,9 @@ enum {
 /* epilogues of mae_gemm_tn */
 enum {
   MAE_EPI_BF16 = 0,       /* out(bf16) = acc + bias                                  (qkv, embed, pred, dgrads) */
-  MAE_EPI_GELU_BF16 = 1,  /* pre_out(bf16) = acc + bias; out(bf16) = gelu_erf(pre)   (mlp.fc1)                  */
+  MAE_EPI_GELU_BF16 = 1,  /* pre=bf16(acc+bias); out(bf16)=gelu_erf(pre); pre_out(bf16)=gelu_erf'(pre) (mlp.fc1) */
   MAE_EPI_RESID_F32 = 2,  /* out(f32) = aux(f32) + acc + bias                        (attn.proj, mlp.fc2)       */
-  MAE_EPI_DGELU_BF16 = 4  /* out(bf16) = acc * gelu_erf'(aux(bf16 pre-activation))   (fc2 dgrad)                */
+  MAE_EPI_DGELU_BF16 = 4  /* out(bf16) = acc * aux(bf16 gelu' saved by EPI 1)         (fc2 dgrad)                */
 };
 
 int mae_version(void);

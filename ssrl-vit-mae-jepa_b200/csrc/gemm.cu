@@ -78,8 +78,8 @@ struct GemmTnParams {
   int nstages;  // TMA ring depth (3 or 4, whatever fits next to the epilogue staging tiles)
   const float* bias;          // [N] or null
   void* out;                  // bf16 [M,N] (EPI 0,1,3,4)  or  f32 [M,N] (EPI 2)
-  __nv_bfloat16* pre_out;     // EPI 1: bf16 [M,N] pre-activation
-  const void* aux;            // EPI 2: f32 residual [M,N];  EPI 4: bf16 pre-activation [M,N]
+  __nv_bfloat16* pre_out;     // EPI 1: bf16 [M,N] GELU'(pre-activation), consumed by EPI 4
+  const void* aux;            // EPI 2: f32 residual [M,N];  EPI 4: bf16 GELU' [M,N] saved by EPI 1
 };
 
 struct GemmSmemHdr {
@@ -176,15 +176,18 @@ __device__ __forceinline__ void epilogue_item(const GemmTnParams& p, uint32_t ta
   constexpr int SB = F32 ? 64 : 32;          // bytes per 16-column sub-chunk
   constexpr int ES = F32 ? 4 : 2;            // output element size
   const int rows_valid = p.M - row0;         // may be <= 0 or > 32
-  const int units = (p.bn + UC - 1) / UC;
-  for (int u = grp; u < units; u += kEpiGroups) {
-    const int c0 = u * UC;
-    int nsub = (p.bn - c0) >> 4;
+  // Balanced split of the bn/16 sub-chunks over the kEpiGroups warps of this lane quarter (contiguous ranges,
+  // e.g. bn=192: 3+3+3+3, bn=144: 3+2+2+2), each range processed in units of at most 128 bytes per row.
+  const int nsc = p.bn >> 4;
+  const int sc_begin = (nsc * grp) / kEpiGroups, sc_end = (nsc * (grp + 1)) / kEpiGroups;
+  for (int sc = sc_begin; sc < sc_end; sc += UC / 16) {
+    const int c0 = sc * 16;
+    int nsub = sc_end - sc;
     if (nsub > UC / 16) nsub = UC / 16;
     const int row_bytes = nsub * SB;
     const int gcol = col_base + c0;
     const size_t gpitch = size_t(p.N) * ES;
-    if constexpr (EPI == MAE_EPI_DGELU_BF16) {  // bring the pre-activation tile in, coalesced
+    if constexpr (EPI == MAE_EPI_DGELU_BF16) {  // bring the saved GELU' tile in, coalesced
       uint8_t* abase = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(p.aux)) + (size_t(row0) * p.N + gcol) * 2;
       stg_copy<false>(stg, abase, gpitch, row_bytes, rows_valid, lane);
       __syncwarp();
@@ -225,16 +228,22 @@ __device__ __forceinline__ void epilogue_item(const GemmTnParams& p, uint32_t ta
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
         } else if constexpr (EPI == MAE_EPI_GELU_BF16) {
-          // autocast semantics: the linear's output is rounded to bf16, GELU reads that bf16 value
+          // autocast semantics: the linear's output is rounded to bf16 and GELU reads that bf16 value.  Both
+          // GELU and GELU' are produced here (shared Phi); GELU' is what the backward needs, so it is saved
+          // in place of the pre-activation and the dgrad epilogue is a plain multiply.
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-            hkeep[sidx][i] = pack_bf16x2(gelu_fast(bf16_lo(o[i])), gelu_fast(bf16_hi(o[i])));
+            const uint32_t pre2 = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            float g0, g1, d0, d1;
+            gelu_fwd_bwd(bf16_lo(pre2), g0, d0);
+            gelu_fwd_bwd(bf16_hi(pre2), g1, d1);
+            o[i] = pack_bf16x2(d0, d1);
+            hkeep[sidx][i] = pack_bf16x2(g0, g1);
           }
         } else {  // DGELU
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            o[i] = pack_bf16x2(v[2 * i] * gelu_fast_grad(bf16_lo(pr[i])), v[2 * i + 1] * gelu_fast_grad(bf16_hi(pr[i])));
+          for (int i = 0; i < 8; ++i)  // pr = GELU'(pre) saved by the forward
+            o[i] = pack_bf16x2(v[2 * i] * bf16_lo(pr[i]), v[2 * i + 1] * bf16_hi(pr[i]));
         }
         uint4* d = reinterpret_cast<uint4*>(my);
         d[0] = make_uint4(o[0], o[1], o[2], o[3]);
