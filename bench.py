@@ -167,13 +167,19 @@ def kernel_breakdown(trainer, images, noise, pk):
             setattr(lib_calls, name, fn)
     fam = {}
     gemm_flops = 0.0
+    gemm_bytes = 0.0
     wgrad_flops = 0.0
     for name, s, e, a in records:
         ms = s.elapsed_time(e)
         d = fam.setdefault(name, [0.0, 0])
         d[0] += ms; d[1] += 1
         if name == "mae_gemm_tn":
-            gemm_flops += 2.0 * a[2] * a[3] * a[4]
+            M, N, K, epi = a[2], a[3], a[4], a[5]
+            gemm_flops += 2.0 * M * N * K
+            # algorithmic bytes of one launch: A once, weights once, the output(s), and the aux operand
+            out_b = {0: 2, 1: 4, 2: 4, 4: 2}[epi]            # bf16 | bf16 h + bf16 gelu' | fp32 | bf16
+            aux_b = {0: 0, 1: 0, 2: 4, 4: 2}[epi]            # - | - | fp32 residual | bf16 gelu'
+            gemm_bytes += M * K * 2.0 + N * K * 2.0 + M * N * (out_b + aux_b)
         if name == "mae_gemm_wgrad":
             wgrad_flops += 2.0 * a[1] * a[3] * a[4]
     total = sum(v[0] for v in fam.values())
@@ -182,11 +188,16 @@ def kernel_breakdown(trainer, images, noise, pk):
     g_ms = fam.get("mae_gemm_tn", [0.0, 0])[0]
     roof = None
     if g_ms > 0:
-        ach = gemm_flops / (g_ms * 1e-3) / 1e12
-        roof = {"kernel": "gemm_tn_kernel (tcgen05, all forward/dgrad GEMMs of one step)", "bound": "tensor",
-                "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                "traffic": None, "peak_source": pk["source"] + " (sustained: timed inside a long step)",
-                "flops_per_step": gemm_flops, "ms_per_step": g_ms}
+        gbs = gemm_bytes / (g_ms * 1e-3) / 1e9
+        tfs = gemm_flops / (g_ms * 1e-3) / 1e12
+        roof = {"kernel": "gemm_tn_kernel (tcgen05 + TMA; the 53 forward/dgrad GEMM launches of one step, K = 144..768)",
+                "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                "traffic": None, "peak_source": pk["source"] + " (copy bandwidth)",
+                "traffic_example": "ncu --set full, decoder qkv launch (M=290000,N=576,K=192): dram read 111.6 MB + write "
+                                   "283.2 MB vs 445.6 MB algorithmic (profiles/README.md)",
+                "algorithmic_bytes_per_step": gemm_bytes, "ms_per_step": g_ms,
+                "tensor": {"achieved_tflops": tfs, "peak_tflops": pk["tf_sustained"], "frac": tfs / pk["tf_sustained"],
+                           "flops_per_step": gemm_flops}}
     w_ms = fam.get("mae_gemm_wgrad", [0.0, 0])[0]
     extra = {"gemm_wgrad_tflops": (wgrad_flops / (w_ms * 1e-3) / 1e12) if w_ms > 0 else None,
              "instrumented_step_ms": total}
