@@ -84,14 +84,14 @@ int mae_gemm_tn(const void* A_bf16, const void* B_bf16, int M, int N, int K, int
                 void* pre_out_bf16, const void* aux, mae_stream_t stream);
 
 /* out[p*so_p + q*so_q] += sum_m P[m,p] * Q[m,q]: weight gradients (autograd of the Linears above).
- * P bf16 (M,Pc), Q bf16 (M,Qc), Qc <= 256, Qc % 16 == 0, Pc % 8 == 0.  fp32 atomics: zero `out` first.
+ * P bf16 (M,Pc), Q bf16 (M,Qc), Qc % 16 == 0, Pc % 8 == 0.  fp32 atomics: zero `out` first.
  * If colsum != NULL the same launch also accumulates the bias gradient: colsum[c] += sum_m P[m,c]
  * (colsum_of_q == 0) or sum_m Q[m,c] (colsum_of_q != 0), read from the tiles already staged in shared memory. */
 int mae_gemm_wgrad(const void* P_bf16, int Pc, const void* Q_bf16, int Qc, int M, float* out, long long so_p,
                    long long so_q, float* colsum, int colsum_of_q, mae_stream_t stream);
 
 /* timm Attention core: F.scaled_dot_product_attention on qkv (B,L,3,H,hd) bf16 -> out (B,L,H*hd) bf16,
- * scale hd^-0.5, plus lse (B,H,L) f32 for the backward.  hd in {24,32}; L <= 160. */
+ * scale hd^-0.5, plus lse (B,H,L) f32 for the backward.  hd in {24,32,64}; L <= 208. */
 int mae_attention_fwd(const void* qkv_bf16, int B, int L, int H, int hd, void* out_bf16, float* lse,
                       mae_stream_t stream);
 int mae_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse, int B,
@@ -128,9 +128,10 @@ int mae_colsum_rows_f32(const float* src, const int64_t* idx, int B, int n_sel, 
 int mae_cast_bf16(const float* src, void* dst_bf16, long long n, mae_stream_t stream);
 
 /* Multi-tensor transposing cast: for each entry t of table (n_entries x 4 int64: src_off, rows, cols, dst_off;
- * device memory) writes dst[dst_off + c*rows + r] = bf16(src[src_off + r*cols + c]). */
-int mae_transpose_cast_bf16(const float* src, void* dst_bf16, const long long* table, int n_entries,
-                            mae_stream_t stream);
+ * device memory) writes dst[dst_off + c*rows + r] = bf16(src[src_off + r*cols + c]).  max_rows / max_cols bound the
+ * entries' shapes (they size the launch grid). */
+int mae_transpose_cast_bf16(const float* src, void* dst_bf16, const long long* table, int n_entries, int max_rows,
+                            int max_cols, mae_stream_t stream);
 
 /* Lightning gradient_clip_val=1.0 ("norm") + torch.optim.AdamW step (reference
  * scripts/training/pretrain_mae.py:124-125, src/training/mae.py:59-65) over one flat fp32 buffer of n

@@ -31,7 +31,7 @@ SIGNATURES = {
     "mae_gather_rows_bf16": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "mae_colsum_rows_f32": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "mae_cast_bf16": [_vp, _vp, _ll, _vp],
-    "mae_transpose_cast_bf16": [_vp, _vp, _vp, _i, _vp],
+    "mae_transpose_cast_bf16": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "mae_grad_sumsq": [_vp, _ll, _vp, _i, _vp],
     "mae_clip_adamw": [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _f, _i, _vp, _i, _vp, _vp],
 }

@@ -16,7 +16,7 @@
 
 namespace mae {
 
-static constexpr int ST = 40;  // smem row stride (bf16): 32 data + 8 pad -> 80-byte rows, conflict-free ldmatrix
+// smem row stride (bf16) = padded head dim + 8: 80-byte (hd 24/32) or 144-byte (hd 64) rows, conflict-free ldmatrix
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const __nv_bfloat16* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -30,26 +30,41 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const __nv_bfloat16*
 }
 
 // A fragment: 16 rows [row0, +16) x 16 k [k0, +16) of a row-major tile.
+template <int ST>
 __device__ __forceinline__ void frag_a(uint32_t (&a)[4], const __nv_bfloat16* tile, int row0, int k0, int lane) {
   ldsm_x4(a, tile + (row0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ST + k0 + (lane >> 4) * 8);
 }
-// B fragments for  D[m][n] += A[m][k] * X[n][k]  (X row-major [n][k], k = the 32 padded head-dim columns):
-// {b[0], b[1]} serve k-step 0, {b[2], b[3]} k-step 1, for the 8 rows n0..n0+7 of X.
-__device__ __forceinline__ void frag_b_rows(uint32_t (&b)[4], const __nv_bfloat16* tile, int n0, int lane) {
-  ldsm_x4(b, tile + (n0 + (lane & 7)) * ST + (lane >> 3) * 8);
+// B fragments for  D[m][n] += A[m][k] * X[n][k]  (X row-major [n][k]) for the 8 rows n0..n0+7 of X and the 32
+// k-columns starting at kc: {b[0], b[1]} serve k-step kc/16, {b[2], b[3]} k-step kc/16 + 1.
+template <int ST>
+__device__ __forceinline__ void frag_b_rows(uint32_t (&b)[4], const __nv_bfloat16* tile, int n0, int kc, int lane) {
+  ldsm_x4(b, tile + (n0 + (lane & 7)) * ST + kc + (lane >> 3) * 8);
+}
+// acc(16x8) += A(16 x 16*KS) . X[n0..n0+7][0..16*KS)^T  with A fragments a[KS]
+template <int ST, int KS>
+__device__ __forceinline__ void mma_rows(float (&acc)[4], const uint32_t (&a)[KS][4], const __nv_bfloat16* tile, int n0,
+                                         int lane) {
+#pragma unroll
+  for (int kp = 0; kp < KS / 2; ++kp) {
+    uint32_t b[4];
+    frag_b_rows<ST>(b, tile, n0, kp * 32, lane);
+    mma_16816(acc, a[2 * kp], b[0], b[1]);
+    mma_16816(acc, a[2 * kp + 1], b[2], b[3]);
+  }
 }
 // B fragments for  D[m][n] += A[m][k] * X[k][n]  (X row-major [k][n]): 16 k-rows k0.., 16 n-columns d0..:
 // {b[0], b[1]} serve n-tile d0, {b[2], b[3]} n-tile d0 + 8.
+template <int ST>
 __device__ __forceinline__ void frag_b_cols(uint32_t (&b)[4], const __nv_bfloat16* tile, int k0, int d0, int lane) {
   ldsm_x4_t(b, tile + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ST + d0 + (lane >> 4) * 8);
 }
 
-template <int NARR>
+template <int NARR, int ST, int CPR>  // CPR = 16-byte chunks per padded row (4 or 8)
 __device__ __forceinline__ void load_tiles(const __nv_bfloat16* const (&src)[NARR], const int (&ld)[NARR],
                                            __nv_bfloat16* const (&dst)[NARR], int L, int Lp, int chunks, int tid,
                                            int nthreads) {
-  for (int i = tid; i < Lp * 4; i += nthreads) {
-    const int r = i >> 2, c = i & 3;
+  for (int i = tid; i < Lp * CPR; i += nthreads) {
+    const int r = i / CPR, c = i % CPR;
     const bool ok = r < L && c < chunks;
 #pragma unroll
     for (int a = 0; a < NARR; ++a) {
@@ -65,7 +80,7 @@ __global__ void __launch_bounds__(NT * 16) attn_fwd_kernel(const __nv_bfloat16* 
                                                            __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
                                                            int L, int H, float scale) {
   pdl_trigger();
-  constexpr int Lp = NT * 8, DN = HD / 8;
+  constexpr int Lp = NT * 8, DN = HD / 8, KD = HD <= 32 ? 32 : 64, KS = KD / 16, ST = KD + 8, DNP = KD / 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
   __nv_bfloat16* sK = sQ + Lp * ST;
@@ -79,25 +94,22 @@ __global__ void __launch_bounds__(NT * 16) attn_fwd_kernel(const __nv_bfloat16* 
     const __nv_bfloat16* const src[3] = {base, base + D, base + 2 * D};
     const int ld[3] = {3 * D, 3 * D, 3 * D};
     __nv_bfloat16* const dst[3] = {sQ, sK, sV};
-    load_tiles<3>(src, ld, dst, L, Lp, HD / 8, tid, NT * 16);
+    load_tiles<3, ST, KD / 8>(src, ld, dst, L, Lp, HD / 8, tid, NT * 16);
   }
   __syncthreads();
 
   const int q0 = w * 16;
-  uint32_t aq[2][4];
-  frag_a(aq[0], sQ, q0, 0, lane);
-  frag_a(aq[1], sQ, q0, 16, lane);
+  uint32_t aq[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) frag_a<ST>(aq[ks], sQ, q0, ks * 16, lane);
   const float sl2 = scale * 1.4426950408889634f;
 
   // pass 1: row max only (no exponentials); key columns >= L exist only in the last tiles, so only those mask
   float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll 2
   for (int nt = 0; nt < NT; ++nt) {
-    uint32_t bk[4];
-    frag_b_rows(bk, sK, nt * 8, lane);
     float s[4] = {0.f, 0.f, 0.f, 0.f};
-    mma_16816(s, aq[0], bk[0], bk[1]);
-    mma_16816(s, aq[1], bk[2], bk[3]);
+    mma_rows<ST, KS>(s, aq, sK, nt * 8, lane);
     if (nt * 8 + 8 > L) {  // warp-uniform
       const int c = nt * 8 + t * 2;
       if (c >= L) { s[0] = -INFINITY; s[2] = -INFINITY; }
@@ -111,9 +123,9 @@ __global__ void __launch_bounds__(NT * 16) attn_fwd_kernel(const __nv_bfloat16* 
   M1 = fmaxf(M1, __shfl_xor_sync(0xffffffffu, M1, 1)); M1 = fmaxf(M1, __shfl_xor_sync(0xffffffffu, M1, 2));
 
   // pass 2: recompute S per 16-key block, P = exp(S - max), row sums and O += P.V; normalised at the end
-  float o[4][4];
+  float o[DNP][4];
 #pragma unroll
-  for (int dn = 0; dn < 4; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
+  for (int dn = 0; dn < DNP; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
   const float ms0 = M0 * sl2, ms1 = M1 * sl2;
   float l0 = 0.f, l1 = 0.f;
 #pragma unroll 2
@@ -122,11 +134,8 @@ __global__ void __launch_bounds__(NT * 16) attn_fwd_kernel(const __nv_bfloat16* 
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
       const int nt = 2 * kk + hf;
-      uint32_t bk[4];
-      frag_b_rows(bk, sK, nt * 8, lane);
       p[hf][0] = p[hf][1] = p[hf][2] = p[hf][3] = 0.f;
-      mma_16816(p[hf], aq[0], bk[0], bk[1]);
-      mma_16816(p[hf], aq[1], bk[2], bk[3]);
+      mma_rows<ST, KS>(p[hf], aq, sK, nt * 8, lane);
       p[hf][0] = exp2f(p[hf][0] * sl2 - ms0); p[hf][1] = exp2f(p[hf][1] * sl2 - ms0);
       p[hf][2] = exp2f(p[hf][2] * sl2 - ms1); p[hf][3] = exp2f(p[hf][3] * sl2 - ms1);
       if (nt * 8 + 8 > L) {  // warp-uniform
@@ -141,9 +150,9 @@ __global__ void __launch_bounds__(NT * 16) attn_fwd_kernel(const __nv_bfloat16* 
     a[0] = pack_bf16x2(p[0][0], p[0][1]); a[1] = pack_bf16x2(p[0][2], p[0][3]);
     a[2] = pack_bf16x2(p[1][0], p[1][1]); a[3] = pack_bf16x2(p[1][2], p[1][3]);
 #pragma unroll
-    for (int dp = 0; dp < 2; ++dp) {
+    for (int dp = 0; dp < DNP / 2; ++dp) {
       uint32_t bv[4];
-      frag_b_cols(bv, sV, kk * 16, dp * 16, lane);
+      frag_b_cols<ST>(bv, sV, kk * 16, dp * 16, lane);
       mma_16816(o[2 * dp], a, bv[0], bv[1]);
       if (2 * dp + 1 < DN) mma_16816(o[2 * dp + 1], a, bv[2], bv[3]);
     }
@@ -171,7 +180,7 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
                                                            const float* __restrict__ lse,
                                                            __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale) {
   pdl_trigger();
-  constexpr int Lp = NT * 8, DN = HD / 8;
+  constexpr int Lp = NT * 8, DN = HD / 8, KD = HD <= 32 ? 32 : 64, KS = KD / 16, ST = KD + 8, DNP = KD / 8, CPR = KD / 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
   __nv_bfloat16* sK = sQ + Lp * ST;
@@ -189,11 +198,12 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
     const __nv_bfloat16* const src[4] = {base, base + D, base + 2 * D, dout + size_t(b) * L * D + h * HD};
     const int ld[4] = {3 * D, 3 * D, 3 * D, D};
     __nv_bfloat16* const dst[4] = {sQ, sK, sV, sdO};
-    load_tiles<4>(src, ld, dst, L, Lp, HD / 8, tid, NT * 16);
+    load_tiles<4, ST, CPR>(src, ld, dst, L, Lp, HD / 8, tid, NT * 16);
   }
-  // delta[q] = sum_d dO[q,d] * O[q,d];  Lp*4 == 2 * blockDim, so every lane runs both iterations (full-warp shuffles)
-  for (int i = tid; i < Lp * 4; i += NT * 16) {
-    const int r = i >> 2, c = i & 3;
+  // delta[q] = sum_d dO[q,d] * O[q,d];  Lp*CPR == (CPR/2) * blockDim, so every lane runs every iteration
+  // (full-warp shuffles); the CPR lanes of a row are adjacent
+  for (int i = tid; i < Lp * CPR; i += NT * 16) {
+    const int r = i / CPR, c = i % CPR;
     float part = 0.f;
     if (r < L && c < HD / 8) {
       const size_t ob = (size_t(b) * L + r) * D + h * HD + c * 8;
@@ -205,6 +215,7 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
     }
     part += __shfl_xor_sync(0xffffffffu, part, 1);
     part += __shfl_xor_sync(0xffffffffu, part, 2);
+    if (CPR == 8) part += __shfl_xor_sync(0xffffffffu, part, 4);
     if (c == 0) {
       sDelta[r] = part;
       sLse[r] = (r < L) ? lse[(size_t(b) * H + h) * L + r] * l2e : 0.f;
@@ -218,25 +229,22 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
 
   // ------------------------------ phase A: dQ ------------------------------
   {
-    uint32_t aq[2][4], ado[2][4];
-    frag_a(aq[0], sQ, x0, 0, lane);   frag_a(aq[1], sQ, x0, 16, lane);
-    frag_a(ado[0], sdO, x0, 0, lane); frag_a(ado[1], sdO, x0, 16, lane);
-    const float l0 = sLse[r0], l1 = sLse[r1], d0 = sDelta[r0], d1 = sDelta[r1];
-    float dq[4][4];
+    uint32_t aq[KS][4], ado[KS][4];
 #pragma unroll
-    for (int dn = 0; dn < 4; ++dn) dq[dn][0] = dq[dn][1] = dq[dn][2] = dq[dn][3] = 0.f;
+    for (int ks = 0; ks < KS; ++ks) { frag_a<ST>(aq[ks], sQ, x0, ks * 16, lane); frag_a<ST>(ado[ks], sdO, x0, ks * 16, lane); }
+    const float l0 = sLse[r0], l1 = sLse[r1], d0 = sDelta[r0], d1 = sDelta[r1];
+    float dq[DNP][4];
+#pragma unroll
+    for (int dn = 0; dn < DNP; ++dn) dq[dn][0] = dq[dn][1] = dq[dn][2] = dq[dn][3] = 0.f;
 #pragma unroll 2
     for (int kk = 0; kk < NT / 2; ++kk) {
       float ds[2][4];
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int nt = 2 * kk + hf;
-        uint32_t bk[4], bv[4];
-        frag_b_rows(bk, sK, nt * 8, lane);
-        frag_b_rows(bv, sV, nt * 8, lane);
         float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_16816(s, aq[0], bk[0], bk[1]);   mma_16816(s, aq[1], bk[2], bk[3]);
-        mma_16816(dp, ado[0], bv[0], bv[1]); mma_16816(dp, ado[1], bv[2], bv[3]);
+        mma_rows<ST, KS>(s, aq, sK, nt * 8, lane);
+        mma_rows<ST, KS>(dp, ado, sV, nt * 8, lane);
         float p0 = exp2f(s[0] * sl2 - l0), p1 = exp2f(s[1] * sl2 - l0);
         float p2 = exp2f(s[2] * sl2 - l1), p3 = exp2f(s[3] * sl2 - l1);
         if (nt * 8 + 8 > L) {  // warp-uniform: only the tail tiles hold padded keys (s = 0 there, exp(-lse) may overflow)
@@ -251,9 +259,9 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
       a[0] = pack_bf16x2(ds[0][0], ds[0][1]); a[1] = pack_bf16x2(ds[0][2], ds[0][3]);
       a[2] = pack_bf16x2(ds[1][0], ds[1][1]); a[3] = pack_bf16x2(ds[1][2], ds[1][3]);
 #pragma unroll
-      for (int dp2 = 0; dp2 < 2; ++dp2) {
+      for (int dp2 = 0; dp2 < DNP / 2; ++dp2) {
         uint32_t kt[4];
-        frag_b_cols(kt, sK, kk * 16, dp2 * 16, lane);
+        frag_b_cols<ST>(kt, sK, kk * 16, dp2 * 16, lane);
         mma_16816(dq[2 * dp2], a, kt[0], kt[1]);
         if (2 * dp2 + 1 < DN) mma_16816(dq[2 * dp2 + 1], a, kt[2], kt[3]);
       }
@@ -268,12 +276,12 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
 
   // ------------------------------ phase B: dK, dV ------------------------------
   {
-    uint32_t ak[2][4], av[2][4];
-    frag_a(ak[0], sK, x0, 0, lane); frag_a(ak[1], sK, x0, 16, lane);
-    frag_a(av[0], sV, x0, 0, lane); frag_a(av[1], sV, x0, 16, lane);
-    float dk[4][4], dv[4][4];
+    uint32_t ak[KS][4], av[KS][4];
 #pragma unroll
-    for (int dn = 0; dn < 4; ++dn) {
+    for (int ks = 0; ks < KS; ++ks) { frag_a<ST>(ak[ks], sK, x0, ks * 16, lane); frag_a<ST>(av[ks], sV, x0, ks * 16, lane); }
+    float dk[DNP][4], dv[DNP][4];
+#pragma unroll
+    for (int dn = 0; dn < DNP; ++dn) {
       dk[dn][0] = dk[dn][1] = dk[dn][2] = dk[dn][3] = 0.f;
       dv[dn][0] = dv[dn][1] = dv[dn][2] = dv[dn][3] = 0.f;
     }
@@ -284,12 +292,9 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         const int nt = 2 * kk + hf;
-        uint32_t bq[4], bd[4];
-        frag_b_rows(bq, sQ, nt * 8, lane);
-        frag_b_rows(bd, sdO, nt * 8, lane);
         float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_16816(s, ak[0], bq[0], bq[1]);  mma_16816(s, ak[1], bq[2], bq[3]);
-        mma_16816(dp, av[0], bd[0], bd[1]); mma_16816(dp, av[1], bd[2], bd[3]);
+        mma_rows<ST, KS>(s, ak, sQ, nt * 8, lane);
+        mma_rows<ST, KS>(dp, av, sdO, nt * 8, lane);
         // no masks needed: for query >= L the Q and dO rows are exactly zero (P^T there meets zero dO / Q rows,
         // sLse/sDelta are 0), and key rows >= L only feed dK/dV rows that are never stored
         const int c = nt * 8 + t * 2;  // query column
@@ -308,10 +313,10 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
       as_[0] = pack_bf16x2(ds[0][0], ds[0][1]); as_[1] = pack_bf16x2(ds[0][2], ds[0][3]);
       as_[2] = pack_bf16x2(ds[1][0], ds[1][1]); as_[3] = pack_bf16x2(ds[1][2], ds[1][3]);
 #pragma unroll
-      for (int dp2 = 0; dp2 < 2; ++dp2) {
+      for (int dp2 = 0; dp2 < DNP / 2; ++dp2) {
         uint32_t dot[4], qt[4];
-        frag_b_cols(dot, sdO, kk * 16, dp2 * 16, lane);
-        frag_b_cols(qt, sQ, kk * 16, dp2 * 16, lane);
+        frag_b_cols<ST>(dot, sdO, kk * 16, dp2 * 16, lane);
+        frag_b_cols<ST>(qt, sQ, kk * 16, dp2 * 16, lane);
         mma_16816(dv[2 * dp2], ap, dot[0], dot[1]);
         mma_16816(dk[2 * dp2], as_, qt[0], qt[1]);
         if (2 * dp2 + 1 < DN) {
@@ -339,7 +344,7 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
 
 template <int HD, int NT>
 static int launch_fwd(const void* qkv, int B, int L, int H, void* out, float* lse, cudaStream_t st) {
-  constexpr int Lp = NT * 8;
+  constexpr int Lp = NT * 8, ST = (HD <= 32 ? 32 : 64) + 8;
   const size_t smem = size_t(3 * Lp * ST) * 2;
   static bool done = false;
   if (!done) {
@@ -356,7 +361,7 @@ static int launch_fwd(const void* qkv, int B, int L, int H, void* out, float* ls
 template <int HD, int NT>
 static int launch_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int B, int L, int H,
                       void* dqkv, cudaStream_t st) {
-  constexpr int Lp = NT * 8;
+  constexpr int Lp = NT * 8, ST = (HD <= 32 ? 32 : 64) + 8;
   const size_t smem = size_t(4 * Lp * ST) * 2 + size_t(2 * Lp) * 4;
   static bool done = false;
   if (!done) {
@@ -372,8 +377,8 @@ static int launch_bwd(const void* qkv, const void* out, const void* dout, const 
 
 static int pick_nt(int L) {
   const int need = 2 * ((L + 15) / 16);
-  const int opts[4] = {4, 6, 10, 20};
-  for (int i = 0; i < 4; ++i)
+  const int opts[5] = {4, 6, 10, 20, 26};
+  for (int i = 0; i < 5; ++i)
     if (opts[i] >= need) return opts[i];
   return 0;
 }
@@ -382,17 +387,16 @@ static int pick_nt(int L) {
 
 using namespace mae;
 
-#define MAE_ATTN_DISPATCH(FN, ...)                                           \
-  switch (hd * 100 + nt) {                                                   \
-    case 2404: return FN<24, 4>(__VA_ARGS__);                                \
-    case 2406: return FN<24, 6>(__VA_ARGS__);                                \
-    case 2410: return FN<24, 10>(__VA_ARGS__);                               \
-    case 2420: return FN<24, 20>(__VA_ARGS__);                               \
-    case 3204: return FN<32, 4>(__VA_ARGS__);                                \
-    case 3206: return FN<32, 6>(__VA_ARGS__);                                \
-    case 3210: return FN<32, 10>(__VA_ARGS__);                               \
-    case 3220: return FN<32, 20>(__VA_ARGS__);                               \
-    default: return MAE_ERR_SHAPE;                                           \
+#define MAE_ATTN_CASE(FN, HDV, NTV, ...) case HDV * 100 + NTV: return FN<HDV, NTV>(__VA_ARGS__);
+#define MAE_ATTN_DISPATCH(FN, ...)                                                                            \
+  switch (hd * 100 + nt) {                                                                                    \
+    MAE_ATTN_CASE(FN, 24, 4, __VA_ARGS__) MAE_ATTN_CASE(FN, 24, 6, __VA_ARGS__) MAE_ATTN_CASE(FN, 24, 10, __VA_ARGS__) \
+    MAE_ATTN_CASE(FN, 24, 20, __VA_ARGS__) MAE_ATTN_CASE(FN, 24, 26, __VA_ARGS__)                             \
+    MAE_ATTN_CASE(FN, 32, 4, __VA_ARGS__) MAE_ATTN_CASE(FN, 32, 6, __VA_ARGS__) MAE_ATTN_CASE(FN, 32, 10, __VA_ARGS__) \
+    MAE_ATTN_CASE(FN, 32, 20, __VA_ARGS__) MAE_ATTN_CASE(FN, 32, 26, __VA_ARGS__)                             \
+    MAE_ATTN_CASE(FN, 64, 4, __VA_ARGS__) MAE_ATTN_CASE(FN, 64, 6, __VA_ARGS__) MAE_ATTN_CASE(FN, 64, 10, __VA_ARGS__) \
+    MAE_ATTN_CASE(FN, 64, 20, __VA_ARGS__) MAE_ATTN_CASE(FN, 64, 26, __VA_ARGS__)                             \
+    default: return MAE_ERR_SHAPE;                                                                            \
   }
 
 extern "C" int mae_attention_fwd(const void* qkv, int B, int L, int H, int hd, void* out, float* lse,

@@ -120,8 +120,10 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const __nv_bfloat1
 }
 
 // ---------------------------------------------------------------------------------------------
-// LayerNorm forward / backward: one warp per row, D <= 256, D % 4 == 0; lane owns columns
-// {4*lane .. 4*lane+3} and {128 + 4*lane ..}.
+// LayerNorm forward / backward: one warp per row, D <= 128*NV, D % 4 == 0; lane owns the float4 column groups
+// {128*j + 4*lane}, j < NV (NV = 2 covers configs/mae.yaml: D = 144 / 192; NV = 4 / 8 cover D <= 512 / 1024).
+// ROWS rows are processed per warp iteration with all their loads issued before the first reduction (these
+// kernels are pure HBM streams, so bytes in flight per warp is what matters).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ long long map_row(long long r, const int64_t* gather_idx, int n_sel, int L_src) {
   if (gather_idx == nullptr) return r;
@@ -129,6 +131,7 @@ __device__ __forceinline__ long long map_row(long long r, const int64_t* gather_
   return b * L_src + gather_idx[r];
 }
 
+template <int NV, int ROWS>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta,
@@ -140,149 +143,162 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
-  const int c0 = lane * 4, c1 = 128 + lane * 4;
-  const bool h0 = c0 < D, h1 = c1 < D;
-  float4 g0 = make_float4(0, 0, 0, 0), g1 = g0, b0 = g0, b1 = g0;
-  if (h0) { g0 = *reinterpret_cast<const float4*>(gamma + c0); b0 = *reinterpret_cast<const float4*>(beta + c0); }
-  if (h1) { g1 = *reinterpret_cast<const float4*>(gamma + c1); b1 = *reinterpret_cast<const float4*>(beta + c1); }
+  float4 gm[NV], bt[NV];
+  bool has[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = 128 * j + 4 * lane;
+    has[j] = c < D;
+    gm[j] = bt[j] = make_float4(0, 0, 0, 0);
+    if (has[j]) { gm[j] = *reinterpret_cast<const float4*>(gamma + c); bt[j] = *reinterpret_cast<const float4*>(beta + c); }
+  }
   const float invD = 1.0f / D;
   const long long stride = (long long)gridDim.x * wpb;
-  // two rows per iteration: both rows' loads are in flight before the first reduction
-  for (long long ra = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); ra < rows; ra += 2 * stride) {
-    float4 v[2][2];
-    long long rr[2] = {ra, ra + stride};
-    bool ok[2];
+  for (long long ra = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); ra < rows; ra += ROWS * stride) {
+    float4 v[ROWS][NV];
+    long long rr[ROWS];
+    bool ok[ROWS];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < ROWS; ++k) {
+      rr[k] = ra + k * stride;
       ok[k] = rr[k] < rows;
       if (!ok[k]) rr[k] = ra;
       const float* src = x + map_row(rr[k], gather_idx, n_sel, L_src) * D;
-      v[k][0] = v[k][1] = make_float4(0, 0, 0, 0);
-      if (h0) v[k][0] = *reinterpret_cast<const float4*>(src + c0);
-      if (h1) v[k][1] = *reinterpret_cast<const float4*>(src + c1);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        v[k][j] = make_float4(0, 0, 0, 0);
+        if (has[j]) v[k][j] = *reinterpret_cast<const float4*>(src + 128 * j + 4 * lane);
+      }
     }
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const float4 v0 = v[k][0], v1 = v[k][1];
-      const float mu = warp_sum(v0.x + v0.y + v0.z + v0.w + v1.x + v1.y + v1.z + v1.w) * invD;
+    for (int k = 0; k < ROWS; ++k) {
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) sum += v[k][j].x + v[k][j].y + v[k][j].z + v[k][j].w;
+      const float mu = warp_sum(sum) * invD;
       float sq = 0.f;
-      if (h0) { float a = v0.x - mu, b = v0.y - mu, c = v0.z - mu, d = v0.w - mu; sq += a * a + b * b + c * c + d * d; }
-      if (h1) { float a = v1.x - mu, b = v1.y - mu, c = v1.z - mu, d = v1.w - mu; sq += a * a + b * b + c * c + d * d; }
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (has[j]) {
+          const float a = v[k][j].x - mu, b = v[k][j].y - mu, c = v[k][j].z - mu, d = v[k][j].w - mu;
+          sq += a * a + b * b + c * c + d * d;
+        }
       const float rs = rsqrtf(warp_sum(sq) * invD + eps);
       if (!ok[k]) continue;
       const long long r = rr[k];
       __nv_bfloat16* dst = xn + r * D;
-      if (h0) {
-        uint2 o;
-        o.x = pack_bf16x2((v0.x - mu) * rs * g0.x + b0.x, (v0.y - mu) * rs * g0.y + b0.y);
-        o.y = pack_bf16x2((v0.z - mu) * rs * g0.z + b0.z, (v0.w - mu) * rs * g0.w + b0.w);
-        *reinterpret_cast<uint2*>(dst + c0) = o;
-      }
-      if (h1) {
-        uint2 o;
-        o.x = pack_bf16x2((v1.x - mu) * rs * g1.x + b1.x, (v1.y - mu) * rs * g1.y + b1.y);
-        o.y = pack_bf16x2((v1.z - mu) * rs * g1.z + b1.z, (v1.w - mu) * rs * g1.w + b1.w);
-        *reinterpret_cast<uint2*>(dst + c1) = o;
-      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (has[j]) {
+          uint2 o;
+          o.x = pack_bf16x2((v[k][j].x - mu) * rs * gm[j].x + bt[j].x, (v[k][j].y - mu) * rs * gm[j].y + bt[j].y);
+          o.y = pack_bf16x2((v[k][j].z - mu) * rs * gm[j].z + bt[j].z, (v[k][j].w - mu) * rs * gm[j].w + bt[j].w);
+          *reinterpret_cast<uint2*>(dst + 128 * j + 4 * lane) = o;
+        }
       if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
     }
   }
 }
 
-// Two rows per warp iteration: all 12 loads of both rows are issued before the first reduction, doubling the
-// bytes in flight per warp (the kernel is a pure HBM stream: ~3 KB per row in + out).
-__global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(
+template <int NV, int ROWS, int MINB>
+__global__ void __launch_bounds__(256, MINB) layernorm_bwd_kernel(
     const __nv_bfloat16* __restrict__ g, const float* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dx_in,
     const int64_t* __restrict__ gather_idx, int n_sel, int L_src, int rows, int D, float* __restrict__ dx_out,
     __nv_bfloat16* __restrict__ dx_out_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   pdl_trigger();
   pdl_wait();
-  __shared__ float s_dg[256], s_db[256];
+  __shared__ float s_dg[128 * NV], s_db[128 * NV];
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+  for (int i = threadIdx.x; i < 128 * NV; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
   __syncthreads();
-  const int c0 = lane * 4, c1 = 128 + lane * 4;
-  const bool h0 = c0 < D, h1 = c1 < D;
-  float4 w0 = make_float4(0, 0, 0, 0), w1 = w0;
-  if (h0) w0 = *reinterpret_cast<const float4*>(gamma + c0);
-  if (h1) w1 = *reinterpret_cast<const float4*>(gamma + c1);
-  const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-  float dg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, db[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float4 wv[NV];
+  bool has[NV];
+  float dg[NV][4], db[NV][4];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = 128 * j + 4 * lane;
+    has[j] = c < D;
+    wv[j] = make_float4(0, 0, 0, 0);
+    if (has[j]) wv[j] = *reinterpret_cast<const float4*>(gamma + c);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { dg[j][e] = 0.f; db[j][e] = 0.f; }
+  }
   const float invD = 1.0f / D;
   const long long stride = (long long)gridDim.x * wpb;
-  for (long long ra = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); ra < rows; ra += 2 * stride) {
-    long long rrow[2] = {ra, ra + stride};
-    long long xr[2];
-    bool ok[2];
-    uint2 gg[2][2];
-    float4 xv[2][2], di[2][2];
-    float mu[2], rs[2];
+  for (long long ra = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); ra < rows; ra += ROWS * stride) {
+    long long rrow[ROWS], xr[ROWS];
+    bool ok[ROWS];
+    uint2 gg[ROWS][NV];
+    float4 xv[ROWS][NV], di[ROWS][NV];
+    float mu[ROWS], rs[ROWS];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < ROWS; ++k) {
+      rrow[k] = ra + k * stride;
       ok[k] = rrow[k] < rows;
       if (!ok[k]) rrow[k] = ra;
       xr[k] = map_row(rrow[k], gather_idx, n_sel, L_src);
       mu[k] = mean[rrow[k]]; rs[k] = rstd[rrow[k]];
-      gg[k][0] = gg[k][1] = make_uint2(0, 0);
-      xv[k][0] = xv[k][1] = di[k][0] = di[k][1] = make_float4(0, 0, 0, 0);
-      if (h0) {
-        gg[k][0] = *reinterpret_cast<const uint2*>(g + rrow[k] * D + c0);
-        xv[k][0] = *reinterpret_cast<const float4*>(x + xr[k] * D + c0);
-        if (dx_in) di[k][0] = *reinterpret_cast<const float4*>(dx_in + xr[k] * D + c0);
-      }
-      if (h1) {
-        gg[k][1] = *reinterpret_cast<const uint2*>(g + rrow[k] * D + c1);
-        xv[k][1] = *reinterpret_cast<const float4*>(x + xr[k] * D + c1);
-        if (dx_in) di[k][1] = *reinterpret_cast<const float4*>(dx_in + xr[k] * D + c1);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c = 128 * j + 4 * lane;
+        gg[k][j] = make_uint2(0, 0);
+        xv[k][j] = di[k][j] = make_float4(0, 0, 0, 0);
+        if (has[j]) {
+          gg[k][j] = *reinterpret_cast<const uint2*>(g + rrow[k] * D + c);
+          xv[k][j] = *reinterpret_cast<const float4*>(x + xr[k] * D + c);
+          if (dx_in) di[k][j] = *reinterpret_cast<const float4*>(dx_in + xr[k] * D + c);
+        }
       }
     }
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const float gv[8] = {bf16_lo(gg[k][0].x), bf16_hi(gg[k][0].x), bf16_lo(gg[k][0].y), bf16_hi(gg[k][0].y),
-                           bf16_lo(gg[k][1].x), bf16_hi(gg[k][1].x), bf16_lo(gg[k][1].y), bf16_hi(gg[k][1].y)};
-      float xh[8] = {(xv[k][0].x - mu[k]) * rs[k], (xv[k][0].y - mu[k]) * rs[k], (xv[k][0].z - mu[k]) * rs[k],
-                     (xv[k][0].w - mu[k]) * rs[k], (xv[k][1].x - mu[k]) * rs[k], (xv[k][1].y - mu[k]) * rs[k],
-                     (xv[k][1].z - mu[k]) * rs[k], (xv[k][1].w - mu[k]) * rs[k]};
-      if (!h0) { xh[0] = xh[1] = xh[2] = xh[3] = 0.f; }
-      if (!h1) { xh[4] = xh[5] = xh[6] = xh[7] = 0.f; }
-      float s1 = 0.f, s2 = 0.f, dxh[8];
+    for (int k = 0; k < ROWS; ++k) {
       const float live = ok[k] ? 1.f : 0.f;  // the duplicate row of a ragged tail must not count twice
+      float s1 = 0.f, s2 = 0.f;
+      float xh[NV][4], dxh[NV][4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        dg[i] += live * gv[i] * xh[i];
-        db[i] += live * gv[i];
-        dxh[i] = gv[i] * wv[i];
-        s1 += dxh[i];
-        s2 += dxh[i] * xh[i];
+      for (int j = 0; j < NV; ++j) {
+        const float gv[4] = {bf16_lo(gg[k][j].x), bf16_hi(gg[k][j].x), bf16_lo(gg[k][j].y), bf16_hi(gg[k][j].y)};
+        const float xs[4] = {xv[k][j].x, xv[k][j].y, xv[k][j].z, xv[k][j].w};
+        const float ws[4] = {wv[j].x, wv[j].y, wv[j].z, wv[j].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          xh[j][e] = has[j] ? (xs[e] - mu[k]) * rs[k] : 0.f;
+          dg[j][e] += live * gv[e] * xh[j][e];
+          db[j][e] += live * gv[e];
+          dxh[j][e] = gv[e] * ws[e];
+          s1 += dxh[j][e];
+          s2 += dxh[j][e] * xh[j][e];
+        }
       }
       s1 = warp_sum(s1) * invD;
       s2 = warp_sum(s2) * invD;
-      float o[8];
+      if (!ok[k]) continue;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = rs[k] * (dxh[i] - s1 - xh[i] * s2);
-      o[0] += di[k][0].x; o[1] += di[k][0].y; o[2] += di[k][0].z; o[3] += di[k][0].w;
-      o[4] += di[k][1].x; o[5] += di[k][1].y; o[6] += di[k][1].z; o[7] += di[k][1].w;
-      if (ok[k]) {
-        if (h0) {
-          *reinterpret_cast<float4*>(dx_out + xr[k] * D + c0) = make_float4(o[0], o[1], o[2], o[3]);
+      for (int j = 0; j < NV; ++j)
+        if (has[j]) {
+          const int c = 128 * j + 4 * lane;
+          float4 o;
+          o.x = rs[k] * (dxh[j][0] - s1 - xh[j][0] * s2) + di[k][j].x;
+          o.y = rs[k] * (dxh[j][1] - s1 - xh[j][1] * s2) + di[k][j].y;
+          o.z = rs[k] * (dxh[j][2] - s1 - xh[j][2] * s2) + di[k][j].z;
+          o.w = rs[k] * (dxh[j][3] - s1 - xh[j][3] * s2) + di[k][j].w;
+          *reinterpret_cast<float4*>(dx_out + xr[k] * D + c) = o;
           if (dx_out_bf16)
-            *reinterpret_cast<uint2*>(dx_out_bf16 + xr[k] * D + c0) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+            *reinterpret_cast<uint2*>(dx_out_bf16 + xr[k] * D + c) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
         }
-        if (h1) {
-          *reinterpret_cast<float4*>(dx_out + xr[k] * D + c1) = make_float4(o[4], o[5], o[6], o[7]);
-          if (dx_out_bf16)
-            *reinterpret_cast<uint2*>(dx_out_bf16 + xr[k] * D + c1) = make_uint2(pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-        }
-      }
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (h0) { atomicAdd(&s_dg[c0 + i], dg[i]); atomicAdd(&s_db[c0 + i], db[i]); }
-    if (h1) { atomicAdd(&s_dg[c1 + i], dg[4 + i]); atomicAdd(&s_db[c1 + i], db[4 + i]); }
-  }
+  for (int j = 0; j < NV; ++j)
+    if (has[j]) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        atomicAdd(&s_dg[128 * j + 4 * lane + e], dg[j][e]);
+        atomicAdd(&s_db[128 * j + 4 * lane + e], db[j][e]);
+      }
+    }
   __syncthreads();
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
     atomicAdd(dgamma + i, s_dg[i]);
@@ -458,28 +474,35 @@ __global__ void __launch_bounds__(256) gather_rows_bf16_kernel(const float* __re
   }
 }
 
+template <int NV>
 __global__ void __launch_bounds__(256) colsum_rows_f32_kernel(const float* __restrict__ src,
                                                              const int64_t* __restrict__ idx, int B, int n_sel,
                                                              int L_src, int row_offset, int D,
                                                              float* __restrict__ out) {
   pdl_trigger();
   pdl_wait();
-  // one warp per row (grid-stride), lane owns columns {4*lane..} and {128+4*lane..}; block-level smem reduce
-  __shared__ float s_acc[256];
+  // one warp per row (grid-stride), lane owns the float4 column groups {128*j + 4*lane}; block-level smem reduce
+  __shared__ float s_acc[128 * NV];
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_acc[i] = 0.f;
+  for (int i = threadIdx.x; i < 128 * NV; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
-  const int c0 = lane * 4, c1 = 128 + lane * 4;
-  const bool h0 = c0 < D, h1 = c1 < D;
-  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+  float4 a[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   const long long nrows = (long long)B * n_sel;
   for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < nrows; r += (long long)gridDim.x * wpb) {
     const float* row = src + sel_row(r, idx, n_sel, L_src, row_offset) * D;
-    if (h0) { const float4 v = *reinterpret_cast<const float4*>(row + c0); a0.x += v.x; a0.y += v.y; a0.z += v.z; a0.w += v.w; }
-    if (h1) { const float4 v = *reinterpret_cast<const float4*>(row + c1); a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w; }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = 128 * j + 4 * lane;
+      if (c < D) { const float4 v = *reinterpret_cast<const float4*>(row + c); a[j].x += v.x; a[j].y += v.y; a[j].z += v.z; a[j].w += v.w; }
+    }
   }
-  if (h0) { atomicAdd(&s_acc[c0], a0.x); atomicAdd(&s_acc[c0 + 1], a0.y); atomicAdd(&s_acc[c0 + 2], a0.z); atomicAdd(&s_acc[c0 + 3], a0.w); }
-  if (h1) { atomicAdd(&s_acc[c1], a1.x); atomicAdd(&s_acc[c1 + 1], a1.y); atomicAdd(&s_acc[c1 + 2], a1.z); atomicAdd(&s_acc[c1 + 3], a1.w); }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = 128 * j + 4 * lane;
+    if (c < D) { atomicAdd(&s_acc[c], a[j].x); atomicAdd(&s_acc[c + 1], a[j].y); atomicAdd(&s_acc[c + 2], a[j].z); atomicAdd(&s_acc[c + 3], a[j].w); }
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < D; i += blockDim.x) atomicAdd(out + i, s_acc[i]);
 }
@@ -632,9 +655,15 @@ extern "C" int mae_layernorm_fwd(const float* x, const float* gamma, const float
                                  cudaStream_t stream) {
   if (rows <= 0) return MAE_OK;
   if (!x || !gamma || !beta || !xn || !mean || !rstd) return MAE_ERR_NULL;
-  if (D > 256 || (D % 4) || (gather_idx && (n_sel <= 0 || L_src <= 0))) return MAE_ERR_SHAPE;
-  mae_launch(layernorm_fwd_kernel, dim3(grid_for(rows, 8)), dim3(256), 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps,
-                                                             reinterpret_cast<__nv_bfloat16*>(xn), mean, rstd);
+  if (D > 1024 || (D % 4) || (gather_idx && (n_sel <= 0 || L_src <= 0))) return MAE_ERR_SHAPE;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(xn);
+  const dim3 grid(grid_for(rows, 8)), block(256);
+  if (D <= 256)
+    mae_launch(layernorm_fwd_kernel<2, 2>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd);
+  else if (D <= 512)
+    mae_launch(layernorm_fwd_kernel<4, 2>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd);
+  else
+    mae_launch(layernorm_fwd_kernel<8, 1>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd);
   return MAE_CHECK_LAUNCH();
 }
 
@@ -644,9 +673,16 @@ extern "C" int mae_layernorm_bwd(const void* g, const float* x, const float* mea
                                  float* dbeta, cudaStream_t stream) {
   if (rows <= 0) return MAE_OK;
   if (!g || !x || !mean || !rstd || !gamma || !dx_out || !dgamma || !dbeta) return MAE_ERR_NULL;
-  if (D > 256 || (D % 4) || (gather_idx && (n_sel <= 0 || L_src <= 0))) return MAE_ERR_SHAPE;
-  mae_launch(layernorm_bwd_kernel, dim3(grid_for(rows, 8, 148 * 8)), dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(g), x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out,
-      reinterpret_cast<__nv_bfloat16*>(dx_out_bf16), dgamma, dbeta);
+  if (D > 1024 || (D % 4) || (gather_idx && (n_sel <= 0 || L_src <= 0))) return MAE_ERR_SHAPE;
+  const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(g);
+  __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(dx_out_bf16);
+  const dim3 grid(grid_for(rows, 8, 148 * 8)), block(256);
+  if (D <= 256)
+    mae_launch(layernorm_bwd_kernel<2, 2, 3>, grid, block, 0, stream, gp, x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out, ob, dgamma, dbeta);
+  else if (D <= 512)
+    mae_launch(layernorm_bwd_kernel<4, 1, 2>, grid, block, 0, stream, gp, x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out, ob, dgamma, dbeta);
+  else
+    mae_launch(layernorm_bwd_kernel<8, 1, 1>, grid, block, 0, stream, gp, x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out, ob, dgamma, dbeta);
   return MAE_CHECK_LAUNCH();
 }
 
@@ -704,9 +740,12 @@ extern "C" int mae_colsum_rows_f32(const float* src, const int64_t* idx, int B, 
                                    int D, float* out, cudaStream_t stream) {
   if (B <= 0 || n_sel <= 0) return MAE_OK;
   if (!src || !out) return MAE_ERR_NULL;
-  if (D > 256 || (D % 4)) return MAE_ERR_SHAPE;
+  if (D > 1024 || (D % 4)) return MAE_ERR_SHAPE;
   const long long nrows = (long long)B * n_sel;
-  mae_launch(colsum_rows_f32_kernel, dim3(grid_for(nrows, 8, 148 * 4)), dim3(256), 0, stream, src, idx, B, n_sel, L_src, row_offset, D, out);
+  const dim3 grid(grid_for(nrows, 8, 148 * 4)), block(256);
+  if (D <= 256) mae_launch(colsum_rows_f32_kernel<2>, grid, block, 0, stream, src, idx, B, n_sel, L_src, row_offset, D, out);
+  else if (D <= 512) mae_launch(colsum_rows_f32_kernel<4>, grid, block, 0, stream, src, idx, B, n_sel, L_src, row_offset, D, out);
+  else mae_launch(colsum_rows_f32_kernel<8>, grid, block, 0, stream, src, idx, B, n_sel, L_src, row_offset, D, out);
   return MAE_CHECK_LAUNCH();
 }
 
@@ -718,11 +757,13 @@ extern "C" int mae_cast_bf16(const float* src, void* dst, long long n, cudaStrea
 }
 
 extern "C" int mae_transpose_cast_bf16(const float* src, void* dst, const long long* table, int n_entries,
-                                       cudaStream_t stream) {
+                                       int max_rows, int max_cols, cudaStream_t stream) {
   if (n_entries <= 0) return MAE_OK;
   if (!src || !dst || !table) return MAE_ERR_NULL;
-  // grid covers the largest weight (<= 1024 x 1024); smaller entries exit early
-  mae_launch(transpose_cast_kernel, dim3(dim3(32, 32, n_entries)), dim3(256), 0, stream, src, reinterpret_cast<__nv_bfloat16*>(dst), table);
+  if (max_rows <= 0 || max_cols <= 0) return MAE_ERR_SHAPE;
+  // grid covers the largest weight of the table; blocks outside a smaller entry exit early
+  mae_launch(transpose_cast_kernel, dim3((max_cols + 31) / 32, (max_rows + 31) / 32, n_entries), dim3(256), 0, stream, src,
+             reinterpret_cast<__nv_bfloat16*>(dst), table);
   return MAE_CHECK_LAUNCH();
 }
 

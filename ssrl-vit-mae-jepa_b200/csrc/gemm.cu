@@ -431,8 +431,9 @@ extern "C" int mae_gemm_tn(const void* A, const void* B, int M, int N, int K, in
 
 // ---------------------------------------------------------------------------------------------
 // gemm_wgrad:  O[p, q] (+)= sum_m P[m, p] * Q[m, q]     (fp32 atomics into `out`)
-//   P: bf16 [M, Pc] row-major, Q: bf16 [M, Qc] row-major, Qc <= 256, Qc % 16 == 0.
-//   grid = (ceil(Pc/128), msplit);  each CTA reduces its own M range into one TMEM accumulator.
+//   P: bf16 [M, Pc] row-major, Q: bf16 [M, Qc] row-major, Qc % 16 == 0.
+//   grid = (ceil(Pc/128), msplit, ceil(Qc/256));  each CTA reduces its own M range of one 128 x <=256 output
+//   tile into one TMEM accumulator.
 //   out element (p, q) lives at out[p * so_p + q * so_q].
 // ---------------------------------------------------------------------------------------------
 namespace mae {
@@ -469,6 +470,10 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int pc = blockIdx.x;
+  const int q0 = blockIdx.z * 256;                       // first Q column of this CTA's output tile
+  const int Qn = (p.Qc - q0) < 256 ? (p.Qc - q0) : 256;  // its width (multiple of 16)
+  const int nqb = (Qn + 63) >> 6;                        // TMA boxes of Q actually loaded per stage
+  const uint32_t tx_bytes = p_bytes + uint32_t(nqb) * box_bytes;
   const int m_begin = blockIdx.y * p.rows_per_cta;
   int m_end = m_begin + p.rows_per_cta;
   if (m_end > p.M) m_end = p.M;
@@ -496,17 +501,17 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
           const int m0 = m_begin + mb * WR;
           mbar_wait(&hdr->empty[stage], phase ^ 1);
           uint8_t* sp = smem + stage * stage_bytes;
-          mbar_expect_tx(&hdr->full[stage], stage_bytes);
+          mbar_expect_tx(&hdr->full[stage], tx_bytes);
           tma_load_2d(sp, &mapP, &hdr->full[stage], pc * 128, m0);
           tma_load_2d(sp + box_bytes, &mapP, &hdr->full[stage], pc * 128 + 64, m0);
-          for (int j = 0; j < p.nqb; ++j)
-            tma_load_2d(sp + p_bytes + j * box_bytes, &mapQ, &hdr->full[stage], j * 64, m0);
+          for (int j = 0; j < nqb; ++j)
+            tma_load_2d(sp + p_bytes + j * box_bytes, &mapQ, &hdr->full[stage], q0 + j * 64, m0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        const uint32_t idesc = umma_idesc_bf16(BM, p.Qc, 1, 1);
+        const uint32_t idesc = umma_idesc_bf16(BM, Qn, 1, 1);
         int stage = 0; uint32_t phase = 0;
         for (int mb = 0; mb < nmb; ++mb) {
           mbar_wait(&hdr->full[stage], phase);
@@ -535,8 +540,8 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
         // Within a 128B-swizzled box the chunk of row r sits at (cc ^ (r&7)) = (cc ^ rg): constant per thread.
         const int t = (warp - 2) * 32 + lane;
         const bool of_q = p.colsum_of_q != 0;
-        const bool active = !of_q || blockIdx.x == 0;
-        const int nbox = of_q ? p.nqb : 2;
+        const bool active = of_q ? (blockIdx.x == 0) : (blockIdx.z == 0);  // each column summed by exactly one CTA row
+        const int nbox = of_q ? nqb : 2;
         const uint32_t tile_off = of_q ? p_bytes : 0u;
         const int cc = t & 7, rg = (t >> 3) & 7;
         const uint32_t thr_off = uint32_t(rg) * 128u + (uint32_t(cc ^ rg) << 4);
@@ -569,7 +574,7 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         if (active) {
-          const int col_base = of_q ? 0 : pc * 128;
+          const int col_base = of_q ? q0 : pc * 128;
           const int ncols = of_q ? p.Qc : p.Pc;
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
@@ -589,11 +594,11 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
       tc_fence_after();
       const int prow = pc * 128 + q * 32 + lane;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
-      for (int c0 = 0; c0 < p.Qc; c0 += 16) {
+      for (int c0 = 0; c0 < Qn; c0 += 16) {
         float v[16];
         tmem_ld16(taddr + c0, v);
         if (prow < p.Pc) {
-          float* o = p.out + (long long)prow * p.so_p + (long long)c0 * p.so_q;
+          float* o = p.out + (long long)prow * p.so_p + (long long)(q0 + c0) * p.so_q;
           if (p.so_q == 1 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
             // 16 consecutive floats of one dW row: four 16-byte vector reductions instead of 16 scalar ones
 #pragma unroll
@@ -620,14 +625,15 @@ extern "C" int mae_gemm_wgrad(const void* P, int Pc, const void* Q, int Qc, int 
                               long long so_q, float* colsum, int colsum_of_q, cudaStream_t stream) {
   if (M <= 0) return MAE_OK;
   if (!P || !Q || !out) return MAE_ERR_NULL;
-  if (Pc <= 0 || Qc <= 0 || Qc > 256 || (Qc % 16) || (Pc % 8)) return MAE_ERR_SHAPE;
+  if (Pc <= 0 || Qc <= 0 || (Qc % 16) || (Pc % 8)) return MAE_ERR_SHAPE;
   WgradParams p;
   p.M = M; p.Pc = Pc; p.Qc = Qc;
-  p.nqb = (Qc + 63) / 64;
+  const int qchunks = (Qc + 255) / 256;
+  p.nqb = Qc >= 256 ? 4 : (Qc + 63) / 64;  // smem is laid out for the widest chunk
   p.out = out; p.so_p = so_p; p.so_q = so_q;
   p.colsum = colsum; p.colsum_of_q = colsum_of_q;
   const int pchunks = (Pc + 127) / 128;
-  int msplit = num_sms() / pchunks;
+  int msplit = num_sms() / (pchunks * qchunks);
   if (msplit < 1) msplit = 1;
   int rows = (M + msplit - 1) / msplit;
   rows = ((rows + WR - 1) / WR) * WR;
@@ -645,6 +651,6 @@ extern "C" int mae_gemm_wgrad(const void* P, int Pc, const void* Q, int Qc, int 
       return MAE_ERR_LAUNCH;
     attr_done = true;
   }
-  mae_launch(gemm_wgrad_kernel, dim3(dim3(pchunks, msplit)), dim3(kWgradThreads), smem, stream, p, mp, mq);
+  mae_launch(gemm_wgrad_kernel, dim3(pchunks, msplit, qchunks), dim3(kWgradThreads), smem, stream, p, mp, mq);
   return cudaGetLastError() == cudaSuccess ? MAE_OK : MAE_ERR_LAUNCH;
 }

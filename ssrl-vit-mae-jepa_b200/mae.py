@@ -215,6 +215,7 @@ class MAEEngine:
             if n.endswith(".weight") and p.dim() == 2:
                 rows.append([self.offsets[n], p.shape[0], p.shape[1], self.offsets[n]])
         self.t_table = torch.tensor(rows, dtype=torch.int64, device=device)
+        self.t_max_rows, self.t_max_cols = max(r[1] for r in rows), max(r[2] for r in rows)
         self._shadow_version = -1
         self._index_blocks()
 
@@ -245,7 +246,7 @@ class MAEEngine:
             return
         calls.mae_cast_bf16(self.flat.data_ptr(), self.flat_bf16.data_ptr(), self.n_total, stream)
         calls.mae_transpose_cast_bf16(self.flat.data_ptr(), self.flat_bf16_t.data_ptr(), self.t_table.data_ptr(),
-                                      self.t_table.shape[0], stream)
+                                      self.t_table.shape[0], self.t_max_rows, self.t_max_cols, stream)
         self._shadow_version = self.flat._version
 
     # pointers into the flat buffers (element offsets -> byte addresses)
@@ -408,8 +409,9 @@ class MAEEngine:
 
     # ---------------- backward ----------------
     def _linear_bwd_w(self, dy: int, n_out: int, x: int, n_in: int, M: int, w_off: int, b_off: int, st: int) -> None:
-        """dW (n_out, n_in) += dY^T X and db += colsum(dY).  The wider operand rides the MMA M axis."""
-        if n_in <= 256 and n_in % 16 == 0:
+        """dW (n_out, n_in) += dY^T X and db += colsum(dY), bias gradient fused into the same launch.  The wider
+        operand rides the MMA M axis (chunks of 128), the narrower one the MMA N axis (chunks of <= 256)."""
+        if n_in <= n_out:
             calls.mae_gemm_wgrad(dy, n_out, x, n_in, M, self.pg(w_off), n_in, 1, self.pg(b_off), 0, st)
         else:
             calls.mae_gemm_wgrad(x, n_in, dy, n_out, M, self.pg(w_off), 1, n_in, self.pg(b_off), 1, st)
@@ -510,7 +512,7 @@ class MAEEngine:
                              betas[1], eps, weight_decay, max_norm, self.step_count, self.partials.data_ptr(), nparts,
                              self.grad_norm.data_ptr(), st)
         calls.mae_transpose_cast_bf16(self.flat.data_ptr(), self.flat_bf16_t.data_ptr(), self.t_table.data_ptr(),
-                                      self.t_table.shape[0], st)
+                                      self.t_table.shape[0], self.t_max_rows, self.t_max_cols, st)
         self._shadow_version = self.flat._version
         return self.grad_norm
 
@@ -573,10 +575,11 @@ class MaskedAutoencoder(nn.Module):
         if len(dec.decoder_blocks):
             dims.append((dec.decoder_embed.out_features, dec.decoder_blocks[0].attn.num_heads))
         for D, H in dims:
-            if D % 16 or D > 256 or D // H not in (24, 32):
-                raise NotImplementedError(f"kernels cover embed dims <= 256 (mult. of 16) with head_dim 24/32; got {D}/{H}")
-        if pd % 16 or self.sequence_length > 160:
-            raise NotImplementedError("kernels cover patch_dim % 16 == 0 and sequence_length <= 160")
+            if D % 16 or D > 1024 or D // H not in (24, 32, 64):
+                raise NotImplementedError(
+                    f"kernels cover embed dims <= 1024 (multiple of 16) with head_dim 24/32/64; got {D}/{H}")
+        if pd % 16 or pd > 768 or self.sequence_length > 208:
+            raise NotImplementedError("kernels cover patch_dim % 16 == 0, patch_dim <= 768 and sequence_length <= 208")
 
     @property
     def engine(self) -> MAEEngine:
@@ -615,7 +618,7 @@ class MaskedAutoencoder(nn.Module):
         if idx_keep is None:
             idx_keep = torch.arange(L, device=images.device).unsqueeze(0).expand(B, -1)
         idx_keep = idx_keep.to(torch.int64).contiguous()
-        if idx_keep.shape[1] > 160:
+        if idx_keep.shape[1] > 208:
             raise NotImplementedError("sequence too long for the fused attention kernel")
         eng._ensure_ws(B, idx_keep.shape[1], images.device)
         st = torch.cuda.current_stream(images.device).cuda_stream

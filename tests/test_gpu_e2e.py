@@ -144,3 +144,47 @@ def test_full_size_batch_properties():
         l = tr.train_step(images, noise)
     report("e2e_full", loss0=l0.item(), loss3=l.item(), grad_norm=mod.model.engine.grad_norm.item())
     assert torch.isfinite(l) and l.item() < l0.item()  # same batch: the loss must go down
+
+
+VITB = {"general": {"image_size": 224, "patch_size": 16, "in_chans": 3},
+        "encoder": {"embed_dim": 768, "depth": 12, "num_heads": 12},
+        "decoder": {"decoder_embed_dim": 512, "decoder_depth": 8, "decoder_num_heads": 16}}
+
+
+def test_vit_b16_stress_config_parity():
+    """BASELINE.json config #5 (ViT-B/16 MAE: 224 px, 196 patches, L=197, keep 49, 768-d x12 x12h encoder, 512-d x8 x16h
+    decoder, head_dim 64 / 32) at a batch the CPU oracle finishes in seconds.  20 bf16 layers deep, so the
+    gradient tolerance is cosine >= 0.995 / rel-L2 <= 8e-2 (loss rel 3e-3, pred max-abs 5e-2)."""
+    torch.manual_seed(3)
+    g = dict(VITB["general"]); g["mask_ratio"] = 0.75
+    o = O.MaskedAutoencoder(g, VITB["encoder"], VITB["decoder"])
+    m = P.MaskedAutoencoder(g, VITB["encoder"], VITB["decoder"]).to("cuda")
+    m.load_state_dict(o.state_dict())
+    assert sum(p.numel() for p in m.parameters()) == sum(p.numel() for p in o.parameters())
+    gen = torch.Generator().manual_seed(4)
+    images, noise = torch.randn(3, 3, 224, 224, generator=gen), torch.rand(3, 197, generator=gen)
+    loss, pred, mask = m.forward_loss(images.cuda(), noise=noise.cuda())
+    l_ref, p_ref, _, g_ref = O.loss_and_grads(o, images, noise)
+    k_ref, m_ref = O.random_token_mask_from_noise(noise, 0.75)
+    ws = m.engine.ws
+    assert torch.equal(ws["idx_keep"].cpu(), k_ref) and torch.equal(ws["idx_mask"].cpu(), m_ref)
+    assert pred.shape == (3, 148, 768) and mask.sum().item() == 3 * 148
+    e, lrel = max_err(pred.cpu(), p_ref), abs(loss.item() - l_ref.item()) / l_ref.item()
+    report("e2e_vitb", pred_max=e, pred_rel=rel_err(pred.cpu(), p_ref), loss=loss.item(), loss_rel=lrel)
+    assert e < 5e-2 and lrel < 3e-3
+    m.engine.backward()
+    mine = m.engine.named_grads()
+    assert set(mine) == set(g_ref)
+    worst_cos, worst_rel = 1.0, 0.0
+    for n in sorted(g_ref):
+        a, b = mine[n].float().cpu(), g_ref[n]
+        if b.norm().item() < 1e-3:
+            continue
+        c, r = cos_sim(a, b), rel_err(a, b)
+        worst_cos, worst_rel = min(worst_cos, c), max(worst_rel, r)
+        assert c >= 0.995 and r <= 8e-2, (n, c, r)
+    report("e2e_vitb_grad_summary", worst_cos=worst_cos, worst_rel=worst_rel)
+    mod_lr = 1e-3
+    m.engine.clip_adamw(mod_lr)
+    torch.cuda.synchronize()
+    assert torch.isfinite(m.encoder.vit.blocks[0].attn.qkv.weight).all()

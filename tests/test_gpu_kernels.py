@@ -84,7 +84,7 @@ def test_gather_patches_and_assemble():
     assert max_err(x, full) < 1e-6
 
 
-@pytest.mark.parametrize("rows,D", [(1000, 144), (777, 192), (5, 16), (300, 256)])
+@pytest.mark.parametrize("rows,D", [(1000, 144), (777, 192), (5, 16), (300, 256), (500, 512), (401, 768), (97, 1024)])
 def test_layernorm_fwd_bwd(rows, D):
     g = torch.Generator().manual_seed(rows)
     x = (torch.randn(rows, D, generator=g) * 2 + 0.5).to(dev)
@@ -182,7 +182,7 @@ def test_gemm_tn_epilogues():
 
 
 WGRAD_SHAPES = [(64, 128, 64), (1000, 432, 144), (1000, 144, 144), (5000, 768, 192), (70000, 576, 144), (333, 192, 192),
-                (218000, 192, 192)]
+                (218000, 192, 192), (3000, 2304, 768), (1000, 768, 512), (900, 512, 304)]
 
 
 @pytest.mark.parametrize("M,Pc,Qc", WGRAD_SHAPES)
@@ -207,7 +207,8 @@ def test_gemm_wgrad(M, Pc, Qc):
 
 
 @pytest.mark.parametrize("B,L,H,hd", [(3, 36, 6, 24), (2, 145, 6, 32), (2, 145, 6, 24), (5, 17, 2, 32), (2, 73, 6, 24),
-                                      (1, 160, 1, 32), (1, 1, 1, 24)])
+                                      (1, 160, 1, 32), (1, 1, 1, 24), (2, 49, 12, 64), (2, 197, 16, 32), (1, 197, 12, 64),
+                                      (1, 208, 2, 64), (2, 99, 3, 64)])
 def test_attention_fwd_bwd(B, L, H, hd):
     D = H * hd
     g = torch.Generator().manual_seed(L * 7 + hd)
@@ -299,12 +300,14 @@ def test_casts_and_clip_adamw():
     dst = torch.empty(n, dtype=torch.bfloat16, device=dev)
     calls.mae_cast_bf16(p(src), p(dst), n, stream())
     assert torch.equal(dst, bf(src))
-    flat = torch.randn(4096 + 432 * 144 + 64, generator=g).to(dev)
-    tbl = torch.tensor([[0, 48, 64, 0], [4096, 432, 144, 4096]], dtype=torch.int64, device=dev)
+    o3 = 4096 + 432 * 144 + 64
+    flat = torch.randn(o3 + 3072 * 768, generator=g).to(dev)
+    tbl = torch.tensor([[0, 48, 64, 0], [4096, 432, 144, 4096], [o3, 3072, 768, o3]], dtype=torch.int64, device=dev)
     dt = torch.zeros(flat.numel(), dtype=torch.bfloat16, device=dev)
-    calls.mae_transpose_cast_bf16(p(flat), p(dt), p(tbl), 2, stream())
+    calls.mae_transpose_cast_bf16(p(flat), p(dt), p(tbl), 3, 3072, 768, stream())
     assert torch.equal(dt[:48 * 64].view(64, 48), bf(flat[:48 * 64].view(48, 64).t()))
     assert torch.equal(dt[4096:4096 + 432 * 144].view(144, 432), bf(flat[4096:4096 + 432 * 144].view(432, 144).t()))
+    assert torch.equal(dt[o3:].view(768, 3072), bf(flat[o3:].view(3072, 768).t()))
     # clip + AdamW, three steps, against the oracle's explicit restatement
     pr = torch.randn(n, generator=g)
     gr = torch.randn(n, generator=g) * 0.01

@@ -28,7 +28,11 @@ def test_constructor_defaults_and_attributes():
     with pytest.raises(AssertionError):
         P.MaskedAutoencoder({}, {}, {})
     with pytest.raises(NotImplementedError):
-        P.MaskedAutoencoder({"patch_size": 8}, {"embed_dim": 384, "depth": 2}, {"decoder_embed_dim": 192, "decoder_depth": 1})
+        P.MaskedAutoencoder({"patch_size": 8}, {"embed_dim": 160, "depth": 2, "num_heads": 4},  # head_dim 40
+                            {"decoder_embed_dim": 192, "decoder_depth": 1})
+    vitb = P.MaskedAutoencoder({"image_size": 224, "patch_size": 16}, {"embed_dim": 768, "depth": 1, "num_heads": 12},
+                               {"decoder_embed_dim": 512, "decoder_depth": 1, "decoder_num_heads": 16})
+    assert vitb.sequence_length == 197 and P.num_keep_tokens(197, 0.75) == 49
 
 
 def test_state_dict_is_interchangeable_with_reference_layout():
