@@ -438,3 +438,22 @@ class OracleTrainer:
         torch.nn.utils.clip_grad_norm_(self.model.parameters(), 1.0)
         self.opt.step()
         return loss.detach()
+
+
+# --------------------------------------------------------------------------------------
+# Downstream classifier restatement (reference src/models/classifier.py:10-57)
+# --------------------------------------------------------------------------------------
+class ViTClassifier(nn.Module):
+    """``encoder.forward_features`` -> CLS / mean pooling -> ``head.classification`` Linear."""
+
+    def __init__(self, encoder: VisionTransformer, num_classes: int = 10, pool: str = "cls"):
+        super().__init__()
+        self.encoder = encoder
+        self.pool_type = pool
+        self.head = nn.Module()
+        self.head.classification = nn.Linear(encoder.embed_dim, num_classes)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        feats = self.encoder.forward_features(x)
+        pooled = feats[:, 0] if self.pool_type == "cls" else feats.mean(dim=1)
+        return self.head.classification(pooled)

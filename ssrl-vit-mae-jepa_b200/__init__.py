@@ -5,3 +5,4 @@ from .build import build  # noqa: F401
 from .mae import MAEEngine, MaskedAutoencoder, num_keep_tokens, sincos_2d  # noqa: F401
 from . import training  # noqa: F401
 from .training import DevicePrefetcher, FusedTrainer, MAEPretrainModule  # noqa: F401
+from .classifier import ClassificationHead, ViTClassifier, ViTClassifierTrainModule, ViTEngine, VisionTransformer  # noqa: F401

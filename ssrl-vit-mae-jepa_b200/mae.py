@@ -57,7 +57,7 @@ class _Block(_HolderMixin, nn.Module):
 class _PatchEmbed(_HolderMixin, nn.Module):
     def __init__(self, img_size: int, patch_size: int, in_chans: int, embed_dim: int):
         super().__init__()
-        self.img_size, self.patch_size = img_size, patch_size
+        self.img_size, self.patch_size, self.in_chans = img_size, patch_size, in_chans
         self.grid_size = img_size // patch_size
         self.num_patches = self.grid_size**2
         self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size, bias=True)
@@ -89,16 +89,33 @@ def _init_linear_ln(root: nn.Module) -> None:
 
 
 class _VisionTransformer(_HolderMixin, nn.Module):
-    """Holder with timm ``VisionTransformer`` parameter names (``src/models/mae.py:28-36``)."""
+    """Holder with timm ``VisionTransformer`` parameter names (``src/models/mae.py:28-36``).  Also usable on its
+    own like ``timm.models.vision_transformer.VisionTransformer(img_size, patch_size, in_chans, embed_dim, depth,
+    num_heads, num_classes=0)`` (reference ``src/training/classifier.py:47-55``): ``forward_features`` runs the
+    B200 kernels over all tokens (see ``classifier.py``)."""
 
-    def __init__(self, img_size, patch_size, in_chans, embed_dim, depth, num_heads):
+    def __init__(self, img_size=96, patch_size=8, in_chans=3, embed_dim=144, depth=4, num_heads=6, num_classes=0):
         super().__init__()
+        if num_classes != 0:
+            raise NotImplementedError("only the headless ViT (num_classes=0) used by the reference is provided")
         self.embed_dim, self.num_heads, self.num_prefix_tokens = embed_dim, num_heads, 1
         self.patch_embed = _PatchEmbed(img_size, patch_size, in_chans, embed_dim)
         self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
         self.pos_embed = nn.Parameter(torch.randn(1, self.patch_embed.num_patches + 1, embed_dim) * 0.02)
         self.blocks = nn.Sequential(*[_Block(embed_dim, num_heads) for _ in range(depth)])
         self.norm = nn.LayerNorm(embed_dim, eps=LN_EPS)
+        for m in self.modules():  # timm defaults for a stand-alone ViT; MaskedAutoencoder re-initialises (lightly)
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=0.02)
+                nn.init.zeros_(m.bias)
+        nn.init.normal_(self.cls_token, std=1e-6)
+
+    def forward_features(self, x: torch.Tensor) -> torch.Tensor:
+        """patch-embed -> cat CLS -> + pos_embed -> blocks -> norm over ALL tokens: (B, num_patches+1, D) fp32
+        (reference ``src/models/classifier.py:48``); differentiable w.r.t. the parameters."""
+        from .classifier import vit_forward_features
+
+        return vit_forward_features(self, x)
 
 
 class _MaskedViT(_HolderMixin, nn.Module):
@@ -160,8 +177,10 @@ class MAEEngine:
     C-ABI kernels for forward, backward and the fused clip+AdamW step."""
 
     ALIGN = 64  # elements; keeps every tensor 128-byte aligned in the bf16 shadow (TMA needs 16)
+    NOGRAD = ("encoder.mask_token", "encoder.vit.pos_embed", "decoder.decoder_pos_embed")  # never receive a gradient
+    EP = "encoder.vit."  # state_dict prefix of the timm-style ViT inside the model
 
-    def __init__(self, model: "MaskedAutoencoder"):
+    def __init__(self, model: nn.Module):
         self.model = model
         self.flat: Optional[torch.Tensor] = None
         self._ws_key = None
@@ -172,25 +191,40 @@ class MAEEngine:
     # ---------------- flat storage ----------------
     def _ordered_params(self) -> List[Tuple[str, nn.Parameter]]:
         named = list(self.model.named_parameters())
-        nograd = {"encoder.mask_token", "encoder.vit.pos_embed", "decoder.decoder_pos_embed"}
+        nograd = set(self.NOGRAD)
         return [(n, p) for n, p in named if n not in nograd] + [(n, p) for n, p in named if n in nograd]
 
+    def _vit(self):
+        return self.model.encoder.vit
+
+    def _flat_is_current(self, device: torch.device) -> bool:
+        """True iff every parameter still is the view into ``self.flat`` this engine created (``.to()``, another
+        engine flattening a shared sub-module, or a replaced ``.data`` all break that)."""
+        if self.flat is None or self.flat.device != device:
+            return False
+        base = self.flat.data_ptr()
+        for n, p in self._param_list:
+            if p.data_ptr() != base + 4 * self.offsets[n]:
+                return False
+        return True
+
     def _ensure_flat(self, device: torch.device) -> None:
-        first = next(self.model.parameters())
-        if self.flat is not None and self.flat.device == device and first.data_ptr() == self._first_ptr and \
-                first.device == device:
+        if self._flat_is_current(device):
             return
         if device.type != "cuda":
             raise RuntimeError("MaskedAutoencoder runs only on CUDA (sm_100a); there is no CPU fallback")
         _lib.load()
         params = self._ordered_params()
+        self._param_list = params
         off, self.offsets, self.n_opt = 0, {}, None
         for n, p in params:
-            if n == "encoder.mask_token":
+            if n in self.NOGRAD and self.n_opt is None:
                 self.n_opt = off
             self.offsets[n] = off
             off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.n_total = off
+        if self.n_opt is None:
+            self.n_opt = off
         flat = torch.zeros(off, dtype=torch.float32, device=device)
         old_m = getattr(self, "exp_avg", None)
         for n, p in params:
@@ -198,7 +232,6 @@ class MAEEngine:
             flat[o:o + p.numel()].copy_(p.data.reshape(-1).to(device=device, dtype=torch.float32))
             p.data = flat[o:o + p.numel()].view(p.shape)
         self.flat = flat
-        self._first_ptr = first.data_ptr()
         self.grads = torch.zeros(self.n_opt, dtype=torch.float32, device=device)
         if old_m is None or old_m.numel() != self.n_opt:
             self.exp_avg = torch.zeros(self.n_opt, dtype=torch.float32, device=device)
@@ -234,8 +267,11 @@ class MAEEngine:
             return b
 
         m = self.model
-        vit = m.encoder.vit
-        self.enc_blocks = [blk(f"encoder.vit.blocks.{i}.", vit.embed_dim, vit.num_heads) for i in range(len(vit.blocks))]
+        vit = self._vit()
+        self.enc_blocks = [blk(f"{self.EP}blocks.{i}.", vit.embed_dim, vit.num_heads) for i in range(len(vit.blocks))]
+        if not hasattr(m, "decoder"):
+            self.dec_blocks = []
+            return
         dd = m.decoder.decoder_embed.out_features
         dh = m.decoder.decoder_blocks[0].attn.num_heads if len(m.decoder.decoder_blocks) else 1
         self.dec_blocks = [blk(f"decoder.decoder_blocks.{i}.", dd, dh) for i in range(len(m.decoder.decoder_blocks))]
@@ -371,22 +407,44 @@ class MAEEngine:
         return ws["pred"], target, ws["loss"]
 
     def _encode(self, images: torch.Tensor, idx_keep: torch.Tensor, st: int) -> None:
-        m, ws, d = self.model, self.ws, self.dims
+        ws, d = self.ws, self.dims
+        pe = self._vit().patch_embed
         B, Lk, De = d["B"], d["Lk"], d["De"]
-        o = self._o
-        calls.mae_gather_patches(images.data_ptr(), idx_keep.data_ptr(), B, m.in_chans, m.image_size, m.patch_size, Lk,
+        o, ep = self._o, self.EP
+        calls.mae_gather_patches(images.data_ptr(), idx_keep.data_ptr(), B, pe.in_chans, pe.img_size, pe.patch_size, Lk,
                                  _ptr(ws["patches"]), st)
-        calls.mae_gemm_tn(_ptr(ws["patches"]), self.pw(o("encoder.vit.patch_embed.proj.weight")), B * (Lk - 1), De,
-                          d["pd"], EPI_BF16, self.pf(o("encoder.vit.patch_embed.proj.bias")), _ptr(ws["tok"]), None,
+        calls.mae_gemm_tn(_ptr(ws["patches"]), self.pw(o(ep + "patch_embed.proj.weight")), B * (Lk - 1), De,
+                          d["pd"], EPI_BF16, self.pf(o(ep + "patch_embed.proj.bias")), _ptr(ws["tok"]), None,
                           None, st)
         x0 = ws["enc"][0]["x_in"] if self.enc_blocks else ws["x_enc"]
-        calls.mae_assemble_tokens(_ptr(ws["tok"]), self.pf(o("encoder.vit.cls_token")), self.pf(o("encoder.vit.pos_embed")),
+        calls.mae_assemble_tokens(_ptr(ws["tok"]), self.pf(o(ep + "cls_token")), self.pf(o(ep + "pos_embed")),
                                   idx_keep.data_ptr(), B, Lk, De, _ptr(x0), st)
         for i, w in enumerate(self.enc_blocks):
             x_out = ws["enc"][i + 1]["x_in"] if i + 1 < len(self.enc_blocks) else ws["x_enc"]
             self._block_fwd(w, ws["enc"][i], x_out, d["Me"], B, Lk, st)
-        calls.mae_layernorm_fwd(_ptr(ws["x_enc"]), self.pf(o("encoder.vit.norm.weight")), self.pf(o("encoder.vit.norm.bias")),
+        calls.mae_layernorm_fwd(_ptr(ws["x_enc"]), self.pf(o(ep + "norm.weight")), self.pf(o(ep + "norm.bias")),
                                 None, 0, 0, d["Me"], De, LN_EPS, _ptr(ws["xnf"]), _ptr(ws["meanf"]), _ptr(ws["rstdf"]), st)
+
+    def _encoder_bwd(self, g_ptr: int, cur, curb, nxt, nxtb, st: int, first_block: int = 0, stem: bool = True):
+        """Backward of ``vit.norm`` + encoder blocks [first_block:] (+ cls_token / patch-embed when ``stem``), given
+        the bf16 gradient ``g`` w.r.t. the normalised encoder output.  The result lands in ``cur``-style buffers."""
+        ws, d = self.ws, self.dims
+        B, Lk, De, pd, Me = d["B"], d["Lk"], d["De"], d["pd"], d["Me"]
+        o, ep = self._o, self.EP
+        calls.mae_layernorm_bwd(g_ptr, _ptr(ws["x_enc"]), _ptr(ws["meanf"]), _ptr(ws["rstdf"]),
+                                self.pf(o(ep + "norm.weight")), None, None, 0, 0, Me, De, _ptr(nxt), _ptr(nxtb),
+                                self.pg(o(ep + "norm.weight")), self.pg(o(ep + "norm.bias")), st)
+        cur, curb, nxt, nxtb = nxt, nxtb, cur, curb
+        for i in reversed(range(first_block, len(self.enc_blocks))):
+            self._block_bwd(self.enc_blocks[i], ws["enc"][i], cur, curb, nxt, nxtb, Me, B, Lk, st)
+            cur, curb, nxt, nxtb = nxt, nxtb, cur, curb
+        if stem and first_block == 0:
+            # tokens = cat(cls, patch_embed(kept patches)) + frozen pos
+            calls.mae_colsum_rows_f32(_ptr(cur), None, B, 1, Lk, 0, De, self.pg(o(ep + "cls_token")), st)
+            calls.mae_gather_rows_bf16(_ptr(cur), None, B, Lk - 1, Lk, 1, De, _ptr(ws["dtok"]), st)
+            self._linear_bwd_w(_ptr(ws["dtok"]), De, _ptr(ws["patches"]), pd, B * (Lk - 1),
+                               o(ep + "patch_embed.proj.weight"), o(ep + "patch_embed.proj.bias"), st)
+        return cur
 
     def _decode(self, st: int) -> None:
         ws, d = self.ws, self.dims
@@ -483,18 +541,7 @@ class MAEEngine:
             bucket_cb("decoder")
         calls.mae_gemm_tn(_ptr(ws["demb"]), self.pwt(o("decoder.decoder_embed.weight")), Me, De, Dd, EPI_BF16, None,
                           _ptr(ws["g"]), None, None, st)
-        calls.mae_layernorm_bwd(_ptr(ws["g"]), _ptr(ws["x_enc"]), _ptr(ws["meanf"]), _ptr(ws["rstdf"]),
-                                self.pf(o("encoder.vit.norm.weight")), None, None, 0, 0, Me, De, _ptr(nxt), _ptr(nxtb),
-                                self.pg(o("encoder.vit.norm.weight")), self.pg(o("encoder.vit.norm.bias")), st)
-        cur, curb, nxt, nxtb = nxt, nxtb, cur, curb
-        for i in reversed(range(len(self.enc_blocks))):
-            self._block_bwd(self.enc_blocks[i], ws["enc"][i], cur, curb, nxt, nxtb, Me, B, Lk, st)
-            cur, curb, nxt, nxtb = nxt, nxtb, cur, curb
-        # tokens = cat(cls, patch_embed(kept patches)) + frozen pos
-        calls.mae_colsum_rows_f32(_ptr(cur), None, B, 1, Lk, 0, De, self.pg(o("encoder.vit.cls_token")), st)
-        calls.mae_gather_rows_bf16(_ptr(cur), None, B, Lk - 1, Lk, 1, De, _ptr(ws["dtok"]), st)
-        self._linear_bwd_w(_ptr(ws["dtok"]), De, _ptr(ws["patches"]), pd, B * (Lk - 1),
-                           o("encoder.vit.patch_embed.proj.weight"), o("encoder.vit.patch_embed.proj.bias"), st)
+        self._encoder_bwd(_ptr(ws["g"]), cur, curb, nxt, nxtb, st)
         if bucket_cb is not None:
             bucket_cb("encoder")
 

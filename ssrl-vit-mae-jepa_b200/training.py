@@ -35,12 +35,12 @@ except Exception:  # noqa: BLE001
             self.logged: Dict[str, Any] = {}
             self.hparams: Dict[str, Any] = {}
 
-        def save_hyperparameters(self, **kw):
+        def save_hyperparameters(self, ignore=(), **kw):
             import inspect
 
             frame = inspect.currentframe().f_back
-            args = {k: v for k, v in frame.f_locals.items() if k not in ("self", "__class__")}
-            self.hparams = dict(args)
+            skip = {"self", "__class__", *([ignore] if isinstance(ignore, str) else ignore)}
+            self.hparams = {k: v for k, v in frame.f_locals.items() if k not in skip}
 
         def log(self, name: str, value, **kw):
             self.logged[name] = value

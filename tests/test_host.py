@@ -133,3 +133,27 @@ def test_grad_buckets_world_size_2_gloo():
     [p.join(60) for p in ps]
     expect = [i * 1.5 for i in range(10)]  # mean of x and 2x
     assert out[0] == expect and out[1] == expect
+
+
+def test_classifier_module_mirrors_reference():
+    from src.models.classifier import ViTClassifier
+    from src.training.classifier import ViTClassifierTrainModule
+    cfg = {"general": O.MAE_YAML["general"], "encoder": O.MAE_YAML["encoder"], "decoder": O.MAE_YAML["decoder"],
+           "head": {"embed_dim": 144, "pool": "cls"}}
+    mae = _build()
+    mod = ViTClassifierTrainModule(pretrained_encoder=mae.encoder.vit, model_cfg=cfg, training_cfg={"freeze_encoder": True})
+    # notebook.ipynb:1689-1698: 1.4 K trainable (1,450) / 1.1 M frozen (1,051,920)
+    assert sum(p.numel() for p in mod.parameters() if p.requires_grad) == 1450
+    assert sum(p.numel() for p in mod.parameters() if not p.requires_grad) == 1_051_920
+    assert isinstance(mod.model, ViTClassifier) and mod.model.pool_type == "cls"
+    assert list(mod.model.state_dict())[-2:] == ["head.classification.weight", "head.classification.bias"]
+    assert list(mod.model.encoder.state_dict()) == list(O.VisionTransformer().state_dict())
+    mod.unfreeze_last_layers(1)
+    tr = {n for n, p in mod.model.named_parameters() if p.requires_grad}
+    assert all(n.startswith(("encoder.blocks.3.", "encoder.norm.", "head.")) for n in tr) and len(tr) == 12 + 2 + 2
+    with pytest.raises(ValueError):
+        mod.unfreeze_last_layers(5)
+    oc = mod.configure_optimizers()
+    assert oc["lr_scheduler"]["monitor"] == "val_loss" and len(oc["optimizer"].param_groups[0]["params"]) == 16
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mod(torch.randn(2, 3, 96, 96))
