@@ -157,3 +157,48 @@ def test_classifier_module_mirrors_reference():
     assert oc["lr_scheduler"]["monitor"] == "val_loss" and len(oc["optimizer"].param_groups[0]["params"]) == 16
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         mod(torch.randn(2, 3, 96, 96))
+
+
+def test_data_module_synthetic_fallback(monkeypatch):
+    import yaml
+    from src.data import get_pretrain_dataloaders, get_train_dataloaders
+    monkeypatch.setenv("MAE_SYNTHETIC_DATA", "1")
+    monkeypatch.setenv("MAE_SYNTHETIC_SIZE", "120")
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "configs", "mae.yaml")))
+    assert cfg["pretrain"]["batch_size"] == 2000 and cfg["model"]["encoder"]["embed_dim"] == 144  # reference values
+    cfg["pretrain"].update(batch_size=8, num_workers=0, val_split=0.25)
+    cfg["train"].update(batch_size=8, num_workers=0, samples_per_class=3)
+    tr, va = get_pretrain_dataloaders(cfg)
+    assert len(tr.dataset) == 90 and len(va.dataset) == 30
+    x, y = next(iter(tr))
+    assert x.shape == (8, 3, 96, 96) and x.dtype == torch.float32 and -1.0 <= x.min() and x.max() <= 1.0
+    x2, _ = next(iter(get_pretrain_dataloaders(cfg)[1]))
+    x3, _ = next(iter(get_pretrain_dataloaders(cfg)[1]))
+    assert torch.equal(x2, x3)  # deterministic
+    tr, va = get_train_dataloaders(cfg)
+    labels = torch.cat([y for _, y in tr])
+    assert len(tr.dataset) == 30 and torch.bincount(labels, minlength=10).tolist() == [3] * 10
+
+
+def test_encoder_checkpoint_prefix_detection(tmp_path):
+    from scripts.utils import load_encoder_weights
+    src = _build()
+    for prefix, wrap in [("encoder.", False), ("model.encoder.", True), ("module.encoder.", False)]:
+        sd = {(("model." if prefix.startswith("model.") else "module." if prefix.startswith("module.") else "") + k): v
+              for k, v in src.state_dict().items()}
+        path = tmp_path / f"w_{prefix.strip('.')}.pt"
+        torch.save({"state_dict": sd} if wrap else sd, path)
+        dst = _build()
+        assert load_encoder_weights(dst.encoder, str(path)) == prefix
+        assert torch.equal(dst.encoder.vit.blocks[2].mlp.fc1.weight, src.encoder.vit.blocks[2].mlp.fc1.weight)
+    torch.save({"foo.bar": torch.zeros(1)}, tmp_path / "bad.pt")
+    with pytest.raises(RuntimeError, match="no encoder weights"):
+        load_encoder_weights(_build().encoder, str(tmp_path / "bad.pt"))
+
+
+def test_cli_flags_match_reference():
+    from scripts.training import pretrain_mae, train_mae
+    a = pretrain_mae.parse_args([])
+    assert (a.config, a.resume_from, a.output_dir_suffix) == ("configs/mae.yaml", None, "mae_pretrain")
+    b = train_mae.parse_args(["--encoder_ckpt", "x.pt"])
+    assert (b.config, b.encoder_ckpt, b.classifier_ckpt, b.output_dir_suffix) == ("configs/mae.yaml", "x.pt", None, "mae_finetune")
