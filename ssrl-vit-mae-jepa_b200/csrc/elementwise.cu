@@ -95,9 +95,18 @@ __global__ void __launch_bounds__(256) gather_patches_kernel(const float* __rest
   const int pp = patch * patch, pd = C * pp;
   const float* src = images + size_t(b) * C * img * img;
   __nv_bfloat16* dst = out + size_t(w) * pd;
-  for (int q = lane; q < pd; q += 32) {
-    const int c = q / pp, py = (q % pp) / patch, px = q % patch;
-    dst[q] = __float2bfloat16_rn(src[(size_t(c) * img + pr * patch + py) * img + pcn * patch + px]);
+  if ((patch & 3) == 0) {  // 4 consecutive px of one (c, py) row per lane: 16-byte loads, 8-byte stores
+    const int p4 = patch >> 2;
+    for (int q = lane; q < (pd >> 2); q += 32) {
+      const int c = q / (patch * p4), py = (q / p4) % patch, px = (q % p4) * 4;
+      const float4 v = *reinterpret_cast<const float4*>(src + (size_t(c) * img + pr * patch + py) * img + pcn * patch + px);
+      *reinterpret_cast<uint2*>(dst + q * 4) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+  } else {
+    for (int q = lane; q < pd; q += 32) {
+      const int c = q / pp, py = (q % pp) / patch, px = q % patch;
+      dst[q] = __float2bfloat16_rn(src[(size_t(c) * img + pr * patch + py) * img + pcn * patch + px]);
+    }
   }
 }
 
@@ -108,14 +117,23 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const __nv_bfloat1
                                                              int num_keep, int D, float* __restrict__ x) {
   pdl_trigger();
   pdl_wait();
-  const long long n = (long long)B * num_keep * D;
+  const int D4 = D >> 2;
+  const long long n = (long long)B * num_keep * D4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int d = int(i % D);
-    const long long r = i / D;
+    const int d = int(i % D4) * 4;
+    const long long r = i / D4;
     const int j = int(r % num_keep), b = int(r / num_keep);
-    const int tokidx = int(idx_keep[size_t(b) * num_keep + j]);
-    float v = (j == 0) ? cls[d] : __bfloat162float(tok[(size_t(b) * (num_keep - 1) + (j - 1)) * D + d]);
-    x[i] = v + pos[size_t(tokidx) * D + d];
+    const int tokidx = int(idx_keep[r]);
+    float4 v;
+    if (j == 0) {
+      v = *reinterpret_cast<const float4*>(cls + d);
+    } else {
+      const uint2 t = *reinterpret_cast<const uint2*>(tok + (size_t(b) * (num_keep - 1) + (j - 1)) * D + d);
+      v = make_float4(bf16_lo(t.x), bf16_hi(t.x), bf16_lo(t.y), bf16_hi(t.y));
+    }
+    const float4 p = *reinterpret_cast<const float4*>(pos + size_t(tokidx) * D + d);
+    v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    *reinterpret_cast<float4*>(x + r * D + d) = v;
   }
 }
 
@@ -646,7 +664,8 @@ extern "C" int mae_assemble_tokens(const void* tok, const float* cls, const floa
                                    int num_keep, int D, float* x, cudaStream_t stream) {
   if (B <= 0) return MAE_OK;
   if (!tok || !cls || !pos || !idx_keep || !x) return MAE_ERR_NULL;
-  mae_launch(assemble_tokens_kernel, dim3(grid_for((long long)B * num_keep * D, 256)), dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(tok), cls, pos, idx_keep, B, num_keep, D, x);
+  if (D % 4) return MAE_ERR_SHAPE;
+  mae_launch(assemble_tokens_kernel, dim3(grid_for((long long)B * num_keep * (D / 4), 256)), dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(tok), cls, pos, idx_keep, B, num_keep, D, x);
   return MAE_CHECK_LAUNCH();
 }
 
