@@ -8,6 +8,8 @@
 // read the TMEM lane quarter (warp_id % 4), so the four warps of a quarter interleave the 16-column chunks.  Operand tiles are staged by TMA with the
 // 128-byte swizzle in a 4-deep mbarrier ring; accumulators live in TMEM (fp32), double buffered for
 // gemm_tn so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <stdlib.h>
+
 #include "mae_internal.h"
 #include "ptx.cuh"
 
@@ -76,6 +78,7 @@ struct GemmTnParams {
   int mtiles;   // ceil(M / 128)
   int nkb;      // ceil(K / 64)
   int nstages;  // TMA ring depth (3 or 4, whatever fits next to the epilogue staging tiles)
+  int use_tma_store;  // bf16 outputs leave through TMA bulk tensor stores (off: MAE_GEMM_NO_TMA_STORE=1, A/B experiments)
   const float* bias;          // [N] or null
   void* out;                  // bf16 [M,N] (EPI 0,1,3,4)  or  f32 [M,N] (EPI 2)
   __nv_bfloat16* pre_out;     // EPI 1: bf16 [M,N] GELU'(pre-activation), consumed by EPI 4
@@ -96,8 +99,25 @@ struct GemmSmemHdr {
 // fp32 columns): the row-per-thread values go through a private padded staging tile in shared memory and
 // leave (or, for aux inputs, arrive) with 8 lanes covering one row, i.e. 4 complete rows per instruction.
 // ---------------------------------------------------------------------------------------------
-static constexpr int kStgRow = 144;                 // 128 data bytes + 16 pad: conflict-free 16-byte accesses
-static constexpr int kStgBytes = 32 * kStgRow;      // per epilogue warp
+static constexpr int kStgRow = 144;                 // manual path: 128 data bytes + 16 pad, conflict-free 16-byte accesses
+static constexpr int kStgBytes = 5 * 1024;          // per epilogue warp: 32 x 144 B (manual) or 32 x 128 B swizzled (TMA store);
+                                                    // 1024-byte aligned because the TMA tile uses the 128-byte swizzle
+
+// TMA bulk tensor store of a [32 rows x 64 bf16] tile (128-byte swizzled in smem) -- SASS: UTMASTG
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// 16-byte chunk `c` (0..7) of row `t` inside a 128-byte-swizzled [32 x 128 B] tile
+__device__ __forceinline__ uint32_t swz128(uint32_t base, int t, int c) { return base + t * 128 + ((c ^ (t & 7)) << 4); }
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -168,32 +188,54 @@ __device__ __forceinline__ void stg_flush_add_f32(const uint8_t* stg, const uint
 }
 
 // One work item (128 x bn accumulator tile) for one epilogue warp.  row0 = first global row of this warp's 32.
+// bf16 outputs: the tile is split into 64-column units dealt round-robin to the kEpiGroups warps of the lane quarter
+// (rotated by `rot` = per-CTA item counter so that e.g. 3 units keep all 4 warps busy on average).  A full unit is
+// written row-per-thread into a 128-byte-swizzled smem tile and leaves through one TMA bulk tensor store (no smem
+// read-back, no per-lane global stores: the LSU only sees the staging writes); ragged units (bn % 64) and the fp32
+// residual epilogue use the manual coalesced path.
 template <int EPI>
 __device__ __forceinline__ void epilogue_item(const GemmTnParams& p, uint32_t taddr, int row0, int col_base, int grp,
-                                              uint8_t* stg, int lane) {
+                                              int rot, uint8_t* stg, int lane, const CUtensorMap* mo,
+                                              const CUtensorMap* mo2) {
   constexpr bool F32 = (EPI == MAE_EPI_RESID_F32);
   constexpr int UC = F32 ? 32 : 64;          // columns per 128-byte unit
   constexpr int SB = F32 ? 64 : 32;          // bytes per 16-column sub-chunk
   constexpr int ES = F32 ? 4 : 2;            // output element size
   const int rows_valid = p.M - row0;         // may be <= 0 or > 32
-  // Balanced split of the bn/16 sub-chunks over the kEpiGroups warps of this lane quarter (contiguous ranges,
-  // e.g. bn=192: 3+3+3+3, bn=144: 3+2+2+2), each range processed in units of at most 128 bytes per row.
-  const int nsc = p.bn >> 4;
-  const int sc_begin = (nsc * grp) / kEpiGroups, sc_end = (nsc * (grp + 1)) / kEpiGroups;
-  for (int sc = sc_begin; sc < sc_end; sc += UC / 16) {
-    const int c0 = sc * 16;
-    int nsub = sc_end - sc;
+  const uint32_t stg_s = smem_u32(stg);
+  const int units = (p.bn + UC - 1) / UC;
+  for (int u = 0; u < units; ++u) {
+    if (((u + rot) & (kEpiGroups - 1)) != grp) continue;
+    const int c0 = u * UC;
+    int nsub = (p.bn - c0) >> 4;
     if (nsub > UC / 16) nsub = UC / 16;
+    const bool tma = !F32 && nsub == 4 && p.use_tma_store;  // warp-uniform
     const int row_bytes = nsub * SB;
     const int gcol = col_base + c0;
     const size_t gpitch = size_t(p.N) * ES;
-    if constexpr (EPI == MAE_EPI_DGELU_BF16) {  // bring the saved GELU' tile in, coalesced
+    if (!F32) {  // the previous TMA store of this warp must have finished READING the staging tile
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+    }
+    uint32_t prk[UC / 16][8];  // EPI_DGELU: the saved GELU' values of this thread's row
+    if constexpr (EPI == MAE_EPI_DGELU_BF16) {  // bring the saved GELU' tile in, coalesced, then row-per-thread
       uint8_t* abase = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(p.aux)) + (size_t(row0) * p.N + gcol) * 2;
       stg_copy<false>(stg, abase, gpitch, row_bytes, rows_valid, lane);
       __syncwarp();
+#pragma unroll
+      for (int sidx = 0; sidx < UC / 16; ++sidx)
+        if (sidx < nsub) {
+          const uint4 a = *reinterpret_cast<const uint4*>(stg + lane * kStgRow + sidx * SB);
+          const uint4 b = *reinterpret_cast<const uint4*>(stg + lane * kStgRow + sidx * SB + 16);
+          prk[sidx][0] = a.x; prk[sidx][1] = a.y; prk[sidx][2] = a.z; prk[sidx][3] = a.w;
+          prk[sidx][4] = b.x; prk[sidx][5] = b.y; prk[sidx][6] = b.z; prk[sidx][7] = b.w;
+        }
+      __syncwarp();  // everyone has its inputs: the tile may now be overwritten (possibly in the swizzled layout)
     }
-    uint32_t hkeep[UC / 16][8];  // EPI_GELU: second output (h) parked in registers while `pre` is flushed
-    for (int sidx = 0; sidx < nsub; ++sidx) {
+    uint32_t hkeep[UC / 16][8];  // EPI_GELU: second output (h) parked in registers while GELU' is flushed
+#pragma unroll
+    for (int sidx = 0; sidx < UC / 16; ++sidx) {
+      if (sidx >= nsub) break;
       uint32_t raw[16];
       tmem_ld16_issue(taddr + c0 + sidx * 16, raw);
       float bia[16];
@@ -208,18 +250,12 @@ __device__ __forceinline__ void epilogue_item(const GemmTnParams& p, uint32_t ta
 #pragma unroll
         for (int i = 0; i < 16; ++i) bia[i] = 0.f;
       }
-      uint8_t* my = stg + lane * kStgRow + sidx * SB;
-      uint32_t pr[8];
-      if constexpr (EPI == MAE_EPI_DGELU_BF16) {
-        const uint4 a = *reinterpret_cast<const uint4*>(my), b = *reinterpret_cast<const uint4*>(my + 16);
-        pr[0] = a.x; pr[1] = a.y; pr[2] = a.z; pr[3] = a.w; pr[4] = b.x; pr[5] = b.y; pr[6] = b.z; pr[7] = b.w;
-      }
       tmem_ld_wait();
       float v[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) + bia[i];
       if constexpr (F32) {
-        float4* d = reinterpret_cast<float4*>(my);
+        float4* d = reinterpret_cast<float4*>(stg + lane * kStgRow + sidx * SB);
 #pragma unroll
         for (int i = 0; i < 4; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       } else {
@@ -242,39 +278,62 @@ __device__ __forceinline__ void epilogue_item(const GemmTnParams& p, uint32_t ta
           }
         } else {  // DGELU
 #pragma unroll
-          for (int i = 0; i < 8; ++i)  // pr = GELU'(pre) saved by the forward
-            o[i] = pack_bf16x2(v[2 * i] * bf16_lo(pr[i]), v[2 * i + 1] * bf16_hi(pr[i]));
+          for (int i = 0; i < 8; ++i)  // prk = GELU'(pre) saved by the forward
+            o[i] = pack_bf16x2(v[2 * i] * bf16_lo(prk[sidx][i]), v[2 * i + 1] * bf16_hi(prk[sidx][i]));
         }
-        uint4* d = reinterpret_cast<uint4*>(my);
-        d[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        if (tma) {
+          sts128(swz128(stg_s, lane, 2 * sidx), o[0], o[1], o[2], o[3]);
+          sts128(swz128(stg_s, lane, 2 * sidx + 1), o[4], o[5], o[6], o[7]);
+        } else {
+          uint4* d = reinterpret_cast<uint4*>(stg + lane * kStgRow + sidx * SB);
+          d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+          d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
       }
     }
-    __syncwarp();
     const size_t goff = (size_t(row0) * p.N + gcol) * ES;
     if constexpr (F32) {
+      __syncwarp();
       stg_flush_add_f32(stg, reinterpret_cast<const uint8_t*>(p.aux) + goff, reinterpret_cast<uint8_t*>(p.out) + goff,
                         gpitch, row_bytes, rows_valid, lane);
-    } else if constexpr (EPI == MAE_EPI_GELU_BF16) {
-      stg_copy<true>(stg, reinterpret_cast<uint8_t*>(p.pre_out) + goff, gpitch, row_bytes, rows_valid, lane);
       __syncwarp();
-      for (int sidx = 0; sidx < nsub; ++sidx) {
-        uint4* d = reinterpret_cast<uint4*>(stg + lane * kStgRow + sidx * SB);
-        d[0] = make_uint4(hkeep[sidx][0], hkeep[sidx][1], hkeep[sidx][2], hkeep[sidx][3]);
-        d[1] = make_uint4(hkeep[sidx][4], hkeep[sidx][5], hkeep[sidx][6], hkeep[sidx][7]);
+    } else if (tma) {
+      fence_proxy_async_smem();  // generic-proxy staging writes -> visible to the TMA (async proxy)
+      __syncwarp();
+      if constexpr (EPI == MAE_EPI_GELU_BF16) {
+        if (lane == 0) { tma_store_2d(mo2, stg_s, gcol, row0); tma_store_wait_read(); }  // GELU' -> pre_out
+        __syncwarp();
+#pragma unroll
+        for (int sidx = 0; sidx < 4; ++sidx) {
+          sts128(swz128(stg_s, lane, 2 * sidx), hkeep[sidx][0], hkeep[sidx][1], hkeep[sidx][2], hkeep[sidx][3]);
+          sts128(swz128(stg_s, lane, 2 * sidx + 1), hkeep[sidx][4], hkeep[sidx][5], hkeep[sidx][6], hkeep[sidx][7]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
       }
-      __syncwarp();
-      stg_copy<true>(stg, reinterpret_cast<uint8_t*>(p.out) + goff, gpitch, row_bytes, rows_valid, lane);
+      if (lane == 0) tma_store_2d(mo, stg_s, gcol, row0);
     } else {
+      __syncwarp();
+      if constexpr (EPI == MAE_EPI_GELU_BF16) {
+        stg_copy<true>(stg, reinterpret_cast<uint8_t*>(p.pre_out) + goff, gpitch, row_bytes, rows_valid, lane);
+        __syncwarp();
+        for (int sidx = 0; sidx < nsub; ++sidx) {
+          uint4* d = reinterpret_cast<uint4*>(stg + lane * kStgRow + sidx * SB);
+          d[0] = make_uint4(hkeep[sidx][0], hkeep[sidx][1], hkeep[sidx][2], hkeep[sidx][3]);
+          d[1] = make_uint4(hkeep[sidx][4], hkeep[sidx][5], hkeep[sidx][6], hkeep[sidx][7]);
+        }
+        __syncwarp();
+      }
       stg_copy<true>(stg, reinterpret_cast<uint8_t*>(p.out) + goff, gpitch, row_bytes, rows_valid, lane);
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
+gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapO2) {
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128-byte swizzle atoms
@@ -293,6 +352,8 @@ gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, c
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
+    tma_prefetch_desc(&mapO);
+    tma_prefetch_desc(&mapO2);
     for (int s = 0; s < nst; ++s) { mbar_init(&hdr->full[s], 1); mbar_init(&hdr->empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&hdr->tfull[a], 1); mbar_init(&hdr->tempty[a], 4 * kEpiGroups); }
     fence_mbar_init();
@@ -352,17 +413,19 @@ gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, c
     const int grp = (warp - 2) >> 2;  // which of the quarter's kEpiGroups warps: takes units grp, grp+4, ...
     uint8_t* stg = stg_all + (warp - 2) * kStgBytes;
     int acc = 0; uint32_t accphase = 0;
-    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    int it = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x, ++it) {
       const int mt = item / p.nchunks, nc = item % p.nchunks;
       mbar_wait(&hdr->tfull[acc], accphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc) * 256u;
-      epilogue_item<EPI>(p, taddr, mt * BM + q * 32, nc * p.bn, grp, stg, lane);
+      epilogue_item<EPI>(p, taddr, mt * BM + q * 32, nc * p.bn, grp, it, stg, lane, &mapO, &mapO2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&hdr->tempty[acc]);
       acc ^= 1; if (acc == 0) accphase ^= 1;
     }
+    if (lane == 0) tma_store_wait_all();  // outstanding bulk stores must complete before the CTA's smem goes away
   }
   tc_fence_before();
   __syncthreads();
@@ -376,7 +439,8 @@ static int pick_bn(int N) {
 }
 
 template <int EPI>
-static int launch_gemm_tn(const GemmTnParams& p, const CUtensorMap& ma, const CUtensorMap& mb, cudaStream_t st) {
+static int launch_gemm_tn(const GemmTnParams& p, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo,
+                          const CUtensorMap& mo2, cudaStream_t st) {
   const size_t smem = size_t(p.nstages) * (BM * BK * 2 + p.bn * BK * 2) + 4 * kEpiGroups * kStgBytes +
                       sizeof(GemmSmemHdr) + 1024;
   static bool attr_done = false;
@@ -387,7 +451,7 @@ static int launch_gemm_tn(const GemmTnParams& p, const CUtensorMap& ma, const CU
   }
   const int total = p.mtiles * p.nchunks;
   const int grid = total < num_sms() ? total : num_sms();
-  mae_launch(gemm_tn_kernel<EPI>, dim3(grid), dim3(kGemmThreads), smem, st, p, ma, mb);
+  mae_launch(gemm_tn_kernel<EPI>, dim3(grid), dim3(kGemmThreads), smem, st, p, ma, mb, mo, mo2);
   return cudaGetLastError() == cudaSuccess ? MAE_OK : MAE_ERR_LAUNCH;
 }
 
@@ -415,16 +479,30 @@ extern "C" int mae_gemm_tn(const void* A, const void* B, int M, int N, int K, in
   if (!A || !B || !out) return MAE_ERR_NULL;
   if (epi == MAE_EPI_GELU_BF16 && !pre_out) return MAE_ERR_NULL;
   if ((epi == MAE_EPI_RESID_F32 || epi == MAE_EPI_DGELU_BF16) && !aux) return MAE_ERR_NULL;
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mo, mo2;
   int rc = make_tmap_bf16(&ma, A, M, K, K, BM);
   if (rc) return rc;
   rc = make_tmap_bf16(&mb, B, N, K, K, p.bn);
   if (rc) return rc;
+  {
+    static const bool no_tma = getenv("MAE_GEMM_NO_TMA_STORE") != nullptr;
+    p.use_tma_store = (epi != MAE_EPI_RESID_F32 && !no_tma) ? 1 : 0;
+  }
+  // output tensor maps: [32 rows x 64 bf16] boxes, 128-byte swizzle (dummy = A's map when unused)
+  mo = ma; mo2 = ma;
+  if (p.use_tma_store) {
+    rc = make_tmap_bf16(&mo, out, M, N, N, 32);
+    if (rc) return rc;
+    if (epi == MAE_EPI_GELU_BF16) {
+      rc = make_tmap_bf16(&mo2, pre_out, M, N, N, 32);
+      if (rc) return rc;
+    }
+  }
   switch (epi) {
-    case MAE_EPI_BF16: return launch_gemm_tn<MAE_EPI_BF16>(p, ma, mb, stream);
-    case MAE_EPI_GELU_BF16: return launch_gemm_tn<MAE_EPI_GELU_BF16>(p, ma, mb, stream);
-    case MAE_EPI_RESID_F32: return launch_gemm_tn<MAE_EPI_RESID_F32>(p, ma, mb, stream);
-    case MAE_EPI_DGELU_BF16: return launch_gemm_tn<MAE_EPI_DGELU_BF16>(p, ma, mb, stream);
+    case MAE_EPI_BF16: return launch_gemm_tn<MAE_EPI_BF16>(p, ma, mb, mo, mo2, stream);
+    case MAE_EPI_GELU_BF16: return launch_gemm_tn<MAE_EPI_GELU_BF16>(p, ma, mb, mo, mo2, stream);
+    case MAE_EPI_RESID_F32: return launch_gemm_tn<MAE_EPI_RESID_F32>(p, ma, mb, mo, mo2, stream);
+    case MAE_EPI_DGELU_BF16: return launch_gemm_tn<MAE_EPI_DGELU_BF16>(p, ma, mb, mo, mo2, stream);
     default: return MAE_ERR_SHAPE;
   }
 }
