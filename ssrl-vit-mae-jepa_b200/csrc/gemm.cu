@@ -100,8 +100,11 @@ struct GemmSmemHdr {
 // leave (or, for aux inputs, arrive) with 8 lanes covering one row, i.e. 4 complete rows per instruction.
 // ---------------------------------------------------------------------------------------------
 static constexpr int kStgRow = 144;                 // manual path: 128 data bytes + 16 pad, conflict-free 16-byte accesses
-static constexpr int kStgBytes = 5 * 1024;          // per epilogue warp: 32 x 144 B (manual) or 32 x 128 B swizzled (TMA store);
-                                                    // 1024-byte aligned because the TMA tile uses the 128-byte swizzle
+// per epilogue warp: 32 x 144 B (manual path) or, for the TMA-store epilogues, 5 KB so that every warp's tile is
+// 1024-byte aligned (128-byte swizzle).  Kept as small as possible: dynamic smem comes out of the L1 carve-out.
+__host__ __device__ constexpr int stg_bytes(int epi) {
+  return (epi == MAE_EPI_BF16 || epi == MAE_EPI_GELU_BF16) ? 5 * 1024 : 32 * kStgRow;
+}
 
 // TMA bulk tensor store of a [32 rows x 64 bf16] tile (128-byte swizzled in smem) -- SASS: UTMASTG
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
@@ -187,6 +190,111 @@ __device__ __forceinline__ void stg_flush_add_f32(const uint8_t* stg, const uint
   }
 }
 
+// Manual-path epilogue (fp32 residual and dGELU): one work item (128 x bn accumulator tile) for one epilogue warp.  row0 = first global row of this warp's 32.
+template <int EPI>
+__device__ __forceinline__ void epilogue_item_manual(const GemmTnParams& p, uint32_t taddr, int row0, int col_base, int grp,
+                                              uint8_t* stg, int lane) {
+  constexpr bool F32 = (EPI == MAE_EPI_RESID_F32);
+  constexpr int UC = F32 ? 32 : 64;          // columns per 128-byte unit
+  constexpr int SB = F32 ? 64 : 32;          // bytes per 16-column sub-chunk
+  constexpr int ES = F32 ? 4 : 2;            // output element size
+  const int rows_valid = p.M - row0;         // may be <= 0 or > 32
+  // Balanced split of the bn/16 sub-chunks over the kEpiGroups warps of this lane quarter (contiguous ranges,
+  // e.g. bn=192: 3+3+3+3, bn=144: 3+2+2+2), each range processed in units of at most 128 bytes per row.
+  const int nsc = p.bn >> 4;
+  const int sc_begin = (nsc * grp) / kEpiGroups, sc_end = (nsc * (grp + 1)) / kEpiGroups;
+  for (int sc = sc_begin; sc < sc_end; sc += UC / 16) {
+    const int c0 = sc * 16;
+    int nsub = sc_end - sc;
+    if (nsub > UC / 16) nsub = UC / 16;
+    const int row_bytes = nsub * SB;
+    const int gcol = col_base + c0;
+    const size_t gpitch = size_t(p.N) * ES;
+    if constexpr (EPI == MAE_EPI_DGELU_BF16) {  // bring the saved GELU' tile in, coalesced
+      uint8_t* abase = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(p.aux)) + (size_t(row0) * p.N + gcol) * 2;
+      stg_copy<false>(stg, abase, gpitch, row_bytes, rows_valid, lane);
+      __syncwarp();
+    }
+    uint32_t hkeep[UC / 16][8];  // EPI_GELU: second output (h) parked in registers while `pre` is flushed
+    for (int sidx = 0; sidx < nsub; ++sidx) {
+      uint32_t raw[16];
+      tmem_ld16_issue(taddr + c0 + sidx * 16, raw);
+      float bia[16];
+      if (p.bias != nullptr) {
+        const float4* bp = reinterpret_cast<const float4*>(p.bias + gcol + sidx * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 t4 = __ldg(bp + i);
+          bia[4 * i] = t4.x; bia[4 * i + 1] = t4.y; bia[4 * i + 2] = t4.z; bia[4 * i + 3] = t4.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bia[i] = 0.f;
+      }
+      uint8_t* my = stg + lane * kStgRow + sidx * SB;
+      uint32_t pr[8];
+      if constexpr (EPI == MAE_EPI_DGELU_BF16) {
+        const uint4 a = *reinterpret_cast<const uint4*>(my), b = *reinterpret_cast<const uint4*>(my + 16);
+        pr[0] = a.x; pr[1] = a.y; pr[2] = a.z; pr[3] = a.w; pr[4] = b.x; pr[5] = b.y; pr[6] = b.z; pr[7] = b.w;
+      }
+      tmem_ld_wait();
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) + bia[i];
+      if constexpr (F32) {
+        float4* d = reinterpret_cast<float4*>(my);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      } else {
+        uint32_t o[8];
+        if constexpr (EPI == MAE_EPI_BF16) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        } else if constexpr (EPI == MAE_EPI_GELU_BF16) {
+          // autocast semantics: the linear's output is rounded to bf16 and GELU reads that bf16 value.  Both
+          // GELU and GELU' are produced here (shared Phi); GELU' is what the backward needs, so it is saved
+          // in place of the pre-activation and the dgrad epilogue is a plain multiply.
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t pre2 = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            float g0, g1, d0, d1;
+            gelu_fwd_bwd(bf16_lo(pre2), g0, d0);
+            gelu_fwd_bwd(bf16_hi(pre2), g1, d1);
+            o[i] = pack_bf16x2(d0, d1);
+            hkeep[sidx][i] = pack_bf16x2(g0, g1);
+          }
+        } else {  // DGELU
+#pragma unroll
+          for (int i = 0; i < 8; ++i)  // pr = GELU'(pre) saved by the forward
+            o[i] = pack_bf16x2(v[2 * i] * bf16_lo(pr[i]), v[2 * i + 1] * bf16_hi(pr[i]));
+        }
+        uint4* d = reinterpret_cast<uint4*>(my);
+        d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+    }
+    __syncwarp();
+    const size_t goff = (size_t(row0) * p.N + gcol) * ES;
+    if constexpr (F32) {
+      stg_flush_add_f32(stg, reinterpret_cast<const uint8_t*>(p.aux) + goff, reinterpret_cast<uint8_t*>(p.out) + goff,
+                        gpitch, row_bytes, rows_valid, lane);
+    } else if constexpr (EPI == MAE_EPI_GELU_BF16) {
+      stg_copy<true>(stg, reinterpret_cast<uint8_t*>(p.pre_out) + goff, gpitch, row_bytes, rows_valid, lane);
+      __syncwarp();
+      for (int sidx = 0; sidx < nsub; ++sidx) {
+        uint4* d = reinterpret_cast<uint4*>(stg + lane * kStgRow + sidx * SB);
+        d[0] = make_uint4(hkeep[sidx][0], hkeep[sidx][1], hkeep[sidx][2], hkeep[sidx][3]);
+        d[1] = make_uint4(hkeep[sidx][4], hkeep[sidx][5], hkeep[sidx][6], hkeep[sidx][7]);
+      }
+      __syncwarp();
+      stg_copy<true>(stg, reinterpret_cast<uint8_t*>(p.out) + goff, gpitch, row_bytes, rows_valid, lane);
+    } else {
+      stg_copy<true>(stg, reinterpret_cast<uint8_t*>(p.out) + goff, gpitch, row_bytes, rows_valid, lane);
+    }
+    __syncwarp();
+  }
+}
+
 // One work item (128 x bn accumulator tile) for one epilogue warp.  row0 = first global row of this warp's 32.
 // bf16 outputs: the tile is split into 64-column units dealt round-robin to the kEpiGroups warps of the lane quarter
 // (rotated by `rot` = per-CTA item counter so that e.g. 3 units keep all 4 warps busy on average).  A full unit is
@@ -203,17 +311,23 @@ __device__ __forceinline__ void epilogue_item(const GemmTnParams& p, uint32_t ta
   constexpr int ES = F32 ? 4 : 2;            // output element size
   const int rows_valid = p.M - row0;         // may be <= 0 or > 32
   const uint32_t stg_s = smem_u32(stg);
-  const int units = (p.bn + UC - 1) / UC;
-  for (int u = 0; u < units; ++u) {
-    if (((u + rot) & (kEpiGroups - 1)) != grp) continue;
-    const int c0 = u * UC;
-    int nsub = (p.bn - c0) >> 4;
+  // Two ways of dealing the tile's 16-column sub-chunks to the kEpiGroups warps of this lane quarter:
+  //  TMA epilogues (plain bf16, GELU): whole 64-column units, round-robin, rotated by the item counter;
+  //  manual epilogues (fp32 residual, dGELU): balanced contiguous ranges (bn=192: 3+3+3+3), <= 128 B per row at a time.
+  constexpr bool kTmaEpi = (EPI == MAE_EPI_BF16 || EPI == MAE_EPI_GELU_BF16);
+  const bool rr = kTmaEpi && p.use_tma_store;
+  const int nsc = p.bn >> 4;
+  const int sc_begin = rr ? 0 : (nsc * grp) / kEpiGroups, sc_end = rr ? nsc : (nsc * (grp + 1)) / kEpiGroups;
+  for (int sc = sc_begin, u = 0; sc < sc_end; sc += UC / 16, ++u) {
+    if (rr && ((u + rot) & (kEpiGroups - 1)) != grp) continue;
+    const int c0 = sc * 16;
+    int nsub = sc_end - sc;
     if (nsub > UC / 16) nsub = UC / 16;
-    const bool tma = !F32 && nsub == 4 && p.use_tma_store;  // warp-uniform
+    const bool tma = rr && nsub == 4;  // warp-uniform
     const int row_bytes = nsub * SB;
     const int gcol = col_base + c0;
     const size_t gpitch = size_t(p.N) * ES;
-    if (!F32) {  // the previous TMA store of this warp must have finished READING the staging tile
+    if (rr) {  // the previous TMA store of this warp must have finished READING the staging tile
       if (lane == 0) tma_store_wait_read();
       __syncwarp();
     }
@@ -343,6 +457,7 @@ gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, c
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const int nst = p.nstages;
   uint8_t* stg_all = smem + nst * stage_bytes;
+  constexpr int kStgBytes = stg_bytes(EPI);
   GemmSmemHdr* hdr = reinterpret_cast<GemmSmemHdr*>(stg_all + 4 * kEpiGroups * kStgBytes);
 
   const int warp = threadIdx.x >> 5;
@@ -419,7 +534,10 @@ gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, c
       mbar_wait(&hdr->tfull[acc], accphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc) * 256u;
-      epilogue_item<EPI>(p, taddr, mt * BM + q * 32, nc * p.bn, grp, it, stg, lane, &mapO, &mapO2);
+      if constexpr (EPI == MAE_EPI_BF16 || EPI == MAE_EPI_GELU_BF16)
+        epilogue_item<EPI>(p, taddr, mt * BM + q * 32, nc * p.bn, grp, it, stg, lane, &mapO, &mapO2);
+      else
+        epilogue_item_manual<EPI>(p, taddr, mt * BM + q * 32, nc * p.bn, grp, stg, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&hdr->tempty[acc]);
@@ -441,7 +559,7 @@ static int pick_bn(int N) {
 template <int EPI>
 static int launch_gemm_tn(const GemmTnParams& p, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo,
                           const CUtensorMap& mo2, cudaStream_t st) {
-  const size_t smem = size_t(p.nstages) * (BM * BK * 2 + p.bn * BK * 2) + 4 * kEpiGroups * kStgBytes +
+  const size_t smem = size_t(p.nstages) * (BM * BK * 2 + p.bn * BK * 2) + 4 * kEpiGroups * stg_bytes(EPI) +
                       sizeof(GemmSmemHdr) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
@@ -471,9 +589,13 @@ extern "C" int mae_gemm_tn(const void* A, const void* B, int M, int N, int K, in
   p.mtiles = (M + BM - 1) / BM;
   p.nkb = (K + BK - 1) / BK;
   {
-    const size_t fixed = 4 * kEpiGroups * kStgBytes + sizeof(GemmSmemHdr) + 1024;
+    const size_t fixed = 4 * kEpiGroups * stg_bytes(epi) + sizeof(GemmSmemHdr) + 1024;
     const size_t per_stage = BM * BK * 2 + size_t(p.bn) * BK * 2;
     p.nstages = (fixed + 4 * per_stage <= 227 * 1024) ? 4 : 3;
+    // Epilogues that touch global memory through the LSU (fp32 residual, dGELU) run faster with a bigger L1: dynamic
+    // smem comes out of the same 228 KB, and with K <= 192 (3 k-blocks per item) two ring stages already cover the loop.
+    if ((epi == MAE_EPI_DGELU_BF16 || epi == MAE_EPI_RESID_F32) && p.nkb <= 3) p.nstages = 2;
+    if (const char* e = getenv("MAE_GEMM_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= p.nstages) p.nstages = v; }  // experiments
   }
   p.bias = bias; p.out = out; p.pre_out = reinterpret_cast<__nv_bfloat16*>(pre_out); p.aux = aux;
   if (!A || !B || !out) return MAE_ERR_NULL;
@@ -486,7 +608,7 @@ extern "C" int mae_gemm_tn(const void* A, const void* B, int M, int N, int K, in
   if (rc) return rc;
   {
     static const bool no_tma = getenv("MAE_GEMM_NO_TMA_STORE") != nullptr;
-    p.use_tma_store = (epi != MAE_EPI_RESID_F32 && !no_tma) ? 1 : 0;
+    p.use_tma_store = ((epi == MAE_EPI_BF16 || epi == MAE_EPI_GELU_BF16) && !no_tma) ? 1 : 0;
   }
   // output tensor maps: [32 rows x 64 bf16] boxes, 128-byte swizzle (dummy = A's map when unused)
   mo = ma; mo2 = ma;
