@@ -18,45 +18,56 @@ namespace mae {
 
 // smem row stride (bf16) = padded head dim + 8: 80-byte (hd 24/32) or 144-byte (hd 64) rows, conflict-free ldmatrix
 
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const __nv_bfloat16* p) {
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(smem_u32(p)));
+               : "r"(saddr));
 }
-__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const __nv_bfloat16* p) {
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t saddr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(smem_u32(p)));
+               : "r"(saddr));
 }
 
-// A fragment: 16 rows [row0, +16) x 16 k [k0, +16) of a row-major tile.
+// All fragment loads take a 32-bit shared address that already contains the lane's own offset, so the loops only
+// add small compile-time-scaled offsets (no 64-bit pointer arithmetic in the hot loops):
+//   "a-type" lane offset  ((lane&7) + ((lane>>3)&1)*8) rows, (lane>>4)*8 columns : A fragments and X[k][n] B fragments
+//   "r-type" lane offset  (lane&7) rows, (lane>>3)*8 columns                      : X[n][k] B fragments
 template <int ST>
-__device__ __forceinline__ void frag_a(uint32_t (&a)[4], const __nv_bfloat16* tile, int row0, int k0, int lane) {
-  ldsm_x4(a, tile + (row0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ST + k0 + (lane >> 4) * 8);
+__device__ __forceinline__ uint32_t lane_off_a(int lane) {
+  return uint32_t((((lane & 7) + ((lane >> 3) & 1) * 8) * ST + (lane >> 4) * 8) * 2);
+}
+template <int ST>
+__device__ __forceinline__ uint32_t lane_off_r(int lane) {
+  return uint32_t(((lane & 7) * ST + (lane >> 3) * 8) * 2);
+}
+// A fragment: 16 rows [row0, +16) x 16 k [k0, +16) of a row-major tile (tile_a = tile base + lane_off_a).
+template <int ST>
+__device__ __forceinline__ void frag_a(uint32_t (&a)[4], uint32_t tile_a, int row0, int k0) {
+  ldsm_x4(a, tile_a + uint32_t((row0 * ST + k0) * 2));
 }
 // B fragments for  D[m][n] += A[m][k] * X[n][k]  (X row-major [n][k]) for the 8 rows n0..n0+7 of X and the 32
-// k-columns starting at kc: {b[0], b[1]} serve k-step kc/16, {b[2], b[3]} k-step kc/16 + 1.
+// k-columns starting at kc: {b[0], b[1]} serve k-step kc/16, {b[2], b[3]} k-step kc/16 + 1 (tile_r = base + lane_off_r).
 template <int ST>
-__device__ __forceinline__ void frag_b_rows(uint32_t (&b)[4], const __nv_bfloat16* tile, int n0, int kc, int lane) {
-  ldsm_x4(b, tile + (n0 + (lane & 7)) * ST + kc + (lane >> 3) * 8);
+__device__ __forceinline__ void frag_b_rows(uint32_t (&b)[4], uint32_t tile_r, int n0, int kc) {
+  ldsm_x4(b, tile_r + uint32_t((n0 * ST + kc) * 2));
 }
 // acc(16x8) += A(16 x 16*KS) . X[n0..n0+7][0..16*KS)^T  with A fragments a[KS]
 template <int ST, int KS>
-__device__ __forceinline__ void mma_rows(float (&acc)[4], const uint32_t (&a)[KS][4], const __nv_bfloat16* tile, int n0,
-                                         int lane) {
+__device__ __forceinline__ void mma_rows(float (&acc)[4], const uint32_t (&a)[KS][4], uint32_t tile_r, int n0) {
 #pragma unroll
   for (int kp = 0; kp < KS / 2; ++kp) {
     uint32_t b[4];
-    frag_b_rows<ST>(b, tile, n0, kp * 32, lane);
+    frag_b_rows<ST>(b, tile_r, n0, kp * 32);
     mma_16816(acc, a[2 * kp], b[0], b[1]);
     mma_16816(acc, a[2 * kp + 1], b[2], b[3]);
   }
 }
 // B fragments for  D[m][n] += A[m][k] * X[k][n]  (X row-major [k][n]): 16 k-rows k0.., 16 n-columns d0..:
-// {b[0], b[1]} serve n-tile d0, {b[2], b[3]} n-tile d0 + 8.
+// {b[0], b[1]} serve n-tile d0, {b[2], b[3]} n-tile d0 + 8 (tile_a = base + lane_off_a).
 template <int ST>
-__device__ __forceinline__ void frag_b_cols(uint32_t (&b)[4], const __nv_bfloat16* tile, int k0, int d0, int lane) {
-  ldsm_x4_t(b, tile + (k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ST + d0 + (lane >> 4) * 8);
+__device__ __forceinline__ void frag_b_cols(uint32_t (&b)[4], uint32_t tile_a, int k0, int d0) {
+  ldsm_x4_t(b, tile_a + uint32_t((k0 * ST + d0) * 2));
 }
 
 template <int NARR, int ST, int CPR>  // CPR = 16-byte chunks per padded row (4 or 8)
@@ -101,7 +112,9 @@ __global__ void __launch_bounds__(NT * 16) attn_fwd_kernel(const __nv_bfloat16* 
   const int q0 = w * 16;
   uint32_t aq[KS][4];
 #pragma unroll
-  for (int ks = 0; ks < KS; ++ks) frag_a<ST>(aq[ks], sQ, q0, ks * 16, lane);
+  const uint32_t qA = smem_u32(sQ) + lane_off_a<ST>(lane), kR = smem_u32(sK) + lane_off_r<ST>(lane),
+                 vA = smem_u32(sV) + lane_off_a<ST>(lane);
+  for (int ks = 0; ks < KS; ++ks) frag_a<ST>(aq[ks], qA, q0, ks * 16);
   const float sl2 = scale * 1.4426950408889634f;
 
   // pass 1: row max only (no exponentials); key columns >= L exist only in the last tiles, so only those mask
@@ -109,7 +122,7 @@ __global__ void __launch_bounds__(NT * 16) attn_fwd_kernel(const __nv_bfloat16* 
 #pragma unroll 2
   for (int nt = 0; nt < NT; ++nt) {
     float s[4] = {0.f, 0.f, 0.f, 0.f};
-    mma_rows<ST, KS>(s, aq, sK, nt * 8, lane);
+    mma_rows<ST, KS>(s, aq, kR, nt * 8);
     if (nt * 8 + 8 > L) {  // warp-uniform
       const int c = nt * 8 + t * 2;
       if (c >= L) { s[0] = -INFINITY; s[2] = -INFINITY; }
@@ -135,9 +148,9 @@ __global__ void __launch_bounds__(NT * 16) attn_fwd_kernel(const __nv_bfloat16* 
     for (int hf = 0; hf < 2; ++hf) {
       const int nt = 2 * kk + hf;
       p[hf][0] = p[hf][1] = p[hf][2] = p[hf][3] = 0.f;
-      mma_rows<ST, KS>(p[hf], aq, sK, nt * 8, lane);
-      p[hf][0] = exp2f(p[hf][0] * sl2 - ms0); p[hf][1] = exp2f(p[hf][1] * sl2 - ms0);
-      p[hf][2] = exp2f(p[hf][2] * sl2 - ms1); p[hf][3] = exp2f(p[hf][3] * sl2 - ms1);
+      mma_rows<ST, KS>(p[hf], aq, kR, nt * 8);
+      p[hf][0] = ex2_approx(p[hf][0] * sl2 - ms0); p[hf][1] = ex2_approx(p[hf][1] * sl2 - ms0);
+      p[hf][2] = ex2_approx(p[hf][2] * sl2 - ms1); p[hf][3] = ex2_approx(p[hf][3] * sl2 - ms1);
       if (nt * 8 + 8 > L) {  // warp-uniform
         const int c = nt * 8 + t * 2;
         if (c >= L) { p[hf][0] = 0.f; p[hf][2] = 0.f; }
@@ -152,7 +165,7 @@ __global__ void __launch_bounds__(NT * 16) attn_fwd_kernel(const __nv_bfloat16* 
 #pragma unroll
     for (int dp = 0; dp < DNP / 2; ++dp) {
       uint32_t bv[4];
-      frag_b_cols<ST>(bv, sV, kk * 16, dp * 16, lane);
+      frag_b_cols<ST>(bv, vA, kk * 16, dp * 16);
       mma_16816(o[2 * dp], a, bv[0], bv[1]);
       if (2 * dp + 1 < DN) mma_16816(o[2 * dp + 1], a, bv[2], bv[3]);
     }
@@ -224,6 +237,10 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
   __syncthreads();
 
   const float sl2 = scale * l2e;
+  const uint32_t qA = smem_u32(sQ) + lane_off_a<ST>(lane), kA = smem_u32(sK) + lane_off_a<ST>(lane),
+                 vA = smem_u32(sV) + lane_off_a<ST>(lane), oA = smem_u32(sdO) + lane_off_a<ST>(lane);
+  const uint32_t qR = smem_u32(sQ) + lane_off_r<ST>(lane), kR = smem_u32(sK) + lane_off_r<ST>(lane),
+                 vR = smem_u32(sV) + lane_off_r<ST>(lane), oR = smem_u32(sdO) + lane_off_r<ST>(lane);
   const int x0 = w * 16;  // first row of this warp's slab (queries in phase A, keys in phase B)
   const int r0 = x0 + g, r1 = x0 + g + 8;
 
@@ -231,7 +248,7 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
   {
     uint32_t aq[KS][4], ado[KS][4];
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) { frag_a<ST>(aq[ks], sQ, x0, ks * 16, lane); frag_a<ST>(ado[ks], sdO, x0, ks * 16, lane); }
+    for (int ks = 0; ks < KS; ++ks) { frag_a<ST>(aq[ks], qA, x0, ks * 16); frag_a<ST>(ado[ks], oA, x0, ks * 16); }
     const float l0 = sLse[r0], l1 = sLse[r1], d0 = sDelta[r0], d1 = sDelta[r1];
     float dq[DNP][4];
 #pragma unroll
@@ -243,10 +260,10 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
       for (int hf = 0; hf < 2; ++hf) {
         const int nt = 2 * kk + hf;
         float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_rows<ST, KS>(s, aq, sK, nt * 8, lane);
-        mma_rows<ST, KS>(dp, ado, sV, nt * 8, lane);
-        float p0 = exp2f(s[0] * sl2 - l0), p1 = exp2f(s[1] * sl2 - l0);
-        float p2 = exp2f(s[2] * sl2 - l1), p3 = exp2f(s[3] * sl2 - l1);
+        mma_rows<ST, KS>(s, aq, kR, nt * 8);
+        mma_rows<ST, KS>(dp, ado, vR, nt * 8);
+        float p0 = ex2_approx(s[0] * sl2 - l0), p1 = ex2_approx(s[1] * sl2 - l0);
+        float p2 = ex2_approx(s[2] * sl2 - l1), p3 = ex2_approx(s[3] * sl2 - l1);
         if (nt * 8 + 8 > L) {  // warp-uniform: only the tail tiles hold padded keys (s = 0 there, exp(-lse) may overflow)
           const int c = nt * 8 + t * 2;
           if (c >= L) { p0 = 0.f; p2 = 0.f; }
@@ -261,7 +278,7 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
 #pragma unroll
       for (int dp2 = 0; dp2 < DNP / 2; ++dp2) {
         uint32_t kt[4];
-        frag_b_cols<ST>(kt, sK, kk * 16, dp2 * 16, lane);
+        frag_b_cols<ST>(kt, kA, kk * 16, dp2 * 16);
         mma_16816(dq[2 * dp2], a, kt[0], kt[1]);
         if (2 * dp2 + 1 < DN) mma_16816(dq[2 * dp2 + 1], a, kt[2], kt[3]);
       }
@@ -278,7 +295,7 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
   {
     uint32_t ak[KS][4], av[KS][4];
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) { frag_a<ST>(ak[ks], sK, x0, ks * 16, lane); frag_a<ST>(av[ks], sV, x0, ks * 16, lane); }
+    for (int ks = 0; ks < KS; ++ks) { frag_a<ST>(ak[ks], kA, x0, ks * 16); frag_a<ST>(av[ks], vA, x0, ks * 16); }
     float dk[DNP][4], dv[DNP][4];
 #pragma unroll
     for (int dn = 0; dn < DNP; ++dn) {
@@ -293,17 +310,17 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
       for (int hf = 0; hf < 2; ++hf) {
         const int nt = 2 * kk + hf;
         float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_rows<ST, KS>(s, ak, sQ, nt * 8, lane);
-        mma_rows<ST, KS>(dp, av, sdO, nt * 8, lane);
+        mma_rows<ST, KS>(s, ak, qR, nt * 8);
+        mma_rows<ST, KS>(dp, av, oR, nt * 8);
         // no masks needed: for query >= L the Q and dO rows are exactly zero (P^T there meets zero dO / Q rows,
         // sLse/sDelta are 0), and key rows >= L only feed dK/dV rows that are never stored
         const int c = nt * 8 + t * 2;  // query column
         const float2 lq = *reinterpret_cast<const float2*>(sLse + c), dl = *reinterpret_cast<const float2*>(sDelta + c);
         const float lq0 = lq.x, lq1 = lq.y, dl0 = dl.x, dl1 = dl.y;
-        pt[hf][0] = exp2f(s[0] * sl2 - lq0);
-        pt[hf][1] = exp2f(s[1] * sl2 - lq1);
-        pt[hf][2] = exp2f(s[2] * sl2 - lq0);
-        pt[hf][3] = exp2f(s[3] * sl2 - lq1);
+        pt[hf][0] = ex2_approx(s[0] * sl2 - lq0);
+        pt[hf][1] = ex2_approx(s[1] * sl2 - lq1);
+        pt[hf][2] = ex2_approx(s[2] * sl2 - lq0);
+        pt[hf][3] = ex2_approx(s[3] * sl2 - lq1);
         ds[hf][0] = pt[hf][0] * (dp[0] - dl0); ds[hf][1] = pt[hf][1] * (dp[1] - dl1);
         ds[hf][2] = pt[hf][2] * (dp[2] - dl0); ds[hf][3] = pt[hf][3] * (dp[3] - dl1);
       }
@@ -315,8 +332,8 @@ __global__ void __launch_bounds__(NT * 16) attn_bwd_kernel(const __nv_bfloat16* 
 #pragma unroll
       for (int dp2 = 0; dp2 < DNP / 2; ++dp2) {
         uint32_t dot[4], qt[4];
-        frag_b_cols<ST>(dot, sdO, kk * 16, dp2 * 16, lane);
-        frag_b_cols<ST>(qt, sQ, kk * 16, dp2 * 16, lane);
+        frag_b_cols<ST>(dot, oA, kk * 16, dp2 * 16);
+        frag_b_cols<ST>(qt, qA, kk * 16, dp2 * 16);
         mma_16816(dv[2 * dp2], ap, dot[0], dot[1]);
         mma_16816(dk[2 * dp2], as_, qt[0], qt[1]);
         if (2 * dp2 + 1 < DN) {
