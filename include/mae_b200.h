@@ -120,6 +120,12 @@ int mae_colsum_bf16(const void* x_bf16, int M, int N, float* out, mae_stream_t s
 int mae_gather_rows_bf16(const float* src, const int64_t* idx, int B, int n_sel, int L_src, int row_offset, int D,
                          void* out_bf16, mae_stream_t stream);
 
+/* dst rows b*L_src + idx[b*n_sel+j] <- 0, in the f32 buffer and (optionally) its bf16 copy: the kept rows of the
+ * decoder stream get no gradient from the prediction head (autograd of get_at_index(idx_mask) at reference
+ * src/models/mae.py:72); replaces two whole-buffer memsets. */
+int mae_zero_rows(float* dst, void* dst_bf16, const int64_t* idx, int B, int n_sel, int L_src, int D,
+                  mae_stream_t stream);
+
 /* out[d] += sum over the same row selection of src[.,d]  (mask_token / cls_token gradients). */
 int mae_colsum_rows_f32(const float* src, const int64_t* idx, int B, int n_sel, int L_src, int row_offset, int D,
                         float* out, mae_stream_t stream);

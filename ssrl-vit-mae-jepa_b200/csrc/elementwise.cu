@@ -434,6 +434,90 @@ __global__ void __launch_bounds__(256) masked_mse_kernel(const __nv_bfloat16* __
   }
 }
 
+// Fast path for 8x8 RGB patches (configs/mae.yaml): lane l owns pixels (py = l/4, px = 2*(l%4) + {0,1}) of the patch in
+// all three channels, i.e. six consecutive elements of the (py,px,c)-ordered target vector: three 8-byte image loads
+// (each 32-byte patch row is covered by 4 adjacent lanes = one sector), three 4-byte pred loads / dpred stores
+// (384 contiguous bytes per warp) and no shared-memory transpose.  Two patches per warp iteration, loads first.
+__global__ void __launch_bounds__(256) masked_mse_p8c3_kernel(const __nv_bfloat16* __restrict__ pred,
+                                                             const float* __restrict__ images,
+                                                             const int64_t* __restrict__ idx_mask, int B, int img,
+                                                             int n_mask, int norm_pix, float inv_numel,
+                                                             float* __restrict__ partials,
+                                                             __nv_bfloat16* __restrict__ dpred,
+                                                             float* __restrict__ target) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float s_red[8];
+  constexpr int ROWS = 2, PD = 192;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int grid = img >> 3;
+  const size_t plane = size_t(img) * img;
+  const int py = lane >> 2, px = (lane & 3) * 2;
+  float acc = 0.f;
+  const long long nrows = (long long)B * n_mask;
+  const long long stride = (long long)gridDim.x * wpb;
+  for (long long ra = (long long)blockIdx.x * wpb + wid; ra < nrows; ra += ROWS * stride) {
+    float2 ch[ROWS][3];
+    uint32_t pv[ROWS][3];
+    long long rr[ROWS];
+    bool ok[ROWS];
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) {
+      rr[k] = ra + k * stride;
+      ok[k] = rr[k] < nrows;
+      if (!ok[k]) rr[k] = ra;
+      const int b = int(rr[k] / n_mask);
+      int pidx = int(idx_mask[rr[k]]) - 1;
+      if (pidx < 0) pidx = 0;  // torch.clamp(idx_mask - 1, min=0)
+      const int pr = pidx / grid, pcn = pidx % grid;
+      const float* src = images + size_t(b) * 3 * plane + size_t(pr * 8 + py) * img + pcn * 8 + px;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ch[k][c] = *reinterpret_cast<const float2*>(src + c * plane);
+      const uint32_t* pp = reinterpret_cast<const uint32_t*>(pred + rr[k] * PD) + lane * 3;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) pv[k][j] = pp[j];
+    }
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) {
+      float t[6] = {ch[k][0].x, ch[k][1].x, ch[k][2].x, ch[k][0].y, ch[k][1].y, ch[k][2].y};
+      if (norm_pix) {  // opt-in MAE-paper variant: (t - mean) / sqrt(var_unbiased + 1e-6)
+        float s = 0.f, ss = 0.f;
+#pragma unroll
+        for (int e = 0; e < 6; ++e) { s += t[e]; ss += t[e] * t[e]; }
+        s = warp_sum(s); ss = warp_sum(ss);
+        const float mu = s / PD;
+        const float rsd = rsqrtf((ss - PD * mu * mu) / (PD - 1) + 1e-6f);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) t[e] = (t[e] - mu) * rsd;
+      }
+      if (!ok[k]) continue;
+      float d[6];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { d[2 * j] = bf16_lo(pv[k][j]) - t[2 * j]; d[2 * j + 1] = bf16_hi(pv[k][j]) - t[2 * j + 1]; }
+#pragma unroll
+      for (int e = 0; e < 6; ++e) acc += d[e] * d[e];
+      if (dpred) {
+        uint32_t* dp = reinterpret_cast<uint32_t*>(dpred + rr[k] * PD) + lane * 3;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) dp[j] = pack_bf16x2(2.0f * d[2 * j] * inv_numel, 2.0f * d[2 * j + 1] * inv_numel);
+      }
+      if (target) {
+        float2* tp = reinterpret_cast<float2*>(target + rr[k] * PD) + lane * 3;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) tp[j] = make_float2(t[2 * j], t[2 * j + 1]);
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) s_red[wid] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < wpb; ++i) t += s_red[i];
+    partials[blockIdx.x] = t;
+  }
+}
+
 __global__ void __launch_bounds__(256) finalize_loss_kernel(const float* __restrict__ partials, int n, float scale,
                                                            float* __restrict__ loss) {
   pdl_trigger();
@@ -489,6 +573,23 @@ __global__ void __launch_bounds__(256) gather_rows_bf16_kernel(const float* __re
     const long long r = i / D4;
     const float4 v = *reinterpret_cast<const float4*>(src + sel_row(r, idx, n_sel, L_src, row_offset) * D + d);
     *reinterpret_cast<uint2*>(out + r * D + d) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+// dst rows b*L_src + idx[b*n_sel+j] <- 0 (fp32 and optional bf16 copy): the kept rows of the decoder stream receive no
+// gradient from decoder_norm / decoder_pred (reference src/models/mae.py:72: only idx_mask rows are predicted).
+__global__ void __launch_bounds__(256) zero_rows_kernel(float* __restrict__ dst, __nv_bfloat16* __restrict__ dst_bf16,
+                                                       const int64_t* __restrict__ idx, int B, int n_sel, int L_src, int D) {
+  pdl_trigger();
+  pdl_wait();
+  const int D4 = D >> 2;
+  const long long n = (long long)B * n_sel * D4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int d = int(i % D4) * 4;
+    const long long r = i / D4;
+    const long long row = (r / n_sel) * L_src + idx[r];
+    *reinterpret_cast<float4*>(dst + row * D + d) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (dst_bf16) *reinterpret_cast<uint2*>(dst_bf16 + row * D + d) = make_uint2(0u, 0u);
   }
 }
 
@@ -726,8 +827,15 @@ extern "C" int mae_masked_mse(const void* pred, const float* images, const int64
   int grid = int((nrows + 7) / 8);
   if (grid > kMsePartials) grid = kMsePartials;
   const float inv_numel = 1.0f / (float(nrows) * float(pd));
-  mae_launch(masked_mse_kernel, dim3(grid), dim3(256), 8 * pd * sizeof(float), stream, reinterpret_cast<const __nv_bfloat16*>(pred), images, idx_mask, B, C, img, patch, n_mask, norm_pix, inv_numel,
-      partials, reinterpret_cast<__nv_bfloat16*>(dpred), target);
+  if (patch == 8 && C == 3 && (img % 8) == 0) {
+    const int g2 = int((nrows + 15) / 16) < grid ? int((nrows + 15) / 16) : grid;  // two patches per warp iteration
+    grid = g2 < 1 ? 1 : g2;
+    mae_launch(masked_mse_p8c3_kernel, dim3(grid), dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(pred), images,
+               idx_mask, B, img, n_mask, norm_pix, inv_numel, partials, reinterpret_cast<__nv_bfloat16*>(dpred), target);
+  } else {
+    mae_launch(masked_mse_kernel, dim3(grid), dim3(256), 8 * pd * sizeof(float), stream, reinterpret_cast<const __nv_bfloat16*>(pred), images, idx_mask, B, C, img, patch, n_mask, norm_pix, inv_numel,
+        partials, reinterpret_cast<__nv_bfloat16*>(dpred), target);
+  }
   if (cudaGetLastError() != cudaSuccess) return MAE_ERR_LAUNCH;
   mae_launch(finalize_loss_kernel, dim3(1), dim3(256), 0, stream, partials, grid, inv_numel, loss);
   return MAE_CHECK_LAUNCH();
@@ -752,6 +860,16 @@ extern "C" int mae_gather_rows_bf16(const float* src, const int64_t* idx, int B,
   if (!src || !out) return MAE_ERR_NULL;
   if (D % 4) return MAE_ERR_SHAPE;
   mae_launch(gather_rows_bf16_kernel, dim3(grid_for((long long)B * n_sel * (D / 4), 256)), dim3(256), 0, stream, src, idx, B, n_sel, L_src, row_offset, D, reinterpret_cast<__nv_bfloat16*>(out));
+  return MAE_CHECK_LAUNCH();
+}
+
+extern "C" int mae_zero_rows(float* dst, void* dst_bf16, const int64_t* idx, int B, int n_sel, int L_src, int D,
+                             cudaStream_t stream) {
+  if (B <= 0 || n_sel <= 0) return MAE_OK;
+  if (!dst || !idx) return MAE_ERR_NULL;
+  if (D % 4 || L_src <= 0) return MAE_ERR_SHAPE;
+  mae_launch(zero_rows_kernel, dim3(grid_for((long long)B * n_sel * (D / 4), 256)), dim3(256), 0, stream, dst,
+             reinterpret_cast<__nv_bfloat16*>(dst_bf16), idx, B, n_sel, L_src, D);
   return MAE_CHECK_LAUNCH();
 }
 

@@ -8,7 +8,9 @@
 // read the TMEM lane quarter (warp_id % 4), so the four warps of a quarter interleave the 16-column chunks.  Operand tiles are staged by TMA with the
 // 128-byte swizzle in a 4-deep mbarrier ring; accumulators live in TMEM (fp32), double buffered for
 // gemm_tn so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "mae_internal.h"
 #include "ptx.cuh"
@@ -77,8 +79,14 @@ struct GemmTnParams {
   int nchunks;  // N / bn
   int mtiles;   // ceil(M / 128)
   int nkb;      // ceil(K / 64)
-  int nstages;  // TMA ring depth (3 or 4, whatever fits next to the epilogue staging tiles)
-  int use_tma_store;  // bf16 outputs leave through TMA bulk tensor stores (off: MAE_GEMM_NO_TMA_STORE=1, A/B experiments)
+  int nstages;  // TMA ring depth (2..4, whatever fits next to the epilogue staging tiles)
+  int use_tma_store;  // epilogue tiles move through TMA (off: MAE_GEMM_NO_TMA_STORE=1, A/B experiments)
+  // shared-memory carve-up (byte offsets from the 1024-aligned base; computed on the host, see plan_smem)
+  uint32_t off_ring, off_hdr, off_tab;  // operand ring, barriers, GELU table (EPI 1 only)
+  uint32_t stg_a0, stg_b0;              // staging tiles [0, stg_nA) start at stg_a0, the rest at stg_b0
+  int stg_nA;
+  uint32_t stg_tile;                    // bytes per staging tile
+  int stg_tpw;                          // staging tiles per epilogue warp (1, or 2 for the dGELU TMA epilogue)
   const float* bias;          // [N] or null
   void* out;                  // bf16 [M,N] (EPI 0,1,3,4)  or  f32 [M,N] (EPI 2)
   __nv_bfloat16* pre_out;     // EPI 1: bf16 [M,N] GELU'(pre-activation), consumed by EPI 4
@@ -90,6 +98,7 @@ struct GemmSmemHdr {
   uint64_t empty[kStages];
   uint64_t tfull[2];
   uint64_t tempty[2];
+  uint64_t auxbar[4 * 4][2];  // dGELU epilogue: one per (epilogue warp, staging tile): "saved GELU' tile has landed"
   uint32_t tmem_base;
 };
 
@@ -100,10 +109,69 @@ struct GemmSmemHdr {
 // leave (or, for aux inputs, arrive) with 8 lanes covering one row, i.e. 4 complete rows per instruction.
 // ---------------------------------------------------------------------------------------------
 static constexpr int kStgRow = 144;                 // manual path: 128 data bytes + 16 pad, conflict-free 16-byte accesses
-// per epilogue warp: 32 x 144 B (manual path) or, for the TMA-store epilogues, 5 KB so that every warp's tile is
-// 1024-byte aligned (128-byte swizzle).  Kept as small as possible: dynamic smem comes out of the L1 carve-out.
-__host__ __device__ constexpr int stg_bytes(int epi) {
-  return (epi == MAE_EPI_BF16 || epi == MAE_EPI_GELU_BF16) ? 5 * 1024 : 32 * kStgRow;
+// Staging tiles per epilogue warp.  Manual path: one 32 x 144 B tile.  TMA epilogues: 1024-byte aligned tiles (128-byte
+// swizzle): plain bf16 / GELU one 5 KB tile (4 KB swizzled unit, or a ragged 32 x 144 B unit), dGELU two 4 KB tiles
+// (the saved GELU' tile of the next item is prefetched by TMA while the current one is multiplied and stored).
+// Kept as small as possible: dynamic smem comes out of the L1 carve-out.
+__host__ __device__ constexpr int stg_tile_bytes(int epi, bool tma) {
+  return !tma ? 32 * kStgRow : (epi == MAE_EPI_DGELU_BF16 ? 4 * 1024 : 5 * 1024);
+}
+__host__ __device__ constexpr int stg_tiles_per_warp(int epi, bool tma) { return (tma && epi == MAE_EPI_DGELU_BF16) ? 2 : 1; }
+
+// ---------------------------------------------------------------------------------------------
+// erf-GELU by table (EPI 1).  The pre-activation is a bf16 value, so GELU and GELU' are pure functions of 16 bits:
+// for 2^-20 <= |x| <= 16 both correctly rounded bf16 results come from a 2 x 3073-entry table (entry = gelu | gelu'<<16,
+// built on the host in double precision from erf), staged in shared memory; outside that range the results are
+// trivial (x/2 and 1/2; x and 1; -0 and 0) and are patched by a rarely taken warp-uniform branch.
+// Shared-memory addressing: entry of the raw 16-bit pattern i (sign included) lives at tab_base + 4*(i - kGeluLo),
+// i.e. the table of the negative inputs sits exactly 0x8000 entries (128 KB) above the positive one.
+// ---------------------------------------------------------------------------------------------
+static constexpr uint32_t kGeluLo = 107u << 7;                  // bf16 bits of 2^-20
+static constexpr uint32_t kGeluHi = 131u << 7;                  // bf16 bits of 16.0
+static constexpr uint32_t kGeluNT = kGeluHi - kGeluLo + 1;       // 3073 entries per sign
+static constexpr uint32_t kGeluTabBytes = kGeluNT * 4;
+static constexpr uint32_t kGeluNegOff = 0x8000u * 4;             // 131072
+__device__ uint32_t g_gelu_tab[2 * kGeluNT];
+
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+// out-of-table inputs (|x| < 2^-20, |x| > 16, inf, nan): entry = gelu | gelu' << 16
+__device__ __noinline__ uint32_t gelu_entry_slow(uint32_t bits16, uint32_t tab_s) {
+  const uint32_t a = bits16 & 0x7fffu;
+  if (a >= kGeluLo && a <= kGeluHi) return lds32(tab_s + bits16 * 4);
+  if (a < kGeluLo) {  // gelu = x/2 (exact), gelu' = 1/2
+    const float x = __uint_as_float(bits16 << 16);
+    return uint32_t(__bfloat16_as_ushort(__float2bfloat16_rn(0.5f * x))) | (0x3f00u << 16);
+  }
+  if (a > 0x7f80u) return bits16 | (bits16 << 16);                    // nan propagates
+  return (bits16 & 0x8000u) ? 0x8000u : (bits16 | (0x3f80u << 16));   // x <= -16: (-0, 0);  x >= 16: (x, 1)
+}
+// 8 packed bf16 pairs of pre-activations -> h (gelu) and d (gelu') pairs.  tab_s = shared address of the positive table
+// minus 4*kGeluLo.
+__device__ __forceinline__ void gelu_table8(const uint32_t (&pre)[8], uint32_t tab_s, uint32_t (&h)[8], uint32_t (&d)[8]) {
+  constexpr uint32_t lo2 = kGeluLo | (kGeluLo << 16), hi2 = kGeluHi | (kGeluHi << 16);
+  uint32_t bad = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t a2 = pre[i] & 0x7fff7fffu;
+    const uint32_t c2 = __vminu2(__vmaxu2(a2, lo2), hi2);  // per-halfword clamp into the table
+    bad |= c2 ^ a2;
+    const uint32_t k2 = c2 | (pre[i] & 0x80008000u);
+    const uint32_t e0 = lds32(tab_s + __byte_perm(k2, 0, 0x4410) * 4), e1 = lds32(tab_s + __byte_perm(k2, 0, 0x4432) * 4);
+    h[i] = __byte_perm(e0, e1, 0x5410);
+    d[i] = __byte_perm(e0, e1, 0x7632);
+  }
+  if (__any_sync(0xffffffffu, bad != 0)) {  // rare: some lane holds an input outside the table
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {  // (fully unrolled: dynamic indexing would push the arrays to local memory)
+      const uint32_t e0 = gelu_entry_slow(pre[i] & 0xffffu, tab_s), e1 = gelu_entry_slow(pre[i] >> 16, tab_s);
+      h[i] = __byte_perm(e0, e1, 0x5410);
+      d[i] = __byte_perm(e0, e1, 0x7632);
+    }
+  }
 }
 
 // TMA bulk tensor store of a [32 rows x 64 bf16] tile (128-byte swizzled in smem) -- SASS: UTMASTG
@@ -215,7 +283,6 @@ __device__ __forceinline__ void epilogue_item_manual(const GemmTnParams& p, uint
       stg_copy<false>(stg, abase, gpitch, row_bytes, rows_valid, lane);
       __syncwarp();
     }
-    uint32_t hkeep[UC / 16][8];  // EPI_GELU: second output (h) parked in registers while `pre` is flushed
     for (int sidx = 0; sidx < nsub; ++sidx) {
       uint32_t raw[16];
       tmem_ld16_issue(taddr + c0 + sidx * 16, raw);
@@ -250,20 +317,8 @@ __device__ __forceinline__ void epilogue_item_manual(const GemmTnParams& p, uint
         if constexpr (EPI == MAE_EPI_BF16) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-        } else if constexpr (EPI == MAE_EPI_GELU_BF16) {
-          // autocast semantics: the linear's output is rounded to bf16 and GELU reads that bf16 value.  Both
-          // GELU and GELU' are produced here (shared Phi); GELU' is what the backward needs, so it is saved
-          // in place of the pre-activation and the dgrad epilogue is a plain multiply.
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t pre2 = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-            float g0, g1, d0, d1;
-            gelu_fwd_bwd(bf16_lo(pre2), g0, d0);
-            gelu_fwd_bwd(bf16_hi(pre2), g1, d1);
-            o[i] = pack_bf16x2(d0, d1);
-            hkeep[sidx][i] = pack_bf16x2(g0, g1);
-          }
         } else {  // DGELU
+          static_assert(EPI != MAE_EPI_GELU_BF16, "the GELU epilogue lives in epilogue_item");
 #pragma unroll
           for (int i = 0; i < 8; ++i)  // pr = GELU'(pre) saved by the forward
             o[i] = pack_bf16x2(v[2 * i] * bf16_lo(pr[i]), v[2 * i + 1] * bf16_hi(pr[i]));
@@ -278,16 +333,6 @@ __device__ __forceinline__ void epilogue_item_manual(const GemmTnParams& p, uint
     if constexpr (F32) {
       stg_flush_add_f32(stg, reinterpret_cast<const uint8_t*>(p.aux) + goff, reinterpret_cast<uint8_t*>(p.out) + goff,
                         gpitch, row_bytes, rows_valid, lane);
-    } else if constexpr (EPI == MAE_EPI_GELU_BF16) {
-      stg_copy<true>(stg, reinterpret_cast<uint8_t*>(p.pre_out) + goff, gpitch, row_bytes, rows_valid, lane);
-      __syncwarp();
-      for (int sidx = 0; sidx < nsub; ++sidx) {
-        uint4* d = reinterpret_cast<uint4*>(stg + lane * kStgRow + sidx * SB);
-        d[0] = make_uint4(hkeep[sidx][0], hkeep[sidx][1], hkeep[sidx][2], hkeep[sidx][3]);
-        d[1] = make_uint4(hkeep[sidx][4], hkeep[sidx][5], hkeep[sidx][6], hkeep[sidx][7]);
-      }
-      __syncwarp();
-      stg_copy<true>(stg, reinterpret_cast<uint8_t*>(p.out) + goff, gpitch, row_bytes, rows_valid, lane);
     } else {
       stg_copy<true>(stg, reinterpret_cast<uint8_t*>(p.out) + goff, gpitch, row_bytes, rows_valid, lane);
     }
@@ -304,7 +349,7 @@ __device__ __forceinline__ void epilogue_item_manual(const GemmTnParams& p, uint
 template <int EPI>
 __device__ __forceinline__ void epilogue_item(const GemmTnParams& p, uint32_t taddr, int row0, int col_base, int grp,
                                               int rot, uint8_t* stg, int lane, const CUtensorMap* mo,
-                                              const CUtensorMap* mo2) {
+                                              const CUtensorMap* mo2, uint32_t tab_s) {
   constexpr bool F32 = (EPI == MAE_EPI_RESID_F32);
   constexpr int UC = F32 ? 32 : 64;          // columns per 128-byte unit
   constexpr int SB = F32 ? 64 : 32;          // bytes per 16-column sub-chunk
@@ -378,18 +423,13 @@ __device__ __forceinline__ void epilogue_item(const GemmTnParams& p, uint32_t ta
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
         } else if constexpr (EPI == MAE_EPI_GELU_BF16) {
-          // autocast semantics: the linear's output is rounded to bf16 and GELU reads that bf16 value.  Both
-          // GELU and GELU' are produced here (shared Phi); GELU' is what the backward needs, so it is saved
-          // in place of the pre-activation and the dgrad epilogue is a plain multiply.
+          // autocast semantics: the linear's output is rounded to bf16 and GELU reads that bf16 value.  GELU and
+          // GELU' of a bf16 input are table look-ups (exactly rounded); GELU' is what the backward needs, so it is
+          // saved in place of the pre-activation and the dgrad epilogue is a plain multiply.
+          uint32_t pre2[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t pre2 = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-            float g0, g1, d0, d1;
-            gelu_fwd_bwd(bf16_lo(pre2), g0, d0);
-            gelu_fwd_bwd(bf16_hi(pre2), g1, d1);
-            o[i] = pack_bf16x2(d0, d1);
-            hkeep[sidx][i] = pack_bf16x2(g0, g1);
-          }
+          for (int i = 0; i < 8; ++i) pre2[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          gelu_table8(pre2, tab_s, hkeep[sidx], o);
         } else {  // DGELU
 #pragma unroll
           for (int i = 0; i < 8; ++i)  // prk = GELU'(pre) saved by the forward
@@ -444,6 +484,77 @@ __device__ __forceinline__ void epilogue_item(const GemmTnParams& p, uint32_t ta
   }
 }
 
+// dGELU epilogue (fc2 dgrad), TMA both ways: the whole persistent loop of one epilogue warp.  Each item is split into
+// 64-column units dealt to the 4 warps of the lane quarter, rotated by the item counter (at most one unit per warp and
+// item since bn <= 256).  The saved GELU' tile [32 rows x 64 bf16] of the warp's NEXT unit is fetched by TMA into the
+// other of its two staging tiles while the current one is multiplied with the accumulator (row per thread, in place,
+// 128-byte swizzle = conflict free) and leaves through a TMA store: the LSU only sees shared-memory traffic.
+__device__ __forceinline__ void epilogue_loop_dgelu_tma(const GemmTnParams& p, GemmSmemHdr* hdr, uint32_t tmem_base,
+                                                        int q, int grp, int ew, uint8_t* tile0, uint8_t* tile1, int lane,
+                                                        int total, const CUtensorMap* mo, const CUtensorMap* maux) {
+  const int nunits = p.bn >> 6;
+  uint64_t* bars = hdr->auxbar[ew];
+  const uint32_t t_s[2] = {smem_u32(tile0), smem_u32(tile1)};
+  uint32_t ph0 = 0, ph1 = 0;
+  int acc = 0; uint32_t accphase = 0;
+  int it = 0;
+  int item = blockIdx.x;
+  if (item < total && lane == 0) {
+    const int u = (grp - 0) & (kEpiGroups - 1);
+    if (u < nunits) {
+      const int mt = item / p.nchunks, nc = item % p.nchunks;
+      mbar_expect_tx(&bars[0], 4096);
+      tma_load_2d(tile0, maux, &bars[0], nc * p.bn + u * 64, mt * BM + q * 32);
+    }
+  }
+  for (; item < total; item += gridDim.x, ++it) {
+    const int mt = item / p.nchunks, nc = item % p.nchunks;
+    const int par = it & 1;
+    {  // prefetch the next item's GELU' tile into the other staging tile
+      const int nitem = item + gridDim.x;
+      const int un = (grp - (it + 1)) & (kEpiGroups - 1);
+      if (nitem < total && un < nunits && lane == 0) {
+        tma_store_wait_read();  // the store issued from that tile (previous item) has finished reading it
+        const int mtn = nitem / p.nchunks, ncn = nitem % p.nchunks;
+        mbar_expect_tx(&bars[par ^ 1], 4096);
+        tma_load_2d(par ? tile0 : tile1, maux, &bars[par ^ 1], ncn * p.bn + un * 64, mtn * BM + q * 32);
+      }
+    }
+    mbar_wait(&hdr->tfull[acc], accphase);
+    tc_fence_after();
+    const int u = (grp - it) & (kEpiGroups - 1);
+    if (u < nunits) {  // warp-uniform
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc) * 256u + uint32_t(u * 64);
+      const uint32_t ts = t_s[par];
+      mbar_wait(&bars[par], par ? ph1 : ph0);
+      if (par) ph1 ^= 1; else ph0 ^= 1;
+#pragma unroll
+      for (int sidx = 0; sidx < 4; ++sidx) {
+        uint32_t raw[16];
+        tmem_ld16_issue(taddr + sidx * 16, raw);
+        uint32_t g[8];
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(g[0]), "=r"(g[1]), "=r"(g[2]), "=r"(g[3]) : "r"(swz128(ts, lane, 2 * sidx)));
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(g[4]), "=r"(g[5]), "=r"(g[6]), "=r"(g[7]) : "r"(swz128(ts, lane, 2 * sidx + 1)));
+        tmem_ld_wait();
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          o[i] = pack_bf16x2(__uint_as_float(raw[2 * i]) * bf16_lo(g[i]), __uint_as_float(raw[2 * i + 1]) * bf16_hi(g[i]));
+        sts128(swz128(ts, lane, 2 * sidx), o[0], o[1], o[2], o[3]);
+        sts128(swz128(ts, lane, 2 * sidx + 1), o[4], o[5], o[6], o[7]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tma_store_2d(mo, ts, nc * p.bn + u * 64, mt * BM + q * 32);
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&hdr->tempty[acc]);
+    acc ^= 1; if (acc == 0) accphase ^= 1;
+  }
+  if (lane == 0) tma_store_wait_all();
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -456,10 +567,8 @@ gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, c
   const uint32_t b_bytes = uint32_t(p.bn) * BK * 2;  // bn rows x 128 B
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const int nst = p.nstages;
-  uint8_t* stg_all = smem + nst * stage_bytes;
-  constexpr int kStgBytes = stg_bytes(EPI);
-  GemmSmemHdr* hdr = reinterpret_cast<GemmSmemHdr*>(stg_all + 4 * kEpiGroups * kStgBytes);
-
+  uint8_t* ring = smem + p.off_ring;
+  GemmSmemHdr* hdr = reinterpret_cast<GemmSmemHdr*>(smem + p.off_hdr);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total = p.mtiles * p.nchunks;
@@ -471,9 +580,16 @@ gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, c
     tma_prefetch_desc(&mapO2);
     for (int s = 0; s < nst; ++s) { mbar_init(&hdr->full[s], 1); mbar_init(&hdr->empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&hdr->tfull[a], 1); mbar_init(&hdr->tempty[a], 4 * kEpiGroups); }
+    if constexpr (EPI == MAE_EPI_DGELU_BF16)
+      for (int w = 0; w < 4 * kEpiGroups; ++w) { mbar_init(&hdr->auxbar[w][0], 1); mbar_init(&hdr->auxbar[w][1], 1); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(&hdr->tmem_base, 512);
+  if constexpr (EPI == MAE_EPI_GELU_BF16) {  // constant table (not produced by the previous kernel): stage it before pdl_wait
+    uint32_t* tpos = reinterpret_cast<uint32_t*>(smem + p.off_tab);
+    uint32_t* tneg = reinterpret_cast<uint32_t*>(smem + p.off_tab + kGeluNegOff);
+    for (uint32_t i = threadIdx.x; i < kGeluNT; i += kGemmThreads) { tpos[i] = g_gelu_tab[i]; tneg[i] = g_gelu_tab[kGeluNT + i]; }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -487,7 +603,7 @@ gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, c
         const int mt = item / p.nchunks, nc = item % p.nchunks;
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(&hdr->empty[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sa = ring + stage * stage_bytes;
           mbar_expect_tx(&hdr->full[stage], stage_bytes);
           tma_load_2d(sa, &mapA, &hdr->full[stage], kb * BK, mt * BM);
           tma_load_2d(sa + a_bytes, &mapB, &hdr->full[stage], kb * BK, nc * p.bn);
@@ -507,7 +623,7 @@ gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, c
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(&hdr->full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sa = smem_u32(ring + stage * stage_bytes);
           const uint32_t sb = sa + a_bytes;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
@@ -526,22 +642,37 @@ gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, c
   } else {
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int grp = (warp - 2) >> 2;  // which of the quarter's kEpiGroups warps: takes units grp, grp+4, ...
-    uint8_t* stg = stg_all + (warp - 2) * kStgBytes;
-    int acc = 0; uint32_t accphase = 0;
-    int it = 0;
-    for (int item = blockIdx.x; item < total; item += gridDim.x, ++it) {
-      const int mt = item / p.nchunks, nc = item % p.nchunks;
-      mbar_wait(&hdr->tfull[acc], accphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc) * 256u;
-      if constexpr (EPI == MAE_EPI_BF16 || EPI == MAE_EPI_GELU_BF16)
-        epilogue_item<EPI>(p, taddr, mt * BM + q * 32, nc * p.bn, grp, it, stg, lane, &mapO, &mapO2);
-      else
-        epilogue_item_manual<EPI>(p, taddr, mt * BM + q * 32, nc * p.bn, grp, stg, lane);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&hdr->tempty[acc]);
-      acc ^= 1; if (acc == 0) accphase ^= 1;
+    const int ew = warp - 2;
+    auto tile_ptr = [&](int t) -> uint8_t* {
+      return smem + (t < p.stg_nA ? p.stg_a0 + uint32_t(t) * p.stg_tile : p.stg_b0 + uint32_t(t - p.stg_nA) * p.stg_tile);
+    };
+    uint8_t* stg = tile_ptr(ew * p.stg_tpw);
+    bool done = false;
+    if constexpr (EPI == MAE_EPI_DGELU_BF16) {
+      if (p.use_tma_store) {
+        epilogue_loop_dgelu_tma(p, hdr, tmem_base, q, grp, ew, stg, tile_ptr(ew * p.stg_tpw + 1), lane, total, &mapO, &mapO2);
+        done = true;
+      }
+    }
+    if (!done) {
+      uint32_t tab_s = 0;
+      if constexpr (EPI == MAE_EPI_GELU_BF16) tab_s = smem_u32(smem + p.off_tab) - kGeluLo * 4;
+      int acc = 0; uint32_t accphase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < total; item += gridDim.x, ++it) {
+        const int mt = item / p.nchunks, nc = item % p.nchunks;
+        mbar_wait(&hdr->tfull[acc], accphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc) * 256u;
+        if constexpr (EPI == MAE_EPI_BF16 || EPI == MAE_EPI_GELU_BF16)
+          epilogue_item<EPI>(p, taddr, mt * BM + q * 32, nc * p.bn, grp, it, stg, lane, &mapO, &mapO2, tab_s);
+        else
+          epilogue_item_manual<EPI>(p, taddr, mt * BM + q * 32, nc * p.bn, grp, stg, lane);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hdr->tempty[acc]);
+        acc ^= 1; if (acc == 0) accphase ^= 1;
+      }
     }
     if (lane == 0) tma_store_wait_all();  // outstanding bulk stores must complete before the CTA's smem goes away
   }
@@ -557,10 +688,8 @@ static int pick_bn(int N) {
 }
 
 template <int EPI>
-static int launch_gemm_tn(const GemmTnParams& p, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo,
-                          const CUtensorMap& mo2, cudaStream_t st) {
-  const size_t smem = size_t(p.nstages) * (BM * BK * 2 + p.bn * BK * 2) + 4 * kEpiGroups * stg_bytes(EPI) +
-                      sizeof(GemmSmemHdr) + 1024;
+static int launch_gemm_tn(const GemmTnParams& p, size_t smem, const CUtensorMap& ma, const CUtensorMap& mb,
+                          const CUtensorMap& mo, const CUtensorMap& mo2, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -571,6 +700,88 @@ static int launch_gemm_tn(const GemmTnParams& p, const CUtensorMap& ma, const CU
   const int grid = total < num_sms() ? total : num_sms();
   mae_launch(gemm_tn_kernel<EPI>, dim3(grid), dim3(kGemmThreads), smem, st, p, ma, mb, mo, mo2);
   return cudaGetLastError() == cudaSuccess ? MAE_OK : MAE_ERR_LAUNCH;
+}
+
+static constexpr size_t kSmemMax = 227 * 1024;
+static inline uint32_t up1k(size_t x) { return uint32_t((x + 1023) & ~size_t(1023)); }
+
+// Shared-memory plan of one gemm_tn launch: picks the ring depth and fills the offsets in `p`; returns the dynamic
+// smem size to request (0 = does not fit).  Regions are 1024-byte aligned relative to the kernel's aligned base.
+//   plain:  [ring][hdr][staging tiles]
+//   GELU:   [gelu table +][ring][hdr][staging A ...]   ...128 KB above the + table: [gelu table -][staging B ...]
+static size_t plan_smem(GemmTnParams& p, int epi) {
+  const bool tma = p.use_tma_store != 0;
+  p.stg_tile = uint32_t(stg_tile_bytes(epi, tma));
+  p.stg_tpw = stg_tiles_per_warp(epi, tma);
+  const int ntiles = 4 * kEpiGroups * p.stg_tpw;
+  const size_t per_stage = BM * BK * 2 + size_t(p.bn) * BK * 2;
+  const size_t hdr = up1k(sizeof(GemmSmemHdr));
+  int want = 4;
+  // Epilogues that touch global memory through the LSU (fp32 residual, manual dGELU) run faster with a bigger L1: dynamic
+  // smem comes out of the same 228 KB, and with K <= 192 (3 k-blocks per item) two ring stages already cover the loop.
+  if ((epi == MAE_EPI_DGELU_BF16 || epi == MAE_EPI_RESID_F32) && p.nkb <= 3) want = 2;
+  if (const char* e = getenv("MAE_GEMM_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 4) want = v; }  // experiments
+  p.off_tab = 0;
+  if (epi != MAE_EPI_GELU_BF16) {
+    const size_t fixed = hdr + size_t(ntiles) * p.stg_tile + 1024;
+    int nst = want;
+    while (nst > 2 && fixed + nst * per_stage > kSmemMax) --nst;
+    if (fixed + nst * per_stage > kSmemMax) return 0;
+    p.nstages = nst;
+    p.off_ring = 0;
+    p.off_hdr = uint32_t(nst * per_stage);
+    p.stg_a0 = p.off_hdr + uint32_t(hdr);
+    p.stg_nA = ntiles; p.stg_b0 = 0;
+    return fixed + nst * per_stage;
+  }
+  // GELU: the two table halves are pinned 128 KB apart; ring, barriers and staging tiles fill the gaps around them
+  p.off_ring = up1k(kGeluTabBytes);
+  const size_t gapA_end = kGeluNegOff;  // start of the negative table
+  int nst = want;
+  while (nst > 2 && p.off_ring + nst * per_stage + hdr > gapA_end) --nst;
+  if (p.off_ring + nst * per_stage + hdr > gapA_end) return 0;
+  p.nstages = nst;
+  p.off_hdr = p.off_ring + uint32_t(nst * per_stage);
+  p.stg_a0 = p.off_hdr + uint32_t(hdr);
+  int nA = int((gapA_end - p.stg_a0) / p.stg_tile);
+  if (nA > ntiles) nA = ntiles;
+  p.stg_nA = nA;
+  p.stg_b0 = up1k(kGeluNegOff + kGeluTabBytes);
+  const size_t total = size_t(p.stg_b0) + size_t(ntiles - nA) * p.stg_tile + 1024;
+  return total <= kSmemMax ? total : 0;
+}
+
+// Host side of the GELU table (see gelu_table8): entry(x) = bf16(gelu(x)) | bf16(gelu'(x)) << 16 for the bf16 inputs
+// x = +-[2^-20, 16], evaluated in double precision (gelu = x Phi(x), gelu' = Phi(x) + x phi(x)).
+static uint32_t host_bf16_bits(double v) {
+  float f = float(v);
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return u >> 16;
+  u += 0x7fffu + ((u >> 16) & 1u);  // round to nearest even
+  return u >> 16;
+}
+static int ensure_gelu_table() {
+  static bool done[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return MAE_ERR_DRIVER;
+  if (done[dev]) return MAE_OK;
+  static uint32_t host[2 * kGeluNT];
+  for (int sgn = 0; sgn < 2; ++sgn)
+    for (uint32_t i = 0; i < kGeluNT; ++i) {
+      const uint32_t bits = (kGeluLo + i) | (sgn ? 0x8000u : 0u);
+      const uint32_t fb = bits << 16;
+      float xf;
+      memcpy(&xf, &fb, 4);
+      const double x = xf;
+      const double cdf = 0.5 * erfc(-x * 0.70710678118654752440);
+      const double pdf = 0.39894228040143267794 * exp(-0.5 * x * x);
+      host[sgn * kGeluNT + i] = host_bf16_bits(x * cdf) | (host_bf16_bits(cdf + x * pdf) << 16);
+    }
+  // one-time, synchronous: later launches on any stream see the table
+  if (cudaMemcpyToSymbol(g_gelu_tab, host, sizeof(host)) != cudaSuccess) return MAE_ERR_DRIVER;
+  done[dev] = true;
+  return MAE_OK;
 }
 
 }  // namespace mae
@@ -588,15 +799,6 @@ extern "C" int mae_gemm_tn(const void* A, const void* B, int M, int N, int K, in
   p.nchunks = N / p.bn;
   p.mtiles = (M + BM - 1) / BM;
   p.nkb = (K + BK - 1) / BK;
-  {
-    const size_t fixed = 4 * kEpiGroups * stg_bytes(epi) + sizeof(GemmSmemHdr) + 1024;
-    const size_t per_stage = BM * BK * 2 + size_t(p.bn) * BK * 2;
-    p.nstages = (fixed + 4 * per_stage <= 227 * 1024) ? 4 : 3;
-    // Epilogues that touch global memory through the LSU (fp32 residual, dGELU) run faster with a bigger L1: dynamic
-    // smem comes out of the same 228 KB, and with K <= 192 (3 k-blocks per item) two ring stages already cover the loop.
-    if ((epi == MAE_EPI_DGELU_BF16 || epi == MAE_EPI_RESID_F32) && p.nkb <= 3) p.nstages = 2;
-    if (const char* e = getenv("MAE_GEMM_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= p.nstages) p.nstages = v; }  // experiments
-  }
   p.bias = bias; p.out = out; p.pre_out = reinterpret_cast<__nv_bfloat16*>(pre_out); p.aux = aux;
   if (!A || !B || !out) return MAE_ERR_NULL;
   if (epi == MAE_EPI_GELU_BF16 && !pre_out) return MAE_ERR_NULL;
@@ -608,23 +810,29 @@ extern "C" int mae_gemm_tn(const void* A, const void* B, int M, int N, int K, in
   if (rc) return rc;
   {
     static const bool no_tma = getenv("MAE_GEMM_NO_TMA_STORE") != nullptr;
-    p.use_tma_store = ((epi == MAE_EPI_BF16 || epi == MAE_EPI_GELU_BF16) && !no_tma) ? 1 : 0;
+    p.use_tma_store = ((epi == MAE_EPI_BF16 || epi == MAE_EPI_GELU_BF16 || (epi == MAE_EPI_DGELU_BF16 && p.bn % 64 == 0)) &&
+                       !no_tma) ? 1 : 0;
   }
-  // output tensor maps: [32 rows x 64 bf16] boxes, 128-byte swizzle (dummy = A's map when unused)
+  const size_t smem = plan_smem(p, epi);
+  if (!smem) return MAE_ERR_SHAPE;
+  // epilogue tensor maps: [32 rows x 64 bf16] boxes, 128-byte swizzle (dummy = A's map when unused)
   mo = ma; mo2 = ma;
   if (p.use_tma_store) {
     rc = make_tmap_bf16(&mo, out, M, N, N, 32);
     if (rc) return rc;
-    if (epi == MAE_EPI_GELU_BF16) {
-      rc = make_tmap_bf16(&mo2, pre_out, M, N, N, 32);
-      if (rc) return rc;
-    }
+    if (epi == MAE_EPI_GELU_BF16) rc = make_tmap_bf16(&mo2, pre_out, M, N, N, 32);
+    if (epi == MAE_EPI_DGELU_BF16) rc = make_tmap_bf16(&mo2, aux, M, N, N, 32);
+    if (rc) return rc;
+  }
+  if (epi == MAE_EPI_GELU_BF16) {
+    rc = ensure_gelu_table();
+    if (rc) return rc;
   }
   switch (epi) {
-    case MAE_EPI_BF16: return launch_gemm_tn<MAE_EPI_BF16>(p, ma, mb, mo, mo2, stream);
-    case MAE_EPI_GELU_BF16: return launch_gemm_tn<MAE_EPI_GELU_BF16>(p, ma, mb, mo, mo2, stream);
-    case MAE_EPI_RESID_F32: return launch_gemm_tn<MAE_EPI_RESID_F32>(p, ma, mb, mo, mo2, stream);
-    case MAE_EPI_DGELU_BF16: return launch_gemm_tn<MAE_EPI_DGELU_BF16>(p, ma, mb, mo, mo2, stream);
+    case MAE_EPI_BF16: return launch_gemm_tn<MAE_EPI_BF16>(p, smem, ma, mb, mo, mo2, stream);
+    case MAE_EPI_GELU_BF16: return launch_gemm_tn<MAE_EPI_GELU_BF16>(p, smem, ma, mb, mo, mo2, stream);
+    case MAE_EPI_RESID_F32: return launch_gemm_tn<MAE_EPI_RESID_F32>(p, smem, ma, mb, mo, mo2, stream);
+    case MAE_EPI_DGELU_BF16: return launch_gemm_tn<MAE_EPI_DGELU_BF16>(p, smem, ma, mb, mo, mo2, stream);
     default: return MAE_ERR_SHAPE;
   }
 }

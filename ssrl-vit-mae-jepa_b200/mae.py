@@ -522,8 +522,8 @@ class MAEEngine:
                            o("decoder.decoder_pred.bias"), st)
         calls.mae_gemm_tn(_ptr(dpred), self.pwt(o("decoder.decoder_pred.weight")), Mm, Dd, pd, EPI_BF16, None,
                           _ptr(ws["g"]), None, None, st)
-        dx_a[:Md * Dd].zero_()
-        dxb_a[:Md * Dd].zero_()
+        # only the masked rows receive a gradient from the prediction head: zero the kept rows, LN-bwd writes the rest
+        calls.mae_zero_rows(_ptr(dx_a), _ptr(dxb_a), _ptr(ws["idx_keep"]), B, Lk, L, Dd, st)
         calls.mae_layernorm_bwd(_ptr(ws["g"]), _ptr(ws["x_dec"]), _ptr(ws["meand"]), _ptr(ws["rstdd"]),
                                 self.pf(o("decoder.decoder_norm.weight")), None, _ptr(ws["idx_mask"]), Lm, L, Mm, Dd,
                                 _ptr(dx_a), _ptr(dxb_a), self.pg(o("decoder.decoder_norm.weight")),

@@ -293,6 +293,89 @@ def test_masked_mse(norm_pix):
     assert max_err(dpred, pr.grad) <= 2 ** -8 * pr.grad.abs().max().item()
 
 
+def test_gemm_tn_gelu_table_exact():
+    """EPI 1 on hand-picked pre-activations (identity weights, K = 16): the table-driven GELU / GELU' must equal the
+    correctly rounded bf16 of the double-precision erf formulas for EVERY bf16 input, including the out-of-table
+    inputs (|x| < 2^-20, |x| > 16, +-0, +-inf)."""
+    K = N = 16
+    bits = torch.arange(0, 65536, dtype=torch.int32)
+    a = bits & 0x7fff
+    bits = bits[(a < 0x7f80) & ((a >= 0x80) | (a == 0))]  # finite, no subnormals (inf / nan are fed through the bias below)
+    xs = bits.to(torch.int16).view(torch.bfloat16)
+    M = (xs.numel() + N - 1) // N
+    pad = torch.zeros(M * N - xs.numel(), dtype=torch.bfloat16)
+    X = torch.cat([xs, pad]).view(M, N)
+    # identity weights: acc[m, n] = X[m, n] exactly, so every bf16 value reaches the epilogue as a pre-activation
+    A = X.to(dev)
+    I = bf(torch.eye(N)).to(dev)
+    h, dact = gemm_tn(A, I, 1, None)
+
+    def refs(xd):
+        cdf = 0.5 * torch.erfc(-xd / math.sqrt(2.0))
+        pdf = torch.exp(-0.5 * xd * xd) / math.sqrt(2 * math.pi)
+        h_ref = torch.where(torch.isinf(xd), torch.where(xd > 0, xd, torch.zeros_like(xd)), xd * cdf)
+        d_ref = torch.where(torch.isinf(xd), (xd > 0).double(), cdf + xd * pdf)
+        return h_ref.float().to(torch.bfloat16), d_ref.float().to(torch.bfloat16)
+
+    h_ref, d_ref = refs(X.double())
+    hc, dc = h.cpu(), dact.cpu()
+    assert torch.equal(hc.float(), h_ref.float()), (hc.float() - h_ref.float()).abs().max()
+    assert torch.equal(dc.float(), d_ref.float()), (dc.float() - d_ref.float()).abs().max()
+    # ... and it agrees with torch's own fp32 erf GELU of the bf16 input to within one bf16 ulp, plus the fp32
+    # cancellation error of torch's 1 + erf(x / sqrt 2) in the negative tail (~6e-8 |x|; the table has none)
+    t = F.gelu(X.float()).to(torch.bfloat16).float()
+    ulp = torch.maximum(t.abs(), torch.tensor(2.0 ** -120)) * 2 ** -7
+    assert ((hc.float() - t).abs() <= ulp + 2e-7 * X.float().abs()).all()
+    report("gemm_tn_gelu_table", mismatches_vs_torch=int((hc.float() != t).sum()), n=int(t.numel()))
+    # +-inf, +-big through the bias (acc = 0)
+    special = torch.tensor([float("inf"), float("-inf"), 3e38, -3e38, 17.0, -17.0, 16.0, -16.0, 1e-7, -1e-7, 2.0 ** -20, -2.0 ** -20,
+                            0.0, -0.0, 1.0, -1.0])
+    hs, ds = gemm_tn(torch.zeros(64, K, dtype=torch.bfloat16, device=dev), I, 1, special.to(dev))
+    hs_ref, ds_ref = refs(special.to(torch.bfloat16).double())
+    assert torch.equal(hs[0].cpu().float(), hs_ref.float()) and torch.equal(ds[5].cpu().float(), ds_ref.float())
+    nan = torch.full((128, 16), float("nan"), dtype=torch.bfloat16, device=dev)
+    hn, dn = gemm_tn(nan, I, 1, None)
+    assert torch.isnan(hn.float()).all() and torch.isnan(dn.float()).all()
+
+
+def test_zero_rows():
+    B, L, Lk, D = 7, 145, 36, 192
+    g = torch.Generator().manual_seed(12)
+    k, m = [t.to(dev) for t in O.random_token_mask_from_noise(torch.rand(B, L, generator=g), 0.75)]
+    x = torch.randn(B, L, D, generator=g).to(dev)
+    xb = bf(x)
+    x0, xb0 = x.clone(), xb.clone()
+    calls.mae_zero_rows(p(x), p(xb), p(k), B, Lk, L, D, stream())
+    keep = torch.zeros(B, L, dtype=torch.bool, device=dev).scatter_(1, k, True)
+    assert (x[keep] == 0).all() and (xb[keep] == 0).all()
+    assert torch.equal(x[~keep], x0[~keep]) and torch.equal(xb[~keep], xb0[~keep])
+
+
+@pytest.mark.parametrize("patch,img,norm_pix", [(4, 32, 0), (16, 64, 1), (6, 36, 0)])
+def test_masked_mse_generic_patch(patch, img, norm_pix):
+    """patch sizes other than the 8x8 fast path go through the generic kernel."""
+    B = 5
+    n_patches = (img // patch) ** 2
+    L, pd = n_patches + 1, 3 * patch * patch
+    g = torch.Generator().manual_seed(22)
+    images = torch.randn(B, 3, img, img, generator=g).to(dev)
+    _, m = O.random_token_mask_from_noise(torch.rand(B, L, generator=g), 0.75)
+    m = m.to(dev)
+    Lm = m.shape[1]
+    pred = bf(torch.randn(B, Lm, pd, generator=g)).to(dev)
+    loss, parts = torch.zeros(1, device=dev), torch.empty(4096, device=dev)
+    dpred, target = torch.empty_like(pred), torch.empty(B, Lm, pd, device=dev)
+    calls.mae_masked_mse(p(pred), p(images), p(m), B, 3, img, patch, Lm, norm_pix, p(loss), p(parts), p(dpred), p(target), stream())
+    t_ref = O.get_at_index(O.patchify(images, patch), torch.clamp(m - 1, min=0))
+    if norm_pix:
+        t_ref = (t_ref - t_ref.mean(-1, keepdim=True)) / (t_ref.var(-1, keepdim=True) + 1e-6) ** 0.5
+        assert max_err(target, t_ref) < 1e-4
+    else:
+        assert torch.equal(target, t_ref)
+    l_ref = F.mse_loss(pred.float(), t_ref)
+    assert abs(loss.item() - l_ref.item()) < 1e-5 * l_ref.item() + 1e-7
+
+
 def test_casts_and_clip_adamw():
     g = torch.Generator().manual_seed(31)
     n = 100_003
