@@ -149,6 +149,17 @@ int mae_clip_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, l
                    float beta2, float eps, float weight_decay, float max_norm, int step, const float* partials,
                    int n_partials, float* grad_norm_out, mae_stream_t stream);
 
+/* The input transform that precedes the hot path (reference src/data.py:15-34), on the GPU: for sample b, crop
+ * rows [i, i+h) x cols [j, j+w) of the uint8 image (B,C,Hs,Ws; torchvision STL10.data layout), resize to S x S exactly
+ * like Pillow's 8-bit bilinear ImagingResample (what RandomResizedCrop does to a PIL image: two separable fixed-point
+ * passes with a uint8 intermediate), flip horizontally if flip != 0, then ToTensor (/255) and Normalize((x-.5)/.5).
+ * params (B,5) int32 = (i, j, h, w, flip) per sample, device memory (the random draws of RandomResizedCrop.get_params
+ * and RandomHorizontalFlip stay with the caller, like the torch.rand of the mask).  The evaluation transform
+ * (Resize(96)+CenterCrop(96) on 96x96 images = identity) is (0, 0, Hs, Ws, 0).  out (B,C,S,S) f32.  Integer path:
+ * bit-exact.  S % 4 == 0; the source may be at most 3x the output size per axis. */
+int mae_augment_u8(const uint8_t* images, const int* params, int B, int C, int Hs, int Ws, int S, float* out,
+                   mae_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

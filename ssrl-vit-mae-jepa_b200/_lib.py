@@ -31,6 +31,7 @@ SIGNATURES = {
     "mae_gather_rows_bf16": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "mae_colsum_rows_f32": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "mae_zero_rows": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "mae_augment_u8": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "mae_cast_bf16": [_vp, _vp, _ll, _vp],
     "mae_transpose_cast_bf16": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "mae_grad_sumsq": [_vp, _ll, _vp, _i, _vp],

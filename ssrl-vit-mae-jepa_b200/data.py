@@ -5,11 +5,16 @@ training, Resize/CenterCrop for evaluation, ToTensor, Normalize(0.5, 0.5)).
 STL-10 cannot be downloaded in this environment (no network), so when the dataset is not already on disk under
 ``data/`` -- or when ``MAE_SYNTHETIC_DATA=1`` -- a deterministic synthetic STL-10-shaped dataset (same sizes,
 value range [-1, 1] after normalisation, 10 classes) is used instead; everything downstream is unchanged.
+
+``<section>.gpu_augment: true`` in the YAML switches the loaders to raw uint8 batches; the trainer then applies the same
+transforms on the GPU (``GpuAugment`` -> ``mae_augment_u8``, bit-exact Pillow bilinear), which removes the CPU
+transform from the loader workers and cuts the host->device copy 4x.
 """
 from __future__ import annotations
 
+import math
 import os
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 from torch.utils.data import DataLoader, Dataset, Subset, random_split
@@ -22,8 +27,9 @@ class SyntheticSTL10(Dataset):
     """Deterministic stand-in: item i is a smooth random 96x96 RGB field in [-1, 1] (seeded by (split, i)) with label
     i % 10.  ``train=True`` applies a random horizontal flip like the reference's augmentation."""
 
-    def __init__(self, split: str, train: bool = True, size: int | None = None, image_size: int = 96):
-        self.split, self.train, self.image_size = split, train, image_size
+    def __init__(self, split: str, train: bool = True, size: int | None = None, image_size: int = 96,
+                 raw_uint8: bool = False):
+        self.split, self.train, self.image_size, self.raw_uint8 = split, train, image_size, raw_uint8
         self.n = int(size if size is not None else SPLIT_SIZES[split])
         self.salt = {"unlabeled": 0, "train": 1, "test": 2}[split]
 
@@ -35,18 +41,93 @@ class SyntheticSTL10(Dataset):
         low = torch.rand(3, 12, 12, generator=g)
         img = torch.nn.functional.interpolate(low[None], size=self.image_size, mode="bilinear", align_corners=False)[0]
         img = (img + 0.1 * torch.rand(3, self.image_size, self.image_size, generator=g)).clamp_(0, 1)
+        if self.raw_uint8:  # as stored by torchvision's STL10.data; crop / flip / normalize happen on the GPU (GpuAugment)
+            return (img * 255.0).round().to(torch.uint8), (int(i) % 10 if self.split != "unlabeled" else -1)
         if self.train and torch.rand(1, generator=g).item() < 0.5:
             img = img.flip(-1)
         label = int(i) % 10 if self.split != "unlabeled" else -1
         return (img - 0.5) / 0.5, label
 
 
-def _real_stl10(split: str, train: bool):
+class RawSTL10(Dataset):
+    """The real STL-10 arrays (``STL10.data`` (N,3,96,96) uint8, ``STL10.labels``) without any CPU transform."""
+
+    def __init__(self, stl10):
+        self.data, self.labels = stl10.data, getattr(stl10, "labels", None)
+
+    def __len__(self) -> int:
+        return len(self.data)
+
+    def __getitem__(self, i: int):
+        return torch.from_numpy(self.data[i]), (int(self.labels[i]) if self.labels is not None else -1)
+
+
+class GpuAugment:
+    """The reference's transforms (``src/data.py:15-34``) applied on the GPU to uint8 batches (B,3,H,W):
+    ``train=True``: RandomResizedCrop(size, scale, ratio) -> RandomHorizontalFlip -> ToTensor -> Normalize(.5,.5);
+    ``train=False``: Resize/CenterCrop (identity for 96x96 STL-10) -> ToTensor -> Normalize.
+    The pixels come from ``mae_augment_u8`` (bit-exact Pillow bilinear); the random crop boxes / flips are drawn here
+    with torch on the device, all samples at once, following ``RandomResizedCrop.get_params`` (10 attempts of
+    area ~ U(scale), log-ratio ~ U(log ratio), first fitting one wins, centre-crop fallback).  H2D traffic is 4x
+    smaller than shipping float32 images."""
+
+    def __init__(self, size: int = 96, scale=(0.8, 1.0), ratio=(3.0 / 4.0, 4.0 / 3.0), train: bool = True,
+                 generator: Optional[torch.Generator] = None):
+        self.size, self.scale, self.ratio, self.train, self.generator = size, scale, ratio, train, generator
+
+    def draw_params(self, B: int, H: int, W: int, device) -> torch.Tensor:
+        """(B,5) int32 rows (i, j, h, w, flip) on ``device``."""
+        if not self.train:
+            p = torch.zeros(B, 5, dtype=torch.int32, device=device)
+            p[:, 2], p[:, 3] = H, W
+            return p
+        g = self.generator
+        u = torch.rand(B, 10, 2, device=device, generator=g, dtype=torch.float32)
+        area = (H * W) * (self.scale[0] + (self.scale[1] - self.scale[0]) * u[..., 0]).double()
+        lo, hi = math.log(self.ratio[0]), math.log(self.ratio[1])
+        aspect = torch.exp((lo + (hi - lo) * u[..., 1])).double()
+        w = torch.round(torch.sqrt(area * aspect)).long()
+        h = torch.round(torch.sqrt(area / aspect)).long()
+        ok = (w > 0) & (w <= W) & (h > 0) & (h <= H)
+        first = torch.argmax(ok.int(), dim=1, keepdim=True)  # first fitting attempt (0 if none)
+        any_ok = ok.any(dim=1)
+        w = torch.where(any_ok, w.gather(1, first)[:, 0], torch.full_like(any_ok, W, dtype=torch.long))
+        h = torch.where(any_ok, h.gather(1, first)[:, 0], torch.full_like(any_ok, H, dtype=torch.long))
+        # fallback for an image whose aspect is inside `ratio` (square STL-10): the whole image
+        v = torch.rand(B, 3, device=device, generator=g, dtype=torch.float32).double()
+        i = torch.clamp((v[:, 0] * (H - h + 1)).long(), max=H - 1)
+        j = torch.clamp((v[:, 1] * (W - w + 1)).long(), max=W - 1)
+        i, j = torch.minimum(i, H - h), torch.minimum(j, W - w)
+        flip = (v[:, 2] < 0.5).long()
+        return torch.stack([i, j, h, w, flip], dim=1).to(torch.int32).contiguous()
+
+    def __call__(self, images_u8: torch.Tensor, params: Optional[torch.Tensor] = None) -> torch.Tensor:
+        from ._lib import calls
+
+        if not images_u8.is_cuda or images_u8.dtype != torch.uint8 or images_u8.dim() != 4:
+            raise RuntimeError("GpuAugment needs a CUDA uint8 (B,C,H,W) batch (there is no CPU fallback)")
+        images_u8 = images_u8.contiguous()
+        B, C, H, W = images_u8.shape
+        if params is None:
+            params = self.draw_params(B, H, W, images_u8.device)
+        params = params.to(device=images_u8.device, dtype=torch.int32).contiguous()
+        if params.shape != (B, 5):
+            raise ValueError(f"params must be ({B},5)")
+        out = torch.empty(B, C, self.size, self.size, dtype=torch.float32, device=images_u8.device)
+        calls.mae_augment_u8(images_u8.data_ptr(), params.data_ptr(), B, C, H, W, self.size, out.data_ptr(),
+                             torch.cuda.current_stream(images_u8.device).cuda_stream)
+        return out
+
+
+def _real_stl10(split: str, train: bool, raw_uint8: bool = False):
     if os.environ.get("MAE_SYNTHETIC_DATA") == "1":
         return None
     try:
         from torchvision import transforms
         from torchvision.datasets import STL10
+
+        if raw_uint8:
+            return RawSTL10(STL10(DATA_DIR, split=split, transform=None, download=False))
 
         if train:
             tf = transforms.Compose([transforms.RandomResizedCrop(96, scale=(0.8, 1.0)), transforms.RandomHorizontalFlip(),
@@ -59,11 +140,11 @@ def _real_stl10(split: str, train: bool):
         return None
 
 
-def _dataset(split: str, train: bool, synthetic_size: int | None = None):
-    ds = _real_stl10(split, train)
+def _dataset(split: str, train: bool, synthetic_size: int | None = None, raw_uint8: bool = False):
+    ds = _real_stl10(split, train, raw_uint8)
     if ds is None:
         size = synthetic_size or int(os.environ.get("MAE_SYNTHETIC_SIZE", SPLIT_SIZES[split]))
-        ds = SyntheticSTL10(split, train=train, size=size)
+        ds = SyntheticSTL10(split, train=train, size=size, raw_uint8=raw_uint8)
         print(f"[data] STL-10 '{split}' split not found under '{DATA_DIR}': using {len(ds)} synthetic STL-10-shaped samples")
     return ds
 
@@ -76,7 +157,7 @@ def _loader(ds, batch_size: int, shuffle: bool, num_workers: int) -> DataLoader:
 def get_pretrain_dataloaders(cfg: dict) -> Tuple[DataLoader, DataLoader]:
     """Unlabeled split -> (train, val) loaders; keys ``pretrain.{batch_size,val_split,data_fraction,num_workers}``, ``seed``."""
     pre, seed = cfg["pretrain"], cfg.get("seed", 73)
-    full = _dataset("unlabeled", train=True)
+    full = _dataset("unlabeled", train=True, raw_uint8=bool(pre.get("gpu_augment", False)))
     frac = pre.get("data_fraction", 1.0)
     if frac < 1.0:
         full = Subset(full, range(int(len(full) * frac)))
@@ -91,11 +172,11 @@ def get_train_dataloaders(cfg: dict) -> Tuple[DataLoader, DataLoader]:
     """Labeled train split -> (train, val): ``train.samples_per_class`` images per class for training, the rest for
     validation (reference ``src/data.py:109-164``)."""
     tr, seed = cfg["train"], cfg.get("seed", 73)
-    full = _dataset("train", train=True)
+    full = _dataset("train", train=True, raw_uint8=bool(tr.get("gpu_augment", False)))
     per_class = int(tr.get("samples_per_class", 400))
     g = torch.Generator().manual_seed(seed)
     order = torch.randperm(len(full), generator=g).tolist()
-    labels = [full[i][1] if isinstance(full, SyntheticSTL10) else int(full.labels[i]) for i in order]
+    labels = [full[i][1] if isinstance(full, SyntheticSTL10) else int(full.labels[i]) for i in order]  # RawSTL10 has .labels too
     taken, train_idx, val_idx = {}, [], []
     for i, y in zip(order, labels):
         if taken.get(y, 0) < per_class:
@@ -110,4 +191,5 @@ def get_train_dataloaders(cfg: dict) -> Tuple[DataLoader, DataLoader]:
 
 def get_test_dataloader(cfg: dict) -> DataLoader:
     te = cfg.get("test", {})
-    return _loader(_dataset("test", train=False), te.get("batch_size", 512), False, te.get("num_workers", 4))
+    return _loader(_dataset("test", train=False, raw_uint8=bool(te.get("gpu_augment", False))), te.get("batch_size", 512), False,
+                   te.get("num_workers", 4))

@@ -123,14 +123,14 @@ class LiteTrainer:
                         e = self._fused.engine
                         e.exp_avg.copy_(st["exp_avg"]); e.exp_avg_sq.copy_(st["exp_avg_sq"]); e.step_count = int(st["step"])
                         st = None
-                    losses.append(self._fused.train_step(batch))
+                    losses.append(self._fused.train_step(self._prep(batch, True)))
                 else:
                     if st is not None and not st.get("fused_adamw"):
                         self._opt.load_state_dict(st)
                         st = None
                     imgs, labels = batch
                     self._opt.zero_grad(set_to_none=True)
-                    loss = module.training_step((imgs.to(self.device, non_blocking=True), labels.to(self.device)), bi)
+                    loss = module.training_step((self._prep(imgs.to(self.device, non_blocking=True), True), labels.to(self.device)), bi)
                     loss.backward()
                     torch.nn.utils.clip_grad_norm_([p for p in module.parameters() if p.requires_grad], self.clip)
                     self._opt.step()
@@ -152,6 +152,17 @@ class LiteTrainer:
             for c in self.callbacks:
                 c.maybe_save(self, epoch, metrics)
 
+    def _prep(self, images: torch.Tensor, train: bool) -> torch.Tensor:
+        """uint8 batches (``gpu_augment`` loaders) get the reference transform on the GPU; float batches pass through."""
+        if images.dtype != torch.uint8:
+            return images
+        from .data import GpuAugment
+
+        key = "_aug_train" if train else "_aug_eval"
+        if getattr(self, key, None) is None:
+            setattr(self, key, GpuAugment(size=images.shape[-1], train=train))
+        return getattr(self, key)(images)
+
     @staticmethod
     def _images_only(loader):
         for batch in loader:
@@ -164,7 +175,8 @@ class LiteTrainer:
             if self.limit_batches is not None and bi >= self.limit_batches:
                 break
             imgs, labels = batch
-            b = (imgs.to(self.device, non_blocking=True), labels.to(self.device) if torch.is_tensor(labels) else labels)
+            b = (self._prep(imgs.to(self.device, non_blocking=True), False),
+                 labels.to(self.device) if torch.is_tensor(labels) else labels)
             loss = module.validation_step(b, bi)
             tot += loss.item() * imgs.shape[0]
             n += imgs.shape[0]

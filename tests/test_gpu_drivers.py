@@ -2,6 +2,7 @@
 Lightning-shaped checkpoints -> resume -> classifier probe from the saved encoder."""
 import os
 
+import numpy as np
 import pytest
 import torch
 import yaml
@@ -47,3 +48,18 @@ def test_pretrain_resume_and_finetune_drivers(tmp_path, monkeypatch):
     enc_before = sd["encoder.vit.blocks.0.attn.qkv.weight"]
     enc_after = torch.load(out2 / "vit-mae.pt")["encoder.blocks.0.attn.qkv.weight"]
     assert torch.equal(enc_before.cpu(), enc_after.cpu())  # frozen encoder untouched by the probe
+
+
+def test_pretrain_driver_with_gpu_augment(tmp_path, monkeypatch):
+    """``pretrain.gpu_augment: true``: uint8 batches from the loader, crop / flip / normalize on the GPU."""
+    from scripts.training import pretrain_mae
+    monkeypatch.setenv("MAE_SYNTHETIC_DATA", "1")
+    monkeypatch.setenv("MAE_SYNTHETIC_SIZE", "160")
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "configs", "mae.yaml")))
+    cfg["pretrain"].update(batch_size=32, num_workers=0, total_epochs=2, warmup_epochs=1, val_split=0.2, gpu_augment=True)
+    cfg["logging"]["output_dir_base"] = str(tmp_path / "outputs")
+    cfg_path = tmp_path / "cfg.yaml"
+    yaml.safe_dump(cfg, open(cfg_path, "w"))
+    tr = pretrain_mae.main(["--config", str(cfg_path), "--output_dir_suffix", "g"])
+    assert getattr(tr, "_aug_train", None) is not None and getattr(tr, "_aug_eval", None) is not None
+    assert len(tr.history) == 2 and all(np.isfinite(h["val_loss"]) and np.isfinite(h["train_loss"]) for h in tr.history)
