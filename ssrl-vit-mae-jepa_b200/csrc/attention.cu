@@ -11,6 +11,8 @@
 // is produced by the warp that owns its rows (no cross-warp reduction, no atomics, no smem round trip for P/dS):
 //   phase A (warp = 16 queries): P, dP = dO.V^T, dS = P o (dP - delta), dQ = dS.K
 //   phase B (warp = 16 keys):    P^T, dP^T = V.dO^T, dS^T,  dV = P^T.dO, dK = dS^T.Q
+#include <stdlib.h>
+
 #include "mae_internal.h"
 #include "ptx.cuh"
 
@@ -422,6 +424,10 @@ extern "C" int mae_attention_fwd(const void* qkv, int B, int L, int H, int hd, v
   if (!qkv || !out || !lse) return MAE_ERR_NULL;
   const int nt = pick_nt(L);
   if (!nt || L < 1 || H < 1) return MAE_ERR_SHAPE;
+  {
+    static const bool no_tc = getenv("MAE_ATTN_NO_TC") != nullptr;  // A/B switch: keep everything on the mma.sync kernels
+    if (!no_tc && hd == 32 && L > 128 && L <= 160 && (H % 2) == 0) return attn_fwd_tc(qkv, B, L, H, out, lse, stream);
+  }
   MAE_ATTN_DISPATCH(launch_fwd, qkv, B, L, H, out, lse, stream)
 }
 

@@ -116,8 +116,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef MAE_MBAR_TIMEOUT_CYCLES
 #define MAE_MBAR_TIMEOUT_CYCLES 4000000000ll  // ~2 s at 2 GHz
 #endif
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// slow path kept out of line: the inlined fast path is a single try_wait (code size matters for kernels with one
+// warp per scheduler: an instruction-cache miss is not hidden by anything)
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > MAE_MBAR_TIMEOUT_CYCLES) {
@@ -126,6 +127,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma operand reads)

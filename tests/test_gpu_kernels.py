@@ -208,7 +208,9 @@ def test_gemm_wgrad(M, Pc, Qc):
 
 @pytest.mark.parametrize("B,L,H,hd", [(3, 36, 6, 24), (2, 145, 6, 32), (2, 145, 6, 24), (5, 17, 2, 32), (2, 73, 6, 24),
                                       (1, 160, 1, 32), (1, 1, 1, 24), (2, 49, 12, 64), (2, 197, 16, 32), (1, 197, 12, 64),
-                                      (1, 208, 2, 64), (2, 99, 3, 64)])
+                                      (1, 208, 2, 64), (2, 99, 3, 64),
+                                      # the tcgen05 forward (128 < L <= 160, hd 32, even H): ragged L, one / many items per CTA
+                                      (1, 129, 2, 32), (3, 160, 4, 32), (2, 131, 6, 32), (250, 145, 6, 32)])
 def test_attention_fwd_bwd(B, L, H, hd):
     D = H * hd
     g = torch.Generator().manual_seed(L * 7 + hd)
