@@ -437,5 +437,9 @@ extern "C" int mae_attention_bwd(const void* qkv, const void* out, const void* d
   if (!qkv || !out || !dout || !lse || !dqkv) return MAE_ERR_NULL;
   const int nt = pick_nt(L);
   if (!nt || L < 1 || H < 1) return MAE_ERR_SHAPE;
+  {
+    static const bool no_tc = getenv("MAE_ATTN_NO_TC") != nullptr || getenv("MAE_ATTN_NO_TC_BWD") != nullptr;
+    if (!no_tc && hd == 32 && L > 128 && L <= 160 && (H % 2) == 0) return attn_bwd_tc(qkv, out, dout, lse, B, L, H, dqkv, stream);
+  }
   MAE_ATTN_DISPATCH(launch_bwd, qkv, out, dout, lse, B, L, H, dqkv, stream)
 }

@@ -406,4 +406,302 @@ int attn_fwd_tc(const void* qkv, int B, int L, int H, void* out, float* lse, cud
   return MAE_CHECK_LAUNCH();
 }
 
+
+// =============================================================================================
+// tcgen05 attention backward, same problem sizes.  Per (sample, head), with the forward's log-sum-exp:
+//   S = Q K^T,  P = exp(S / sqrt(hd) - lse),  dP = dO V^T,  delta = rowsum(dO o O),  dS = P o (dP - delta)
+//   dQ = dS K / sqrt(hd),  dK = dS^T Q / sqrt(hd),  dV = P^T dO
+// Work item = (sample, pair of heads): Q, K, V, dO boxes [160 x 64] by TMA (single buffered: P / dS tiles take the rest
+// of shared memory).  Per head the two query tiles (rows 0..127, 128..159) go through S and dP in TMEM one after the
+// other; the softmax warps (4 for tile 0, 1 for tile 1, row per thread) turn them into bf16 P and dS tiles in shared
+// memory (128-byte-swizzled, rows = queries), which feed three more MMA groups without any transpose:
+//   dQ_t  = dS_t . K       A = dS tile as K-major, B = K tile as MN-major
+//   dV   += P_t^T . dO_t   A = the SAME P tile read as MN-major (M = keys), B = dO tile as MN-major
+//   dK   += dS_t^T . Q_t   likewise
+// dK / dV (keys on the TMEM lanes, two 128-lane tiles) accumulate over both query tiles.  TMEM: S 160 + dP 160 + dQ 2x32 +
+// dK 2x32 + dV 2x32 = 512 columns.  Gradients leave as 64-byte row segments straight from registers.
+// =============================================================================================
+struct TcbBars {
+  uint64_t ld_full, ld_empty;
+  uint64_t sd_full[2], sd_free[2];    // [query tile]: S and dP complete / pulled out of TMEM
+  uint64_t pds_ready[2], pds_free[2]; // [query tile]: P and dS tiles written / the MMAs reading them are done
+  uint64_t dq_full[2], dq_free[2];
+  uint64_t dkv_full, dkv_free;
+  uint32_t tmem_base;
+};
+struct TcbSmem {  // P0/dS0 first: the MN-major reads of the second key tile run 16 KB past a tile's end, into valid memory
+  static constexpr uint32_t p0 = 0, ds0 = 49152;
+  static constexpr uint32_t p1 = 98304, ds1 = 98304 + 12288;
+  // Q and dO first: as A operands of tile 1 (rows 128..255) they are read 12 KB past their 160 rows, into the next tile
+  static constexpr uint32_t q = 122880, dO = q + kTcTile, k = dO + kTcTile, v = k + kTcTile;
+  static constexpr uint32_t bars = v + kTcTile;
+  static constexpr uint32_t total = bars + 1024;
+};
+static constexpr uint32_t kbS = 0, kbDP = 160, kbDQ = 320, kbDK = 384, kbDV = 448;
+
+// 32 values of one TMEM row segment -> 64 contiguous bytes of a global bf16 row
+__device__ __forceinline__ void store_row32(__nv_bfloat16* dst, const uint32_t (&o)[32], float mul) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint4 w;
+    w.x = pack_bf16x2(__uint_as_float(o[8 * k]) * mul, __uint_as_float(o[8 * k + 1]) * mul);
+    w.y = pack_bf16x2(__uint_as_float(o[8 * k + 2]) * mul, __uint_as_float(o[8 * k + 3]) * mul);
+    w.z = pack_bf16x2(__uint_as_float(o[8 * k + 4]) * mul, __uint_as_float(o[8 * k + 5]) * mul);
+    w.w = pack_bf16x2(__uint_as_float(o[8 * k + 6]) * mul, __uint_as_float(o[8 * k + 7]) * mul);
+    *reinterpret_cast<uint4*>(dst + 8 * k) = w;
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ CUtensorMap mapDO,
+                   const __nv_bfloat16* __restrict__ out, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
+                   int B, int L, int H, float scale) {
+  pdl_trigger();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  TcbBars* bars = reinterpret_cast<TcbBars*>(smem + TcbSmem::bars);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int HP = H >> 1, D = H * 32;
+  const int nitems = B * HP;
+  const int my_items = nitems > int(blockIdx.x) ? (nitems - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
+  const int nheads = 2 * my_items;
+
+  if (warp == 2 && lane == 0) {
+    tma_prefetch_desc(&mapQKV);
+    tma_prefetch_desc(&mapDO);
+    mbar_init(&bars->ld_full, 1); mbar_init(&bars->ld_empty, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&bars->sd_full[t], 1); mbar_init(&bars->sd_free[t], t == 0 ? 4 : 1);
+      mbar_init(&bars->pds_ready[t], t == 0 ? 4 : 1); mbar_init(&bars->pds_free[t], 1);
+      mbar_init(&bars->dq_full[t], 1); mbar_init(&bars->dq_free[t], t == 0 ? 4 : 1);
+    }
+    mbar_init(&bars->dkv_full, 1); mbar_init(&bars->dkv_free, 5);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  pdl_wait();
+
+  if (warp == 2) {
+    if (lane == 0) {
+      for (int k = 0; k < my_items; ++k) {
+        const int item = int(blockIdx.x) + k * int(gridDim.x);
+        const int b = item / HP, hp = item % HP;
+        mbar_wait(&bars->ld_empty, (k & 1) ^ 1);
+        mbar_expect_tx(&bars->ld_full, 4 * kTcTile);
+        tma_load_3d(smem + TcbSmem::q, &mapQKV, &bars->ld_full, hp * 64, 0, b);
+        tma_load_3d(smem + TcbSmem::k, &mapQKV, &bars->ld_full, D + hp * 64, 0, b);
+        tma_load_3d(smem + TcbSmem::v, &mapQKV, &bars->ld_full, 2 * D + hp * 64, 0, b);
+        tma_load_3d(smem + TcbSmem::dO, &mapDO, &bars->ld_full, hp * 64, 0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t id_s = umma_idesc_bf16(128, kTcLp, 0, 0);   // S, dP: both operands K-major
+      const uint32_t id_q = umma_idesc_bf16(128, 32, 0, 1);      // dQ: A K-major, B MN-major
+      const uint32_t id_kv = umma_idesc_bf16(128, 32, 1, 1);     // dK, dV: both MN-major
+      const uint32_t sq = smem_u32(smem + TcbSmem::q), sk = smem_u32(smem + TcbSmem::k), sv = smem_u32(smem + TcbSmem::v),
+                     sdo = smem_u32(smem + TcbSmem::dO);
+      const uint32_t sp[2] = {smem_u32(smem + TcbSmem::p0), smem_u32(smem + TcbSmem::p1)};
+      const uint32_t sds[2] = {smem_u32(smem + TcbSmem::ds0), smem_u32(smem + TcbSmem::ds1)};
+      auto issue_sdp = [&](int hh, int t) {  // S_t = Q_t K^T and dP_t = dO_t V^T
+        const uint32_t co = uint32_t(hh) * 64u, ro = uint32_t(t) * 16384u;
+#pragma unroll
+        for (int k16 = 0; k16 < 2; ++k16)
+          umma_bf16(tmem_base + kbS, umma_sdesc_sw128(sq + ro + co + k16 * 32, 16, 1024), umma_sdesc_sw128(sk + co + k16 * 32, 16, 1024), id_s, k16 != 0);
+#pragma unroll
+        for (int k16 = 0; k16 < 2; ++k16)
+          umma_bf16(tmem_base + kbDP, umma_sdesc_sw128(sdo + ro + co + k16 * 32, 16, 1024), umma_sdesc_sw128(sv + co + k16 * 32, 16, 1024), id_s, k16 != 0);
+        umma_commit(&bars->sd_full[t]);
+      };
+      auto issue_grads = [&](int hh, int t, bool last_of_head) {
+        const uint32_t co = uint32_t(hh) * 64u, ro = uint32_t(t) * 16384u;
+        const uint32_t box = t ? 4096u : 16384u;
+        // dQ_t = dS_t . K
+#pragma unroll
+        for (int j = 0; j < kTcLp / 16; ++j)
+          umma_bf16(tmem_base + kbDQ + uint32_t(t) * 32u, umma_sdesc_sw128(sds[t] + uint32_t(j >> 2) * box + uint32_t(j & 3) * 32u, 16, 1024),
+                    umma_sdesc_sw128(sk + co + uint32_t(j) * 2048u, kTcTile, 1024), id_q, j != 0);
+        umma_commit(&bars->dq_full[t]);
+        // dV += P_t^T dO_t,  dK += dS_t^T Q_t   (M = keys: tile m covers keys 128 m ..; K = the query rows of tile t)
+        const int ksteps = t ? 2 : 8;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          for (int s = 0; s < ksteps; ++s) {
+            const uint32_t acc = (t != 0 || s != 0) ? 1u : 0u;
+            umma_bf16(tmem_base + kbDV + uint32_t(m) * 32u, umma_sdesc_sw128(sp[t] + uint32_t(2 * m) * box + uint32_t(s) * 2048u, box, 1024),
+                      umma_sdesc_sw128(sdo + ro + co + uint32_t(s) * 2048u, kTcTile, 1024), id_kv, acc);
+          }
+          for (int s = 0; s < ksteps; ++s) {
+            const uint32_t acc = (t != 0 || s != 0) ? 1u : 0u;
+            umma_bf16(tmem_base + kbDK + uint32_t(m) * 32u, umma_sdesc_sw128(sds[t] + uint32_t(2 * m) * box + uint32_t(s) * 2048u, box, 1024),
+                      umma_sdesc_sw128(sq + ro + co + uint32_t(s) * 2048u, kTcTile, 1024), id_kv, acc);
+          }
+        }
+        umma_commit(&bars->pds_free[t]);
+        if (last_of_head) umma_commit(&bars->dkv_full);
+      };
+      uint32_t ph_sdfree[2] = {0, 0}, ph_ready[2] = {0, 0}, ph_dqfree[2] = {0, 0}, ph_dkvfree = 0;
+      for (int n = 0; n < nheads; ++n) {
+        const int hh = n & 1;
+        if (hh == 0) { mbar_wait(&bars->ld_full, (n >> 1) & 1); }
+        // S0 / dP0: the S / dP columns were last used by the previous head's tile 1
+        if (n > 0) { mbar_wait(&bars->sd_free[1], ph_sdfree[1]); ph_sdfree[1] ^= 1; }
+        tc_fence_after();
+        issue_sdp(hh, 0);
+        // tile 0's P / dS written (S0 / dP0 drained): S1 / dP1 first, so that tile 1's softmax runs under tile 0's MMAs
+        mbar_wait(&bars->pds_ready[0], ph_ready[0]); ph_ready[0] ^= 1;
+        mbar_wait(&bars->sd_free[0], ph_sdfree[0]); ph_sdfree[0] ^= 1;
+        tc_fence_after();
+        issue_sdp(hh, 1);
+        if (n > 0) {
+          mbar_wait(&bars->dq_free[0], ph_dqfree[0]); ph_dqfree[0] ^= 1;
+          mbar_wait(&bars->dkv_free, ph_dkvfree); ph_dkvfree ^= 1;
+          tc_fence_after();
+        }
+        issue_grads(hh, 0, false);
+        mbar_wait(&bars->pds_ready[1], ph_ready[1]); ph_ready[1] ^= 1;
+        if (n > 0) { mbar_wait(&bars->dq_free[1], ph_dqfree[1]); ph_dqfree[1] ^= 1; }
+        tc_fence_after();
+        issue_grads(hh, 1, true);
+        if (hh == 1) umma_commit(&bars->ld_empty);
+      }
+    }
+  } else if (warp == 0 || warp >= 4) {
+    const int tile = warp == 0 ? 1 : 0;
+    const int quarter = warp & 3;
+    const float l2e = 1.4426950408889634f, sl2 = scale * l2e;
+    const int row = tile ? 128 + lane : quarter * 32 + lane;   // query token (softmax) and key token (dK / dV epilogue)
+    const int prow = tile ? lane : row;
+    const uint32_t lane_off = uint32_t(tile ? 0 : quarter * 32) << 16;
+    const uint32_t p_base = smem_u32(smem + (tile ? TcbSmem::p1 : TcbSmem::p0));
+    const uint32_t ds_base = smem_u32(smem + (tile ? TcbSmem::ds1 : TcbSmem::ds0));
+    const uint32_t box_bytes = tile ? 4096u : 16384u;
+    const uint32_t do_s = smem_u32(smem + TcbSmem::dO);
+    uint32_t ph_sdfull = 0, ph_pdsfree = 0, ph_dqfull = 0, ph_dkvfull = 0;
+#pragma unroll 1
+    for (int n = 0; n < nheads; ++n) {
+      const int item = int(blockIdx.x) + (n >> 1) * int(gridDim.x);
+      const int b = item / HP, hp = item % HP, hh = n & 1, h = hp * 2 + hh;
+      if (hh == 0) mbar_wait(&bars->ld_full, (n >> 1) & 1);
+      // per-row constants: log-sum-exp (in log2 units) and delta = sum_d dO o O
+      float lse2 = INFINITY, delta = 0.f;
+      if (row < L) {
+        lse2 = lse[(size_t(b) * H + h) * L + row] * l2e;
+        const uint4* op = reinterpret_cast<const uint4*>(out + (size_t(b) * L + row) * D + h * 32);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint4 o4 = __ldg(op + k);
+          uint32_t d0, d1, d2, d3;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3) : "r"(swz(do_s, row, hh * 4 + k)));
+          delta += bf16_lo(o4.x) * bf16_lo(d0) + bf16_hi(o4.x) * bf16_hi(d0) + bf16_lo(o4.y) * bf16_lo(d1) + bf16_hi(o4.y) * bf16_hi(d1) +
+                   bf16_lo(o4.z) * bf16_lo(d2) + bf16_hi(o4.z) * bf16_hi(d2) + bf16_lo(o4.w) * bf16_lo(d3) + bf16_hi(o4.w) * bf16_hi(d3);
+        }
+      }
+      mbar_wait(&bars->sd_full[tile], ph_sdfull); ph_sdfull ^= 1;
+      tc_fence_after();
+      if (n > 0) { mbar_wait(&bars->pds_free[tile], ph_pdsfree); ph_pdsfree ^= 1; }  // previous head's MMAs have read the tiles
+      const uint32_t s_addr = tmem_base + lane_off + kbS, dp_addr = tmem_base + lane_off + kbDP;
+      uint32_t sA[32], dA[32], sB[32], dB[32];
+      tmem_ld32_nowait(s_addr, sA);
+      tmem_ld32_nowait(dp_addr, dA);
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        uint32_t (&sc)[32] = (c & 1) ? sB : sA;
+        uint32_t (&dc)[32] = (c & 1) ? dB : dA;
+        tmem_wait_ld();
+        if (c < 4) {  // prefetch the next chunk while this one is processed
+          tmem_ld32_nowait(s_addr + (c + 1) * 32, (c & 1) ? sA : sB);
+          tmem_ld32_nowait(dp_addr + (c + 1) * 32, (c & 1) ? dA : dB);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->sd_free[tile]);
+        }
+        uint32_t pk[16], dk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = ex2_approx(__uint_as_float(sc[2 * i]) * sl2 - lse2);
+          float p1 = ex2_approx(__uint_as_float(sc[2 * i + 1]) * sl2 - lse2);
+          if (c == 4) {
+            if (128 + 2 * i >= L) p0 = 0.f;
+            if (128 + 2 * i + 1 >= L) p1 = 0.f;
+          }
+          pk[i] = pack_bf16x2(p0, p1);
+          dk[i] = pack_bf16x2(p0 * (__uint_as_float(dc[2 * i]) - delta), p1 * (__uint_as_float(dc[2 * i + 1]) - delta));
+        }
+        const uint32_t boxo = uint32_t(c >> 1) * box_bytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          sts16(swz(p_base + boxo, prow, (c & 1) * 4 + k), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+          sts16(swz(ds_base + boxo, prow, (c & 1) * 4 + k), dk[4 * k], dk[4 * k + 1], dk[4 * k + 2], dk[4 * k + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->pds_ready[tile]);
+      // dQ rows of this tile
+      {
+        mbar_wait(&bars->dq_full[tile], ph_dqfull); ph_dqfull ^= 1;
+        tc_fence_after();
+        uint32_t o[32];
+        tmem_ld32_nowait(tmem_base + lane_off + kbDQ + uint32_t(tile) * 32u, o);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->dq_free[tile]);
+        if (row < L) store_row32(dqkv + (size_t(b) * L + row) * 3 * D + h * 32, o, scale);
+      }
+      // dK / dV rows (keys = TMEM lanes) once both query tiles have been accumulated
+      {
+        mbar_wait(&bars->dkv_full, ph_dkvfull); ph_dkvfull ^= 1;
+        tc_fence_after();
+        uint32_t o[32], o2[32];
+        tmem_ld32_nowait(tmem_base + lane_off + kbDK + uint32_t(tile) * 32u, o);
+        tmem_ld32_nowait(tmem_base + lane_off + kbDV + uint32_t(tile) * 32u, o2);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->dkv_free);
+        if (row < L) {
+          __nv_bfloat16* base = dqkv + (size_t(b) * L + row) * 3 * D + h * 32;
+          store_row32(base + D, o, scale);
+          store_row32(base + 2 * D, o2, 1.0f);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, int B, int L, int H, void* dqkv,
+                cudaStream_t st) {
+  CUtensorMap mq, md;
+  const int D = H * 32;
+  int rc = make_tmap_bf16_3d(&mq, qkv, 3 * D, L, B, 3 * D, kTcLp);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&md, dout, D, L, B, D, kTcLp);
+  if (rc) return rc;
+  static bool done = false;
+  if (!done) {
+    if (cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TcbSmem::total) + 1024) != cudaSuccess)
+      return MAE_ERR_LAUNCH;
+    done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int nitems = B * (H / 2);
+  const int grid = nitems < sms ? nitems : sms;
+  mae_launch(attn_bwd_tc_kernel, dim3(grid), dim3(kTcThreads), size_t(TcbSmem::total) + 1024, st, mq, md,
+             reinterpret_cast<const __nv_bfloat16*>(out), lse, reinterpret_cast<__nv_bfloat16*>(dqkv), B, L, H,
+             1.0f / sqrtf(32.0f));
+  return MAE_CHECK_LAUNCH();
+}
+
 }  // namespace mae

@@ -12,6 +12,8 @@ namespace mae {
 int make_tmap_bf16(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows);
 // attention_tc.cu: tcgen05 attention for 128 < L <= 160, head_dim 32, even H
 int attn_fwd_tc(const void* qkv, int B, int L, int H, void* out, float* lse, cudaStream_t st);
+int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, int B, int L, int H, void* dqkv,
+                cudaStream_t st);
 }
 
 // Launch with the programmatic-dependent-launch attribute (see ptx.cuh: pdl_trigger / pdl_wait).
