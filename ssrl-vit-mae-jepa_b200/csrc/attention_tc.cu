@@ -454,8 +454,8 @@ __device__ __forceinline__ void store_row32(__nv_bfloat16* dst, const uint32_t (
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ CUtensorMap mapDO,
-                   const __nv_bfloat16* __restrict__ out, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
-                   int B, int L, int H, float scale) {
+                   const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                   const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, int B, int L, int H, float scale) {
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -545,13 +545,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
         if (last_of_head) umma_commit(&bars->dkv_full);
       };
       uint32_t ph_sdfree[2] = {0, 0}, ph_ready[2] = {0, 0}, ph_dqfree[2] = {0, 0}, ph_dkvfree = 0;
+      bool sdp0_issued = false;  // S0 / dP0 of the current head were issued ahead (at the end of the previous head)
       for (int n = 0; n < nheads; ++n) {
         const int hh = n & 1;
-        if (hh == 0) { mbar_wait(&bars->ld_full, (n >> 1) & 1); }
-        // S0 / dP0: the S / dP columns were last used by the previous head's tile 1
-        if (n > 0) { mbar_wait(&bars->sd_free[1], ph_sdfree[1]); ph_sdfree[1] ^= 1; }
-        tc_fence_after();
-        issue_sdp(hh, 0);
+        if (!sdp0_issued) {
+          if (hh == 0) { mbar_wait(&bars->ld_full, (n >> 1) & 1); }
+          // the S / dP columns were last used by the previous head's tile 1
+          if (n > 0) { mbar_wait(&bars->sd_free[1], ph_sdfree[1]); ph_sdfree[1] ^= 1; }
+          tc_fence_after();
+          issue_sdp(hh, 0);
+        }
+        sdp0_issued = false;
         // tile 0's P / dS written (S0 / dP0 drained): S1 / dP1 first, so that tile 1's softmax runs under tile 0's MMAs
         mbar_wait(&bars->pds_ready[0], ph_ready[0]); ph_ready[0] ^= 1;
         mbar_wait(&bars->sd_free[0], ph_sdfree[0]); ph_sdfree[0] ^= 1;
@@ -564,6 +568,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
         }
         issue_grads(hh, 0, false);
         mbar_wait(&bars->pds_ready[1], ph_ready[1]); ph_ready[1] ^= 1;
+        if (hh == 0 && n + 1 < nheads) {  // second head of the same item: its S0 / dP0 go ahead of this head's last MMA group
+          mbar_wait(&bars->sd_free[1], ph_sdfree[1]); ph_sdfree[1] ^= 1;
+          tc_fence_after();
+          issue_sdp(1, 0);
+          sdp0_issued = true;
+        }
         if (n > 0) { mbar_wait(&bars->dq_free[1], ph_dqfree[1]); ph_dqfree[1] ^= 1; }
         tc_fence_after();
         issue_grads(hh, 1, true);
@@ -580,27 +590,43 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
     const uint32_t p_base = smem_u32(smem + (tile ? TcbSmem::p1 : TcbSmem::p0));
     const uint32_t ds_base = smem_u32(smem + (tile ? TcbSmem::ds1 : TcbSmem::ds0));
     const uint32_t box_bytes = tile ? 4096u : 16384u;
-    const uint32_t do_s = smem_u32(smem + TcbSmem::dO);
     uint32_t ph_sdfull = 0, ph_pdsfree = 0, ph_dqfull = 0, ph_dkvfull = 0;
+    // per-row constants of head m: log-sum-exp (in log2 units) and delta = sum_d dO o O, straight from global memory, one
+    // head ahead (rows >= L: lse = +inf makes P and dS vanish).  issue (loads only) and finish (arithmetic) are separate
+    // so that the loads of head n + 1 stay in flight across the epilogue waits of head n.
+    uint4 rc_o[4], rc_d[4];
+    float rc_l = INFINITY;
+    auto row_consts_issue = [&](int m) {
+      rc_l = INFINITY;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { rc_o[k] = make_uint4(0, 0, 0, 0); rc_d[k] = make_uint4(0, 0, 0, 0); }
+      if (m >= nheads || row >= L) return;
+      const int item = int(blockIdx.x) + (m >> 1) * int(gridDim.x);
+      const int b = item / HP, h = (item % HP) * 2 + (m & 1);
+      rc_l = __ldg(lse + (size_t(b) * H + h) * L + row);
+      const uint4* op = reinterpret_cast<const uint4*>(out + (size_t(b) * L + row) * D + h * 32);
+      const uint4* dp = reinterpret_cast<const uint4*>(dout + (size_t(b) * L + row) * D + h * 32);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { rc_o[k] = __ldg(op + k); rc_d[k] = __ldg(dp + k); }
+    };
+    auto row_consts_finish = [&](float& lse2, float& delta) {
+      lse2 = rc_l * l2e;
+      delta = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint4 o4 = rc_o[k], d4 = rc_d[k];
+        delta += bf16_lo(o4.x) * bf16_lo(d4.x) + bf16_hi(o4.x) * bf16_hi(d4.x) + bf16_lo(o4.y) * bf16_lo(d4.y) + bf16_hi(o4.y) * bf16_hi(d4.y) +
+                 bf16_lo(o4.z) * bf16_lo(d4.z) + bf16_hi(o4.z) * bf16_hi(d4.z) + bf16_lo(o4.w) * bf16_lo(d4.w) + bf16_hi(o4.w) * bf16_hi(d4.w);
+      }
+    };
+    float lse2_next, delta_next;
+    row_consts_issue(0);
+    row_consts_finish(lse2_next, delta_next);
 #pragma unroll 1
     for (int n = 0; n < nheads; ++n) {
       const int item = int(blockIdx.x) + (n >> 1) * int(gridDim.x);
       const int b = item / HP, hp = item % HP, hh = n & 1, h = hp * 2 + hh;
-      if (hh == 0) mbar_wait(&bars->ld_full, (n >> 1) & 1);
-      // per-row constants: log-sum-exp (in log2 units) and delta = sum_d dO o O
-      float lse2 = INFINITY, delta = 0.f;
-      if (row < L) {
-        lse2 = lse[(size_t(b) * H + h) * L + row] * l2e;
-        const uint4* op = reinterpret_cast<const uint4*>(out + (size_t(b) * L + row) * D + h * 32);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint4 o4 = __ldg(op + k);
-          uint32_t d0, d1, d2, d3;
-          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3) : "r"(swz(do_s, row, hh * 4 + k)));
-          delta += bf16_lo(o4.x) * bf16_lo(d0) + bf16_hi(o4.x) * bf16_hi(d0) + bf16_lo(o4.y) * bf16_lo(d1) + bf16_hi(o4.y) * bf16_hi(d1) +
-                   bf16_lo(o4.z) * bf16_lo(d2) + bf16_hi(o4.z) * bf16_hi(d2) + bf16_lo(o4.w) * bf16_lo(d3) + bf16_hi(o4.w) * bf16_hi(d3);
-        }
-      }
+      const float lse2 = lse2_next, delta = delta_next;
       mbar_wait(&bars->sd_full[tile], ph_sdfull); ph_sdfull ^= 1;
       tc_fence_after();
       if (n > 0) { mbar_wait(&bars->pds_free[tile], ph_pdsfree); ph_pdsfree ^= 1; }  // previous head's MMAs have read the tiles
@@ -643,6 +669,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->pds_ready[tile]);
+      row_consts_issue(n + 1);  // in flight during the epilogue waits below
       // dQ rows of this tile
       {
         mbar_wait(&bars->dq_full[tile], ph_dqfull); ph_dqfull ^= 1;
@@ -672,6 +699,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
           store_row32(base + 2 * D, o2, 1.0f);
         }
       }
+      row_consts_finish(lse2_next, delta_next);
     }
   }
   tc_fence_before();
@@ -699,7 +727,7 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
   const int nitems = B * (H / 2);
   const int grid = nitems < sms ? nitems : sms;
   mae_launch(attn_bwd_tc_kernel, dim3(grid), dim3(kTcThreads), size_t(TcbSmem::total) + 1024, st, mq, md,
-             reinterpret_cast<const __nv_bfloat16*>(out), lse, reinterpret_cast<__nv_bfloat16*>(dqkv), B, L, H,
+             reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), lse, reinterpret_cast<__nv_bfloat16*>(dqkv), B, L, H,
              1.0f / sqrtf(32.0f));
   return MAE_CHECK_LAUNCH();
 }
