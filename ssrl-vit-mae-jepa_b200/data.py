@@ -111,7 +111,10 @@ class GpuAugment:
         if params is None:
             # drawn on the host (a few vectorised ops that run ahead of the GPU) and shipped as one 40 KB pinned copy:
             # on the device the same ~35 tiny elementwise launches would sit in the compute stream (~0.4 ms per step)
-            params = self.draw_params(B, H, W, "cpu").pin_memory()
+            where = self.generator.device if self.generator is not None else torch.device("cpu")
+            params = self.draw_params(B, H, W, where)
+            if params.device.type == "cpu":
+                params = params.pin_memory()
         params = params.to(device=images_u8.device, dtype=torch.int32, non_blocking=True).contiguous()
         if params.shape != (B, 5):
             raise ValueError(f"params must be ({B},5)")
