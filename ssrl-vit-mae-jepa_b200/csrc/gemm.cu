@@ -852,6 +852,10 @@ struct WgradParams {
   int M, Pc, Qc;
   int nqb;          // ceil(Qc / 64) TMA boxes for Q per stage
   int rows_per_cta; // multiple of WR
+  int pcc;          // P chunks (of 128 columns) per CTA: 1 or 2.  Two accumulators share every staged Q tile, which halves
+                    // the Q re-reads and doubles the MMA work per ring stage (the ring is bound by the ~1.5 us turnaround
+                    // of a stage, not by bytes)
+  int nstages;      // ring depth (whatever fits: 3 or 4)
   float* out;
   long long so_p, so_q;
   float* colsum;    // optional: += column sums of P (colsum_of_q == 0) or of Q (== 1): the bias gradient
@@ -870,14 +874,16 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t box_bytes = WR * 128;  // one [64 rows x 64 cols] bf16 box = 8 KB
-  const uint32_t p_bytes = 2 * box_bytes;
+  const int npb = 2 * p.pcc;            // P boxes per stage
+  const uint32_t p_bytes = uint32_t(npb) * box_bytes;
   const uint32_t q_bytes = uint32_t(p.nqb) * box_bytes;
   const uint32_t stage_bytes = p_bytes + q_bytes;
-  GemmSmemHdr* hdr = reinterpret_cast<GemmSmemHdr*>(smem + kStages * stage_bytes);
+  const int nst = p.nstages;
+  GemmSmemHdr* hdr = reinterpret_cast<GemmSmemHdr*>(smem + nst * stage_bytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int pc = blockIdx.x;
+  const int pc0 = blockIdx.x * p.pcc;                    // first 128-column P chunk of this CTA
   const int q0 = blockIdx.z * 256;                       // first Q column of this CTA's output tile
   const int Qn = (p.Qc - q0) < 256 ? (p.Qc - q0) : 256;  // its width (multiple of 16)
   const int nqb = (Qn + 63) >> 6;                        // TMA boxes of Q actually loaded per stage
@@ -891,11 +897,11 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
     tma_prefetch_desc(&mapP);
     tma_prefetch_desc(&mapQ);
     // a stage is released by the MMA commit and, when column sums are fused, by the 4 epilogue warps too
-    for (int s = 0; s < kStages; ++s) { mbar_init(&hdr->full[s], 1); mbar_init(&hdr->empty[s], p.colsum ? 5 : 1); }
+    for (int s = 0; s < nst; ++s) { mbar_init(&hdr->full[s], 1); mbar_init(&hdr->empty[s], p.colsum ? 5 : 1); }
     mbar_init(&hdr->tfull[0], 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(&hdr->tmem_base, 256);
+  if (warp == 1) tmem_alloc(&hdr->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -910,11 +916,11 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
           mbar_wait(&hdr->empty[stage], phase ^ 1);
           uint8_t* sp = smem + stage * stage_bytes;
           mbar_expect_tx(&hdr->full[stage], tx_bytes);
-          tma_load_2d(sp, &mapP, &hdr->full[stage], pc * 128, m0);
-          tma_load_2d(sp + box_bytes, &mapP, &hdr->full[stage], pc * 128 + 64, m0);
+          for (int j = 0; j < npb; ++j)  // columns past Pc are zero-filled by the TMA
+            tma_load_2d(sp + j * box_bytes, &mapP, &hdr->full[stage], pc0 * 128 + j * 64, m0);
           for (int j = 0; j < nqb; ++j)
             tma_load_2d(sp + p_bytes + j * box_bytes, &mapQ, &hdr->full[stage], q0 + j * 64, m0);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
         }
       }
     } else if (warp == 1) {
@@ -926,16 +932,18 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
           tc_fence_after();
           const uint32_t sp = smem_u32(smem + stage * stage_bytes);
           const uint32_t sq = sp + p_bytes;
+          for (int c = 0; c < p.pcc; ++c) {
 #pragma unroll
-          for (int k = 0; k < WR / 16; ++k) {
-            // MN-major SW128: 64 MN elements contiguous (128 B) per reduction row; 8-row groups 1024 B apart
-            // (SBO); successive 64-element MN groups one TMA box apart (LBO); +2048 B per K=16 step.
-            const uint64_t adesc = umma_sdesc_sw128(sp + k * 2048, box_bytes, 1024);
-            const uint64_t bdesc = umma_sdesc_sw128(sq + k * 2048, box_bytes, 1024);
-            umma_bf16(tmem_base, adesc, bdesc, idesc, (mb | k) != 0);
+            for (int k = 0; k < WR / 16; ++k) {
+              // MN-major SW128: 64 MN elements contiguous (128 B) per reduction row; 8-row groups 1024 B apart
+              // (SBO); successive 64-element MN groups one TMA box apart (LBO); +2048 B per K=16 step.
+              const uint64_t adesc = umma_sdesc_sw128(sp + uint32_t(2 * c) * box_bytes + k * 2048, box_bytes, 1024);
+              const uint64_t bdesc = umma_sdesc_sw128(sq + k * 2048, box_bytes, 1024);
+              umma_bf16(tmem_base + uint32_t(c) * 256u, adesc, bdesc, idesc, (mb | k) != 0);
+            }
           }
           umma_commit(&hdr->empty[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
         }
         umma_commit(&hdr->tfull[0]);
       }
@@ -944,12 +952,12 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
       if (p.colsum != nullptr) {
         // The epilogue warps are idle during the main loop: they add up the columns of the staged dY tile
         // (bias gradient) straight from shared memory, so dY is read from HBM exactly once.
-        // Thread t of 128: box (t>>6), 16-byte column chunk cc = t&7, row group rg = (t>>3)&7 -> rows rg+8i.
+        // Thread t of 128: box (t>>6) + 2j, 16-byte column chunk cc = t&7, row group rg = (t>>3)&7 -> rows rg+8i.
         // Within a 128B-swizzled box the chunk of row r sits at (cc ^ (r&7)) = (cc ^ rg): constant per thread.
         const int t = (warp - 2) * 32 + lane;
         const bool of_q = p.colsum_of_q != 0;
         const bool active = of_q ? (blockIdx.x == 0) : (blockIdx.z == 0);  // each column summed by exactly one CTA row
-        const int nbox = of_q ? nqb : 2;
+        const int nbox = of_q ? nqb : npb;
         const uint32_t tile_off = of_q ? p_bytes : 0u;
         const int cc = t & 7, rg = (t >> 3) & 7;
         const uint32_t thr_off = uint32_t(rg) * 128u + (uint32_t(cc ^ rg) << 4);
@@ -979,10 +987,10 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&hdr->empty[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
         }
         if (active) {
-          const int col_base = of_q ? q0 : pc * 128;
+          const int col_base = of_q ? q0 : pc0 * 128;
           const int ncols = of_q ? p.Qc : p.Pc;
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
@@ -1000,23 +1008,25 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
       }
       mbar_wait(&hdr->tfull[0], 0);
       tc_fence_after();
-      const int prow = pc * 128 + q * 32 + lane;
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
-      for (int c0 = 0; c0 < Qn; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + c0, v);
-        if (prow < p.Pc) {
-          float* o = p.out + (long long)prow * p.so_p + (long long)(q0 + c0) * p.so_q;
-          if (p.so_q == 1 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-            // 16 consecutive floats of one dW row: four 16-byte vector reductions instead of 16 scalar ones
+      for (int c = 0; c < p.pcc; ++c) {
+        const int prow = (pc0 + c) * 128 + q * 32 + lane;
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c) * 256u;
+        for (int c0 = 0; c0 < Qn; c0 += 16) {
+          float v[16];
+          tmem_ld16(taddr + c0, v);
+          if (prow < p.Pc) {
+            float* o = p.out + (long long)prow * p.so_p + (long long)(q0 + c0) * p.so_q;
+            if (p.so_q == 1 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+              // 16 consecutive floats of one dW row: four 16-byte vector reductions instead of 16 scalar ones
 #pragma unroll
-            for (int i = 0; i < 16; i += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + i), "f"(v[i]), "f"(v[i + 1]),
-                           "f"(v[i + 2]), "f"(v[i + 3])
-                           : "memory");
-          } else {
+              for (int i = 0; i < 16; i += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + i), "f"(v[i]), "f"(v[i + 1]),
+                             "f"(v[i + 2]), "f"(v[i + 3])
+                             : "memory");
+            } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) atomicAdd(o + (long long)i * p.so_q, v[i]);
+              for (int i = 0; i < 16; ++i) atomicAdd(o + (long long)i * p.so_q, v[i]);
+            }
           }
         }
       }
@@ -1024,7 +1034,7 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace mae
@@ -1041,7 +1051,17 @@ extern "C" int mae_gemm_wgrad(const void* P, int Pc, const void* Q, int Qc, int 
   p.out = out; p.so_p = so_p; p.so_q = so_q;
   p.colsum = colsum; p.colsum_of_q = colsum_of_q;
   const int pchunks = (Pc + 127) / 128;
-  int msplit = num_sms() / (pchunks * qchunks);
+  {
+    static const int force = getenv("MAE_WGRAD_PCC") ? atoi(getenv("MAE_WGRAD_PCC")) : 0;  // experiments
+    p.pcc = (pchunks >= 6 && pchunks % 2 == 0) ? 2 : 1;  // measured: 768-wide P 106 -> 99 us; narrower P loses M-splits / stages
+    if (force == 1 || force == 2) p.pcc = force;
+  }
+  const size_t stage = size_t(2 * p.pcc + p.nqb) * WR * 128;
+  p.nstages = kStages;
+  while (p.nstages > 2 && size_t(p.nstages) * stage + sizeof(GemmSmemHdr) + 1024 > 227 * 1024) --p.nstages;
+  if (size_t(p.nstages) * stage + sizeof(GemmSmemHdr) + 1024 > 227 * 1024) return MAE_ERR_SHAPE;
+  const int pgroups = (pchunks + p.pcc - 1) / p.pcc;
+  int msplit = num_sms() / (pgroups * qchunks);
   if (msplit < 1) msplit = 1;
   int rows = (M + msplit - 1) / msplit;
   rows = ((rows + WR - 1) / WR) * WR;
@@ -1052,13 +1072,13 @@ extern "C" int mae_gemm_wgrad(const void* P, int Pc, const void* Q, int Qc, int 
   if (rc) return rc;
   rc = make_tmap_bf16(&mq, Q, M, Qc, Qc, WR);
   if (rc) return rc;
-  const size_t smem = size_t(kStages) * (2 + p.nqb) * WR * 128 + sizeof(GemmSmemHdr) + 1024;
+  const size_t smem = size_t(p.nstages) * stage + sizeof(GemmSmemHdr) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return MAE_ERR_LAUNCH;
     attr_done = true;
   }
-  mae_launch(gemm_wgrad_kernel, dim3(pchunks, msplit, qchunks), dim3(kWgradThreads), smem, stream, p, mp, mq);
+  mae_launch(gemm_wgrad_kernel, dim3(pgroups, msplit, qchunks), dim3(kWgradThreads), smem, stream, p, mp, mq);
   return cudaGetLastError() == cudaSuccess ? MAE_OK : MAE_ERR_LAUNCH;
 }
