@@ -27,7 +27,8 @@ typedef CUresult (*PFN_encodeTiled3)(CUtensorMap*, CUtensorMapDataType, cuuint32
 
 // bf16 tensor viewed as (cols, rows_per_sample, samples): element (c, r, b) at ptr[(b * rows + r) * ld + c];
 // box = [64 cols x box_rows x 1], 128-byte swizzle.
-static int make_tmap_bf16_3d(CUtensorMap* map, const void* ptr, int cols, int rows, int samples, int ld, int box_rows) {
+static int make_tmap_bf16_3d(CUtensorMap* map, const void* ptr, int cols, int rows, int samples, int ld, int box_rows,
+                             int box_cols = 64) {
   static PFN_encodeTiled3 enc = nullptr;
   if (!enc) {
     void* p = nullptr;
@@ -40,12 +41,20 @@ static int make_tmap_bf16_3d(CUtensorMap* map, const void* ptr, int cols, int ro
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((size_t(ld) * 2) & 15) || box_rows > 256 || box_rows < 1) return MAE_ERR_ALIGN;
   cuuint64_t dims[3] = {cuuint64_t(cols), cuuint64_t(rows), cuuint64_t(samples)};
   cuuint64_t strides[2] = {cuuint64_t(ld) * 2, cuuint64_t(rows) * cuuint64_t(ld) * 2};
-  cuuint32_t box[3] = {64, cuuint32_t(box_rows), 1};
+  cuuint32_t box[3] = {cuuint32_t(box_cols), cuuint32_t(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
+  // the swizzle span equals the box row: 64 columns = 128 bytes, 32 columns = 64 bytes
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MAE_OK : MAE_ERR_DRIVER;
+}
+
+// Shared-memory matrix descriptor for the 64-byte swizzle (cute::UMMA::LayoutType::SWIZZLE_64B = 4): rows of 64 bytes,
+// 8-row groups `sbo_bytes` apart.  K-major: +32 B per K=16 step; MN-major (32 MN elements per row): +2 * sbo per K=16 step.
+__device__ __forceinline__ uint64_t umma_sdesc_sw64(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return uint64_t((smem_addr & 0x3ffffu) >> 4) | (uint64_t((lbo_bytes >> 4) & 0x3fffu) << 16) |
+         (uint64_t((sbo_bytes >> 4) & 0x3fffu) << 32) | (uint64_t(1) << 46) | (uint64_t(4) << 61);
 }
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
@@ -425,7 +434,7 @@ int attn_fwd_tc(const void* qkv, int B, int L, int H, void* out, float* lse, cud
 // dK 2x32 + dV 2x32 = 512 columns.  Gradients leave as 64-byte row segments straight from registers.
 // =============================================================================================
 struct TcbBars {
-  uint64_t ld_full, ld_empty;
+  uint64_t ld_full[2], ld_empty[2];   // [buffer]: Q / dO / K / V of a head landed / every MMA reading them has completed
   uint64_t sd_full[2], sd_free[2];    // [query tile]: S and dP complete / pulled out of TMEM
   uint64_t pds_ready[2], pds_free[2]; // [query tile]: P and dS tiles written / the MMAs reading them are done
   uint64_t dq_full[2], dq_free[2];
@@ -435,9 +444,11 @@ struct TcbBars {
 struct TcbSmem {  // P0/dS0 first: the MN-major reads of the second key tile run 16 KB past a tile's end, into valid memory
   static constexpr uint32_t p0 = 0, ds0 = 49152;
   static constexpr uint32_t p1 = 98304, ds1 = 98304 + 12288;
-  // Q and dO first: as A operands of tile 1 (rows 128..255) they are read 12 KB past their 160 rows, into the next tile
-  static constexpr uint32_t q = 122880, dO = q + kTcTile, k = dO + kTcTile, v = k + kTcTile;
-  static constexpr uint32_t bars = v + kTcTile;
+  // per head and buffer: Q, dO, K, V boxes [160 rows x 32 cols] (64-byte rows, 64-byte swizzle), double buffered across
+  // heads.  Q and dO first: as A operands of tile 1 (rows 128..255) they are read 6 KB past their 160 rows, into the next tile
+  static constexpr uint32_t tile = kTcLp * 64;            // 10240 B
+  static constexpr uint32_t tiles = 122880;               // [2 buffers][Q, dO, K, V]
+  static constexpr uint32_t bars = tiles + 2 * 4 * tile;  // 204800
   static constexpr uint32_t total = bars + 1024;
 };
 static constexpr uint32_t kbS = 0, kbDP = 160, kbDQ = 320, kbDK = 384, kbDV = 448;
@@ -464,16 +475,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   TcbBars* bars = reinterpret_cast<TcbBars*>(smem + TcbSmem::bars);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int HP = H >> 1, D = H * 32;
-  const int nitems = B * HP;
-  const int my_items = nitems > int(blockIdx.x) ? (nitems - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
-  const int nheads = 2 * my_items;
+  const int D = H * 32;
+  const int nitems = B * H;  // work item = (sample, head)
+  const int nheads = nitems > int(blockIdx.x) ? (nitems - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
 
   if (warp == 2 && lane == 0) {
     tma_prefetch_desc(&mapQKV);
     tma_prefetch_desc(&mapDO);
-    mbar_init(&bars->ld_full, 1); mbar_init(&bars->ld_empty, 1);
     for (int t = 0; t < 2; ++t) {
+      mbar_init(&bars->ld_full[t], 1); mbar_init(&bars->ld_empty[t], 1);
       mbar_init(&bars->sd_full[t], 1); mbar_init(&bars->sd_free[t], t == 0 ? 4 : 1);
       mbar_init(&bars->pds_ready[t], t == 0 ? 4 : 1); mbar_init(&bars->pds_free[t], 1);
       mbar_init(&bars->dq_full[t], 1); mbar_init(&bars->dq_free[t], t == 0 ? 4 : 1);
@@ -490,15 +500,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
 
   if (warp == 2) {
     if (lane == 0) {
-      for (int k = 0; k < my_items; ++k) {
+      for (int k = 0; k < nheads; ++k) {
         const int item = int(blockIdx.x) + k * int(gridDim.x);
-        const int b = item / HP, hp = item % HP;
-        mbar_wait(&bars->ld_empty, (k & 1) ^ 1);
-        mbar_expect_tx(&bars->ld_full, 4 * kTcTile);
-        tma_load_3d(smem + TcbSmem::q, &mapQKV, &bars->ld_full, hp * 64, 0, b);
-        tma_load_3d(smem + TcbSmem::k, &mapQKV, &bars->ld_full, D + hp * 64, 0, b);
-        tma_load_3d(smem + TcbSmem::v, &mapQKV, &bars->ld_full, 2 * D + hp * 64, 0, b);
-        tma_load_3d(smem + TcbSmem::dO, &mapDO, &bars->ld_full, hp * 64, 0, b);
+        const int b = item / H, h = item % H, buf = k & 1;
+        uint8_t* dst = smem + TcbSmem::tiles + buf * 4 * TcbSmem::tile;
+        mbar_wait(&bars->ld_empty[buf], ((k >> 1) & 1) ^ 1);
+        mbar_expect_tx(&bars->ld_full[buf], 4 * TcbSmem::tile);
+        tma_load_3d(dst, &mapQKV, &bars->ld_full[buf], h * 32, 0, b);
+        tma_load_3d(dst + TcbSmem::tile, &mapDO, &bars->ld_full[buf], h * 32, 0, b);
+        tma_load_3d(dst + 2 * TcbSmem::tile, &mapQKV, &bars->ld_full[buf], D + h * 32, 0, b);
+        tma_load_3d(dst + 3 * TcbSmem::tile, &mapQKV, &bars->ld_full[buf], 2 * D + h * 32, 0, b);
       }
     }
   } else if (warp == 1) {
@@ -506,43 +517,48 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
       const uint32_t id_s = umma_idesc_bf16(128, kTcLp, 0, 0);   // S, dP: both operands K-major
       const uint32_t id_q = umma_idesc_bf16(128, 32, 0, 1);      // dQ: A K-major, B MN-major
       const uint32_t id_kv = umma_idesc_bf16(128, 32, 1, 1);     // dK, dV: both MN-major
-      const uint32_t sq = smem_u32(smem + TcbSmem::q), sk = smem_u32(smem + TcbSmem::k), sv = smem_u32(smem + TcbSmem::v),
-                     sdo = smem_u32(smem + TcbSmem::dO);
+      const uint32_t tiles0 = smem_u32(smem + TcbSmem::tiles);
       const uint32_t sp[2] = {smem_u32(smem + TcbSmem::p0), smem_u32(smem + TcbSmem::p1)};
       const uint32_t sds[2] = {smem_u32(smem + TcbSmem::ds0), smem_u32(smem + TcbSmem::ds1)};
-      auto issue_sdp = [&](int hh, int t) {  // S_t = Q_t K^T and dP_t = dO_t V^T
-        const uint32_t co = uint32_t(hh) * 64u, ro = uint32_t(t) * 16384u;
-#pragma unroll
-        for (int k16 = 0; k16 < 2; ++k16)
-          umma_bf16(tmem_base + kbS, umma_sdesc_sw128(sq + ro + co + k16 * 32, 16, 1024), umma_sdesc_sw128(sk + co + k16 * 32, 16, 1024), id_s, k16 != 0);
-#pragma unroll
-        for (int k16 = 0; k16 < 2; ++k16)
-          umma_bf16(tmem_base + kbDP, umma_sdesc_sw128(sdo + ro + co + k16 * 32, 16, 1024), umma_sdesc_sw128(sv + co + k16 * 32, 16, 1024), id_s, k16 != 0);
+      // Descriptor templates: the start-address field is the low 14 bits (address >> 4) and every operand lives below
+      // 256 KB, so stepping through a tile is one 64-bit add of (byte offset >> 4): the issuing thread is on the critical
+      // path (60+ MMAs per head from one lane), building each descriptor from scratch cost ~65 cycles per MMA.
+      const uint64_t t64k = umma_sdesc_sw64(0, 16, 512);            // 64-byte rows: tiles loaded by TMA (K- or MN-major)
+      const uint64_t t128k = umma_sdesc_sw128(0, 16, 1024);         // P / dS tiles as K-major A
+      auto d_at = [](uint64_t templ, uint32_t addr) { return templ + uint64_t((addr & 0x3ffffu) >> 4); };
+      auto issue_sdp = [&](int n, int t) {  // S_t = Q_t K^T and dP_t = dO_t V^T of head n
+        const uint32_t tb = tiles0 + uint32_t(n & 1) * 4u * TcbSmem::tile, ro = uint32_t(t) * 8192u;
+        const uint64_t dq_ = d_at(t64k, tb + ro), ddo = d_at(t64k, tb + TcbSmem::tile + ro);
+        const uint64_t dk_ = d_at(t64k, tb + 2 * TcbSmem::tile), dv_ = d_at(t64k, tb + 3 * TcbSmem::tile);
+        umma_bf16(tmem_base + kbS, dq_, dk_, id_s, 0);
+        umma_bf16(tmem_base + kbS, dq_ + 2, dk_ + 2, id_s, 1);       // +32 B per K = 16
+        umma_bf16(tmem_base + kbDP, ddo, dv_, id_s, 0);
+        umma_bf16(tmem_base + kbDP, ddo + 2, dv_ + 2, id_s, 1);
         umma_commit(&bars->sd_full[t]);
       };
-      auto issue_grads = [&](int hh, int t, bool last_of_head) {
-        const uint32_t co = uint32_t(hh) * 64u, ro = uint32_t(t) * 16384u;
+      auto issue_grads = [&](int n, int t, bool last_of_head) {
+        const uint32_t tb = tiles0 + uint32_t(n & 1) * 4u * TcbSmem::tile, ro = uint32_t(t) * 8192u;
         const uint32_t box = t ? 4096u : 16384u;
-        // dQ_t = dS_t . K
+        // dQ_t = dS_t . K   (B = K tile as MN-major: 32 head dims per 64-byte row, +1024 B per 16 keys)
+        {
+          const uint64_t a0 = d_at(t128k, sds[t]);
+          uint64_t b = d_at(t64k, tb + 2 * TcbSmem::tile);
 #pragma unroll
-        for (int j = 0; j < kTcLp / 16; ++j)
-          umma_bf16(tmem_base + kbDQ + uint32_t(t) * 32u, umma_sdesc_sw128(sds[t] + uint32_t(j >> 2) * box + uint32_t(j & 3) * 32u, 16, 1024),
-                    umma_sdesc_sw128(sk + co + uint32_t(j) * 2048u, kTcTile, 1024), id_q, j != 0);
+          for (int j = 0; j < kTcLp / 16; ++j, b += 64)
+            umma_bf16(tmem_base + kbDQ + uint32_t(t) * 32u, a0 + uint64_t((uint32_t(j >> 2) * box + uint32_t(j & 3) * 32u) >> 4), b, id_q, j != 0);
+        }
         umma_commit(&bars->dq_full[t]);
         // dV += P_t^T dO_t,  dK += dS_t^T Q_t   (M = keys: tile m covers keys 128 m ..; K = the query rows of tile t)
         const int ksteps = t ? 2 : 8;
+        const uint64_t tmn = umma_sdesc_sw128(0, box, 1024);          // P / dS tiles as MN-major A (LBO = box stride)
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
-          for (int s = 0; s < ksteps; ++s) {
-            const uint32_t acc = (t != 0 || s != 0) ? 1u : 0u;
-            umma_bf16(tmem_base + kbDV + uint32_t(m) * 32u, umma_sdesc_sw128(sp[t] + uint32_t(2 * m) * box + uint32_t(s) * 2048u, box, 1024),
-                      umma_sdesc_sw128(sdo + ro + co + uint32_t(s) * 2048u, kTcTile, 1024), id_kv, acc);
-          }
-          for (int s = 0; s < ksteps; ++s) {
-            const uint32_t acc = (t != 0 || s != 0) ? 1u : 0u;
-            umma_bf16(tmem_base + kbDK + uint32_t(m) * 32u, umma_sdesc_sw128(sds[t] + uint32_t(2 * m) * box + uint32_t(s) * 2048u, box, 1024),
-                      umma_sdesc_sw128(sq + ro + co + uint32_t(s) * 2048u, kTcTile, 1024), id_kv, acc);
-          }
+          uint64_t a = d_at(tmn, sp[t] + uint32_t(2 * m) * box), b = d_at(t64k, tb + TcbSmem::tile + ro);
+          for (int s = 0; s < ksteps; ++s, a += 128, b += 64)          // +2048 B / +1024 B per 16 query rows
+            umma_bf16(tmem_base + kbDV + uint32_t(m) * 32u, a, b, id_kv, (t != 0 || s != 0) ? 1u : 0u);
+          a = d_at(tmn, sds[t] + uint32_t(2 * m) * box); b = d_at(t64k, tb + ro);
+          for (int s = 0; s < ksteps; ++s, a += 128, b += 64)
+            umma_bf16(tmem_base + kbDK + uint32_t(m) * 32u, a, b, id_kv, (t != 0 || s != 0) ? 1u : 0u);
         }
         umma_commit(&bars->pds_free[t]);
         if (last_of_head) umma_commit(&bars->dkv_full);
@@ -550,37 +566,37 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
       uint32_t ph_sdfree[2] = {0, 0}, ph_ready[2] = {0, 0}, ph_dqfree[2] = {0, 0}, ph_dkvfree = 0;
       bool sdp0_issued = false;  // S0 / dP0 of the current head were issued ahead (at the end of the previous head)
       for (int n = 0; n < nheads; ++n) {
-        const int hh = n & 1;
         if (!sdp0_issued) {
-          if (hh == 0) { mbar_wait(&bars->ld_full, (n >> 1) & 1); }
+          mbar_wait(&bars->ld_full[n & 1], (n >> 1) & 1);
           // the S / dP columns were last used by the previous head's tile 1
           if (n > 0) { mbar_wait(&bars->sd_free[1], ph_sdfree[1]); ph_sdfree[1] ^= 1; }
           tc_fence_after();
-          issue_sdp(hh, 0);
+          issue_sdp(n, 0);
         }
         sdp0_issued = false;
         // tile 0's P / dS written (S0 / dP0 drained): S1 / dP1 first, so that tile 1's softmax runs under tile 0's MMAs
         mbar_wait(&bars->pds_ready[0], ph_ready[0]); ph_ready[0] ^= 1;
         mbar_wait(&bars->sd_free[0], ph_sdfree[0]); ph_sdfree[0] ^= 1;
         tc_fence_after();
-        issue_sdp(hh, 1);
+        issue_sdp(n, 1);
         if (n > 0) {
           mbar_wait(&bars->dq_free[0], ph_dqfree[0]); ph_dqfree[0] ^= 1;
           mbar_wait(&bars->dkv_free, ph_dkvfree); ph_dkvfree ^= 1;
           tc_fence_after();
         }
-        issue_grads(hh, 0, false);
+        issue_grads(n, 0, false);
         mbar_wait(&bars->pds_ready[1], ph_ready[1]); ph_ready[1] ^= 1;
-        if (hh == 0 && n + 1 < nheads) {  // second head of the same item: its S0 / dP0 go ahead of this head's last MMA group
+        if (n + 1 < nheads) {  // the next head (its tiles sit in the other buffer): S0 / dP0 ahead of this head's last MMA group
+          mbar_wait(&bars->ld_full[(n + 1) & 1], ((n + 1) >> 1) & 1);
           mbar_wait(&bars->sd_free[1], ph_sdfree[1]); ph_sdfree[1] ^= 1;
           tc_fence_after();
-          issue_sdp(1, 0);
+          issue_sdp(n + 1, 0);
           sdp0_issued = true;
         }
         if (n > 0) { mbar_wait(&bars->dq_free[1], ph_dqfree[1]); ph_dqfree[1] ^= 1; }
         tc_fence_after();
-        issue_grads(hh, 1, true);
-        if (hh == 1) umma_commit(&bars->ld_empty);
+        issue_grads(n, 1, true);
+        umma_commit(&bars->ld_empty[n & 1]);
       }
     }
   } else if (warp == 0 || warp >= 4) {
@@ -604,8 +620,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
 #pragma unroll
       for (int k = 0; k < 4; ++k) { rc_o[k] = make_uint4(0, 0, 0, 0); rc_d[k] = make_uint4(0, 0, 0, 0); }
       if (m >= nheads || row >= L) return;
-      const int item = int(blockIdx.x) + (m >> 1) * int(gridDim.x);
-      const int b = item / HP, h = (item % HP) * 2 + (m & 1);
+      const int item = int(blockIdx.x) + m * int(gridDim.x);
+      const int b = item / H, h = item % H;
       rc_l = __ldg(lse + (size_t(b) * H + h) * L + row);
       const uint4* op = reinterpret_cast<const uint4*>(out + (size_t(b) * L + row) * D + h * 32);
       const uint4* dp = reinterpret_cast<const uint4*>(dout + (size_t(b) * L + row) * D + h * 32);
@@ -625,10 +641,26 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
     float lse2_next, delta_next;
     row_consts_issue(0);
     row_consts_finish(lse2_next, delta_next);
+    __nv_bfloat16* prev_base = nullptr;  // tile-0 warps: dqkv row of the head whose dK / dV epilogue is pending
+    auto dkv_epilogue = [&](__nv_bfloat16* base) {
+      mbar_wait(&bars->dkv_full, ph_dkvfull); ph_dkvfull ^= 1;
+      tc_fence_after();
+      uint32_t o[32], o2[32];
+      tmem_ld32_nowait(tmem_base + lane_off + kbDK + uint32_t(tile) * 32u, o);
+      tmem_ld32_nowait(tmem_base + lane_off + kbDV + uint32_t(tile) * 32u, o2);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->dkv_free);
+      if (row < L) {
+        store_row32(base + D, o, scale);
+        store_row32(base + 2 * D, o2, 1.0f);
+      }
+    };
 #pragma unroll 1
     for (int n = 0; n < nheads; ++n) {
-      const int item = int(blockIdx.x) + (n >> 1) * int(gridDim.x);
-      const int b = item / HP, hp = item % HP, hh = n & 1, h = hp * 2 + hh;
+      const int item = int(blockIdx.x) + n * int(gridDim.x);
+      const int b = item / H, h = item % H;
       const float lse2 = lse2_next, delta = delta_next;
       mbar_wait(&bars->sd_full[tile], ph_sdfull); ph_sdfull ^= 1;
       tc_fence_after();
@@ -673,6 +705,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->pds_ready[tile]);
       row_consts_issue(n + 1);  // in flight during the epilogue waits below
+      if (!tile && n > 0) dkv_epilogue(prev_base);  // the previous head's dK / dV rows
       // dQ rows of this tile
       {
         mbar_wait(&bars->dq_full[tile], ph_dqfull); ph_dqfull ^= 1;
@@ -685,25 +718,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
         if (lane == 0) mbar_arrive(&bars->dq_free[tile]);
         if (row < L) store_row32(dqkv + (size_t(b) * L + row) * 3 * D + h * 32, o, scale);
       }
-      // dK / dV rows (keys = TMEM lanes) once both query tiles have been accumulated
-      {
-        mbar_wait(&bars->dkv_full, ph_dkvfull); ph_dkvfull ^= 1;
-        tc_fence_after();
-        uint32_t o[32], o2[32];
-        tmem_ld32_nowait(tmem_base + lane_off + kbDK + uint32_t(tile) * 32u, o);
-        tmem_ld32_nowait(tmem_base + lane_off + kbDV + uint32_t(tile) * 32u, o2);
-        tmem_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->dkv_free);
-        if (row < L) {
-          __nv_bfloat16* base = dqkv + (size_t(b) * L + row) * 3 * D + h * 32;
-          store_row32(base + D, o, scale);
-          store_row32(base + 2 * D, o2, 1.0f);
-        }
-      }
+      // dK / dV rows (keys = TMEM lanes) once both query tiles have been accumulated.  The tile-0 warps defer this to
+      // after the next head's softmax (dkv_epilogue below): the wait for tile 1 and its gradient MMAs is the longest of the
+      // head, and the next head's S0 / dP0 are already in TMEM.
+      if (tile) dkv_epilogue(dqkv + (size_t(b) * L + row) * 3 * D + h * 32);
+      else prev_base = dqkv + (size_t(b) * L + row) * 3 * D + h * 32;
       row_consts_finish(lse2_next, delta_next);
     }
+    if (!tile && nheads > 0) dkv_epilogue(prev_base);
   }
   tc_fence_before();
   __syncthreads();
@@ -714,9 +736,9 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
                 cudaStream_t st) {
   CUtensorMap mq, md;
   const int D = H * 32;
-  int rc = make_tmap_bf16_3d(&mq, qkv, 3 * D, L, B, 3 * D, kTcLp);
+  int rc = make_tmap_bf16_3d(&mq, qkv, 3 * D, L, B, 3 * D, kTcLp, 32);
   if (rc) return rc;
-  rc = make_tmap_bf16_3d(&md, dout, D, L, B, D, kTcLp);
+  rc = make_tmap_bf16_3d(&md, dout, D, L, B, D, kTcLp, 32);
   if (rc) return rc;
   static bool done = false;
   if (!done) {
@@ -727,7 +749,7 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int nitems = B * (H / 2);
+  const int nitems = B * H;
   const int grid = nitems < sms ? nitems : sms;
   mae_launch(attn_bwd_tc_kernel, dim3(grid), dim3(kTcThreads), size_t(TcbSmem::total) + 1024, st, mq, md,
              reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), lse, reinterpret_cast<__nv_bfloat16*>(dqkv), B, L, H,
