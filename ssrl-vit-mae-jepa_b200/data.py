@@ -74,6 +74,7 @@ class GpuAugment:
     def __init__(self, size: int = 96, scale=(0.8, 1.0), ratio=(3.0 / 4.0, 4.0 / 3.0), train: bool = True,
                  generator: Optional[torch.Generator] = None):
         self.size, self.scale, self.ratio, self.train, self.generator = size, scale, ratio, train, generator
+        self._next, self._next_key = None, None  # parameters drawn ahead for the next call
 
     def draw_params(self, B: int, H: int, W: int, device) -> torch.Tensor:
         """(B,5) int32 rows (i, j, h, w, flip) on ``device``."""
@@ -108,20 +109,30 @@ class GpuAugment:
             raise RuntimeError("GpuAugment needs a CUDA uint8 (B,C,H,W) batch (there is no CPU fallback)")
         images_u8 = images_u8.contiguous()
         B, C, H, W = images_u8.shape
-        if params is None:
-            # drawn on the host (a few vectorised ops that run ahead of the GPU) and shipped as one 40 KB pinned copy:
-            # on the device the same ~35 tiny elementwise launches would sit in the compute stream (~0.4 ms per step)
-            where = self.generator.device if self.generator is not None else torch.device("cpu")
-            params = self.draw_params(B, H, W, where)
-            if params.device.type == "cpu":
-                params = params.pin_memory()
+        drawn_here = params is None
+        if drawn_here:
+            # Drawn on the host (a few vectorised ops) and shipped as one 40 KB copy from a persistent pinned buffer:
+            # on the device the same ~35 tiny elementwise launches would sit in the compute stream (~0.4 ms per step).
+            # The draw for the NEXT call is made right after this call's kernel launch, so the host work overlaps the
+            # GPU instead of delaying the first launch of a step.
+            key = (B, H, W)
+            if self._next_key != key:
+                self._next, self._next_key = self._draw_host(B, H, W), key
+            params = self._next
         params = params.to(device=images_u8.device, dtype=torch.int32, non_blocking=True).contiguous()
         if params.shape != (B, 5):
             raise ValueError(f"params must be ({B},5)")
         out = torch.empty(B, C, self.size, self.size, dtype=torch.float32, device=images_u8.device)
         calls.mae_augment_u8(images_u8.data_ptr(), params.data_ptr(), B, C, H, W, self.size, out.data_ptr(),
                              torch.cuda.current_stream(images_u8.device).cuda_stream)
+        if drawn_here:
+            self._next = self._draw_host(B, H, W)  # the previous pinned buffer is kept alive by `params` until its copy ran
         return out
+
+    def _draw_host(self, B: int, H: int, W: int) -> torch.Tensor:
+        where = self.generator.device if self.generator is not None else torch.device("cpu")
+        p = self.draw_params(B, H, W, where)
+        return p.pin_memory() if p.device.type == "cpu" else p
 
 
 def _real_stl10(split: str, train: bool, raw_uint8: bool = False):
