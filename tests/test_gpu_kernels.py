@@ -239,6 +239,37 @@ def test_attention_fwd_bwd(B, L, H, hd):
             assert max_err(dqkv[:, :, i], qf.grad[:, :, i]) < 2e-2
 
 
+@pytest.mark.parametrize("B,L,H", [(1, 145, 2), (74, 145, 6), (149, 133, 4), (301, 160, 2)])
+def test_attention_tc_repeatable_and_item_distribution(B, L, H):
+    """The tcgen05 attention kernels are persistent (148 CTAs walking (sample, head) items through mbarrier pipelines) and
+    use no atomics: results must be bit-identical from run to run and correct for 1 item, fewer / more items than CTAs and
+    item counts that are not multiples of the grid (a lost or reordered pipeline phase shows up as a mismatch)."""
+    hd, D = 32, H * 32
+    g = torch.Generator().manual_seed(B + L)
+    qkv = bf(torch.randn(B, L, 3, H, hd, generator=g)).to(dev)
+    dout = bf(torch.randn(B, L, D, generator=g)).to(dev)
+    outs = []
+    for _ in range(3):
+        out = torch.full((B, L, D), float("nan"), dtype=torch.bfloat16, device=dev)
+        lse = torch.full((B, H, L), float("nan"), device=dev)
+        dqkv = torch.full_like(qkv, float("nan"))
+        calls.mae_attention_fwd(p(qkv), B, L, H, hd, p(out), p(lse), stream())
+        calls.mae_attention_bwd(p(qkv), p(out), p(dout), p(lse), B, L, H, hd, p(dqkv), stream())
+        outs.append((out, lse, dqkv))
+    for o in outs[1:]:
+        assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2])
+    out, lse, dqkv = outs[0]
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all() and torch.isfinite(dqkv.float()).all()
+    # spot-check samples spread over the batch (first, middle, last) against fp32 torch
+    for b in sorted({0, B // 2, B - 1}):
+        qf = qkv[b:b + 1].float().requires_grad_(True)
+        q, k, v = qf.permute(2, 0, 3, 1, 4).unbind(0)
+        ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(1, L, D)
+        ref.backward(dout[b:b + 1].float())
+        assert max_err(out[b:b + 1], ref) < 2e-2
+        assert rel_err(dqkv[b:b + 1], qf.grad) < 3e-2
+
+
 def test_scatter_decoder_and_row_ops():
     B, L, Lk, D = 5, 145, 36, 192
     g = torch.Generator().manual_seed(11)
