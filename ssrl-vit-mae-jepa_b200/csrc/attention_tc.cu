@@ -123,6 +123,13 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 static constexpr int kTcLp = 160;                       // padded tokens (keys = MMA N, query tiles 128 + 32)
@@ -435,7 +442,7 @@ int attn_fwd_tc(const void* qkv, int B, int L, int H, void* out, float* lse, cud
 // =============================================================================================
 struct TcbBars {
   uint64_t ld_full[2], ld_empty[2];   // [buffer]: Q / dO / K / V of a head landed / every MMA reading them has completed
-  uint64_t sd_full[2], sd_free[2];    // [query tile]: S and dP complete / pulled out of TMEM
+  uint64_t sd_full[2][2], sd_free[2][2];  // [query tile][key half]: S and dP of 80 keys complete / pulled out of TMEM
   uint64_t pds_ready[2], pds_free[2]; // [query tile]: P and dS tiles written / the MMAs reading them are done
   uint64_t dq_full[2], dq_free[2];
   uint64_t dkv_full, dkv_free;
@@ -451,7 +458,9 @@ struct TcbSmem {  // P0/dS0 first: the MN-major reads of the second key tile run
   static constexpr uint32_t bars = tiles + 2 * 4 * tile;  // 204800
   static constexpr uint32_t total = bars + 1024;
 };
-static constexpr uint32_t kbS = 0, kbDP = 160, kbDQ = 320, kbDK = 384, kbDV = 448;
+// TMEM: two S / dP buffers of 80 key columns each (buffer = key half; S at +0, dP at +80): the two query tiles of a head
+// take turns in them half by half, so tile 1's softmax overlaps tile 0's second half and the next head's first half
+static constexpr uint32_t kbSD = 0, kbDQ = 320, kbDK = 384, kbDV = 448;
 
 // 32 values of one TMEM row segment -> 64 contiguous bytes of a global bf16 row
 __device__ __forceinline__ void store_row32(__nv_bfloat16* dst, const uint32_t (&o)[32], float mul) {
@@ -484,7 +493,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
     tma_prefetch_desc(&mapDO);
     for (int t = 0; t < 2; ++t) {
       mbar_init(&bars->ld_full[t], 1); mbar_init(&bars->ld_empty[t], 1);
-      mbar_init(&bars->sd_full[t], 1); mbar_init(&bars->sd_free[t], t == 0 ? 4 : 1);
+      for (int hf = 0; hf < 2; ++hf) { mbar_init(&bars->sd_full[t][hf], 1); mbar_init(&bars->sd_free[t][hf], t == 0 ? 4 : 1); }
       mbar_init(&bars->pds_ready[t], t == 0 ? 4 : 1); mbar_init(&bars->pds_free[t], 1);
       mbar_init(&bars->dq_full[t], 1); mbar_init(&bars->dq_free[t], t == 0 ? 4 : 1);
     }
@@ -526,15 +535,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
       const uint64_t t64k = umma_sdesc_sw64(0, 16, 512);            // 64-byte rows: tiles loaded by TMA (K- or MN-major)
       const uint64_t t128k = umma_sdesc_sw128(0, 16, 1024);         // P / dS tiles as K-major A
       auto d_at = [](uint64_t templ, uint32_t addr) { return templ + uint64_t((addr & 0x3ffffu) >> 4); };
-      auto issue_sdp = [&](int n, int t) {  // S_t = Q_t K^T and dP_t = dO_t V^T of head n
-        const uint32_t tb = tiles0 + uint32_t(n & 1) * 4u * TcbSmem::tile, ro = uint32_t(t) * 8192u;
+      const uint32_t id_s80 = umma_idesc_bf16(128, 80, 0, 0);
+      auto issue_sdp = [&](int n, int t, int hf) {  // S_t = Q_t K^T and dP_t = dO_t V^T of head n, keys [80 hf, 80 hf + 80)
+        const uint32_t tb = tiles0 + uint32_t(n & 1) * 4u * TcbSmem::tile, ro = uint32_t(t) * 8192u, ko = uint32_t(hf) * 80u * 64u;
         const uint64_t dq_ = d_at(t64k, tb + ro), ddo = d_at(t64k, tb + TcbSmem::tile + ro);
-        const uint64_t dk_ = d_at(t64k, tb + 2 * TcbSmem::tile), dv_ = d_at(t64k, tb + 3 * TcbSmem::tile);
-        umma_bf16(tmem_base + kbS, dq_, dk_, id_s, 0);
-        umma_bf16(tmem_base + kbS, dq_ + 2, dk_ + 2, id_s, 1);       // +32 B per K = 16
-        umma_bf16(tmem_base + kbDP, ddo, dv_, id_s, 0);
-        umma_bf16(tmem_base + kbDP, ddo + 2, dv_ + 2, id_s, 1);
-        umma_commit(&bars->sd_full[t]);
+        const uint64_t dk_ = d_at(t64k, tb + 2 * TcbSmem::tile + ko), dv_ = d_at(t64k, tb + 3 * TcbSmem::tile + ko);
+        const uint32_t d = tmem_base + kbSD + uint32_t(hf) * 160u;
+        umma_bf16(d, dq_, dk_, id_s80, 0);
+        umma_bf16(d, dq_ + 2, dk_ + 2, id_s80, 1);       // +32 B per K = 16
+        umma_bf16(d + 80, ddo, dv_, id_s80, 0);
+        umma_bf16(d + 80, ddo + 2, dv_ + 2, id_s80, 1);
+        umma_commit(&bars->sd_full[t][hf]);
       };
       auto issue_grads = [&](int n, int t, bool last_of_head) {
         const uint32_t tb = tiles0 + uint32_t(n & 1) * 4u * TcbSmem::tile, ro = uint32_t(t) * 8192u;
@@ -563,36 +574,41 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
         umma_commit(&bars->pds_free[t]);
         if (last_of_head) umma_commit(&bars->dkv_full);
       };
-      uint32_t ph_sdfree[2] = {0, 0}, ph_ready[2] = {0, 0}, ph_dqfree[2] = {0, 0}, ph_dkvfree = 0;
-      bool sdp0_issued = false;  // S0 / dP0 of the current head were issued ahead (at the end of the previous head)
+      uint32_t ph_sdfree[2][2] = {{0, 0}, {0, 0}}, ph_ready[2] = {0, 0}, ph_dqfree[2] = {0, 0}, ph_dkvfree = 0;
+      auto wait_sdfree = [&](int t, int hf) { mbar_wait(&bars->sd_free[t][hf], ph_sdfree[t][hf]); ph_sdfree[t][hf] ^= 1; };
+      bool sdp0_issued = false;  // tile 0's S / dP of the current head were issued ahead (inside the previous head)
       for (int n = 0; n < nheads; ++n) {
         if (!sdp0_issued) {
           mbar_wait(&bars->ld_full[n & 1], (n >> 1) & 1);
-          // the S / dP columns were last used by the previous head's tile 1
-          if (n > 0) { mbar_wait(&bars->sd_free[1], ph_sdfree[1]); ph_sdfree[1] ^= 1; }
-          tc_fence_after();
-          issue_sdp(n, 0);
+          for (int hf = 0; hf < 2; ++hf) {  // each buffer was last used by the previous head's tile 1
+            if (n > 0) wait_sdfree(1, hf);
+            tc_fence_after();
+            issue_sdp(n, 0, hf);
+          }
         }
         sdp0_issued = false;
-        // tile 0's P / dS written (S0 / dP0 drained): S1 / dP1 first, so that tile 1's softmax runs under tile 0's MMAs
+        for (int hf = 0; hf < 2; ++hf) {  // tile 1 follows tile 0 through the two buffers
+          wait_sdfree(0, hf);
+          tc_fence_after();
+          issue_sdp(n, 1, hf);
+        }
         mbar_wait(&bars->pds_ready[0], ph_ready[0]); ph_ready[0] ^= 1;
-        mbar_wait(&bars->sd_free[0], ph_sdfree[0]); ph_sdfree[0] ^= 1;
-        tc_fence_after();
-        issue_sdp(n, 1);
         if (n > 0) {
           mbar_wait(&bars->dq_free[0], ph_dqfree[0]); ph_dqfree[0] ^= 1;
           mbar_wait(&bars->dkv_free, ph_dkvfree); ph_dkvfree ^= 1;
-          tc_fence_after();
         }
+        tc_fence_after();
         issue_grads(n, 0, false);
-        mbar_wait(&bars->pds_ready[1], ph_ready[1]); ph_ready[1] ^= 1;
-        if (n + 1 < nheads) {  // the next head (its tiles sit in the other buffer): S0 / dP0 ahead of this head's last MMA group
+        if (n + 1 < nheads) {  // the next head's tile 0 as soon as tile 1 has drained each buffer
           mbar_wait(&bars->ld_full[(n + 1) & 1], ((n + 1) >> 1) & 1);
-          mbar_wait(&bars->sd_free[1], ph_sdfree[1]); ph_sdfree[1] ^= 1;
-          tc_fence_after();
-          issue_sdp(n + 1, 0);
+          for (int hf = 0; hf < 2; ++hf) {
+            wait_sdfree(1, hf);
+            tc_fence_after();
+            issue_sdp(n + 1, 0, hf);
+          }
           sdp0_issued = true;
         }
+        mbar_wait(&bars->pds_ready[1], ph_ready[1]); ph_ready[1] ^= 1;
         if (n > 0) { mbar_wait(&bars->dq_free[1], ph_dqfree[1]); ph_dqfree[1] ^= 1; }
         tc_fence_after();
         issue_grads(n, 1, true);
@@ -662,45 +678,57 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
       const int item = int(blockIdx.x) + n * int(gridDim.x);
       const int b = item / H, h = item % H;
       const float lse2 = lse2_next, delta = delta_next;
-      mbar_wait(&bars->sd_full[tile], ph_sdfull); ph_sdfull ^= 1;
-      tc_fence_after();
-      if (n > 0) { mbar_wait(&bars->pds_free[tile], ph_pdsfree); ph_pdsfree ^= 1; }  // previous head's MMAs have read the tiles
-      const uint32_t s_addr = tmem_base + lane_off + kbS, dp_addr = tmem_base + lane_off + kbDP;
-      uint32_t sA[32], dA[32], sB[32], dB[32];
-      tmem_ld32_nowait(s_addr, sA);
-      tmem_ld32_nowait(dp_addr, dA);
 #pragma unroll
-      for (int c = 0; c < 5; ++c) {
-        uint32_t (&sc)[32] = (c & 1) ? sB : sA;
-        uint32_t (&dc)[32] = (c & 1) ? dB : dA;
-        tmem_wait_ld();
-        if (c < 4) {  // prefetch the next chunk while this one is processed
-          tmem_ld32_nowait(s_addr + (c + 1) * 32, (c & 1) ? sA : sB);
-          tmem_ld32_nowait(dp_addr + (c + 1) * 32, (c & 1) ? dA : dB);
-        } else {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->sd_free[tile]);
-        }
-        uint32_t pk[16], dk[16];
+      for (int hf = 0; hf < 2; ++hf) {  // keys [80 hf, 80 hf + 80): chunks of 32, 32 and 16 columns
+        mbar_wait(&bars->sd_full[tile][hf], ph_sdfull); 
+        tc_fence_after();
+        if (hf == 0 && n > 0) { mbar_wait(&bars->pds_free[tile], ph_pdsfree); ph_pdsfree ^= 1; }  // previous head's MMAs have read the tiles
+        const uint32_t s_addr = tmem_base + lane_off + kbSD + uint32_t(hf) * 160u, dp_addr = s_addr + 80;
+        uint32_t sA[32], dA[32], sB[32], dB[32];
+        tmem_ld32_nowait(s_addr, sA);
+        tmem_ld32_nowait(dp_addr, dA);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = ex2_approx(__uint_as_float(sc[2 * i]) * sl2 - lse2);
-          float p1 = ex2_approx(__uint_as_float(sc[2 * i + 1]) * sl2 - lse2);
-          if (c == 4) {
-            if (128 + 2 * i >= L) p0 = 0.f;
-            if (128 + 2 * i + 1 >= L) p1 = 0.f;
+        for (int c = 0; c < 3; ++c) {
+          uint32_t (&sc)[32] = (c & 1) ? sB : sA;
+          uint32_t (&dc)[32] = (c & 1) ? dB : dA;
+          tmem_wait_ld();
+          if (c == 0) {
+            tmem_ld32_nowait(s_addr + 32, sB);
+            tmem_ld32_nowait(dp_addr + 32, dB);
+          } else if (c == 1) {
+            tmem_ld16_nowait(s_addr + 64, sA);
+            tmem_ld16_nowait(dp_addr + 64, dA);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->sd_free[tile][hf]);
           }
-          pk[i] = pack_bf16x2(p0, p1);
-          dk[i] = pack_bf16x2(p0 * (__uint_as_float(dc[2 * i]) - delta), p1 * (__uint_as_float(dc[2 * i + 1]) - delta));
-        }
-        const uint32_t boxo = uint32_t(c >> 1) * box_bytes;
+          const int npair = c < 2 ? 16 : 8;
+          const int col0 = hf * 80 + c * 32;
+          uint32_t pk[16], dk[16];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          sts16(swz(p_base + boxo, prow, (c & 1) * 4 + k), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
-          sts16(swz(ds_base + boxo, prow, (c & 1) * 4 + k), dk[4 * k], dk[4 * k + 1], dk[4 * k + 2], dk[4 * k + 3]);
+          for (int i = 0; i < 16; ++i) {
+            if (i >= npair) break;
+            float p0 = ex2_approx(__uint_as_float(sc[2 * i]) * sl2 - lse2);
+            float p1 = ex2_approx(__uint_as_float(sc[2 * i + 1]) * sl2 - lse2);
+            if (hf == 1 && c >= 1) {  // only columns >= 112 can reach L (> 128)
+              if (col0 + 2 * i >= L) p0 = 0.f;
+              if (col0 + 2 * i + 1 >= L) p1 = 0.f;
+            }
+            pk[i] = pack_bf16x2(p0, p1);
+            dk[i] = pack_bf16x2(p0 * (__uint_as_float(dc[2 * i]) - delta), p1 * (__uint_as_float(dc[2 * i + 1]) - delta));
+          }
+          const int g0 = col0 >> 3;  // first 16-byte chunk of this step inside the tile row: box g / 8, chunk g % 8
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k >= npair / 4) break;
+            const int g = g0 + k;
+            sts16(swz(p_base + uint32_t(g >> 3) * box_bytes, prow, g & 7), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
+            sts16(swz(ds_base + uint32_t(g >> 3) * box_bytes, prow, g & 7), dk[4 * k], dk[4 * k + 1], dk[4 * k + 2], dk[4 * k + 3]);
+          }
         }
       }
+      ph_sdfull ^= 1;
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->pds_ready[tile]);
