@@ -129,9 +129,69 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def algorithmic_cost(name, a):
+    """(bytes, flops, shape label) one C-ABI call has to move / compute at minimum (every operand once; the argument order
+    is include/mae_b200.h's).  Used for the per-kernel roofline table; unknown entry points return (None, None, "")."""
+    nz = lambda p: 1 if p else 0
+    if name == "mae_gemm_tn":
+        M, N, K, epi = a[2], a[3], a[4], a[5]
+        out_b = {0: 2, 1: 4, 2: 4, 4: 2}[epi]            # bf16 | bf16 h + bf16 gelu' | fp32 | bf16
+        aux_b = {0: 0, 1: 0, 2: 4, 4: 2}[epi]            # - | - | fp32 residual | bf16 gelu'
+        return M * K * 2.0 + N * K * 2.0 + M * N * (out_b + aux_b), 2.0 * M * N * K, f"M={M} N={N} K={K} epi={epi}"
+    if name == "mae_gemm_wgrad":
+        Pc, Qc, M = a[1], a[3], a[4]
+        return M * (Pc + Qc) * 2.0 + Pc * Qc * 4.0, 2.0 * M * Pc * Qc, f"M={M} P={Pc} Q={Qc}"
+    if name == "mae_attention_fwd":
+        B, L, H, hd = a[1], a[2], a[3], a[4]
+        return B * L * H * hd * 2.0 * 4 + B * H * L * 4.0, 4.0 * B * H * L * L * hd, f"B={B} L={L} H={H} hd={hd}"
+    if name == "mae_attention_bwd":
+        B, L, H, hd = a[4], a[5], a[6], a[7]
+        return B * L * H * hd * 2.0 * 8 + B * H * L * 4.0, 10.0 * B * H * L * L * hd, f"B={B} L={L} H={H} hd={hd}"
+    if name == "mae_layernorm_fwd":
+        rows, D = a[6], a[7]
+        return rows * D * 6.0 + rows * 8.0, 0.0, f"rows={rows} D={D}"
+    if name == "mae_layernorm_bwd":
+        rows, D = a[9], a[10]
+        return rows * D * (2.0 + 4 + 4 * nz(a[5]) + 4 + 2 * nz(a[12])) + rows * 8.0, 0.0, f"rows={rows} D={D}"
+    if name == "mae_random_token_mask":
+        B, L = a[1], a[2]
+        return B * L * 12.0, 0.0, f"B={B} L={L}"
+    if name == "mae_gather_patches":
+        B, C, patch, nk = a[2], a[3], a[5], a[6]
+        return B * (nk - 1) * C * patch * patch * 6.0, 0.0, f"B={B} kept={nk - 1}"
+    if name == "mae_assemble_tokens":
+        B, nk, D = a[4], a[5], a[6]
+        return B * nk * D * 6.0, 0.0, f"B={B} kept={nk} D={D}"
+    if name == "mae_scatter_decoder_tokens":
+        B, L, nk, D = a[5], a[6], a[7], a[8]
+        return B * nk * D * 2.0 + B * L * D * 4.0, 0.0, f"B={B} L={L} D={D}"
+    if name == "mae_masked_mse":
+        B, C, patch, nm = a[3], a[4], a[6], a[7]
+        return B * nm * C * patch * patch * (2.0 + 4 + 2 * nz(a[11]) + 4 * nz(a[12])), 0.0, f"B={B} masked={nm}"
+    if name == "mae_colsum_bf16":
+        return a[1] * a[2] * 2.0, 0.0, f"M={a[1]} N={a[2]}"
+    if name == "mae_gather_rows_bf16":
+        return a[2] * a[3] * a[6] * 6.0, 0.0, f"rows={a[2] * a[3]} D={a[6]}"
+    if name == "mae_zero_rows":
+        return a[3] * a[4] * a[6] * (4.0 + 2 * nz(a[1])), 0.0, f"rows={a[3] * a[4]} D={a[6]}"
+    if name == "mae_colsum_rows_f32":
+        return a[2] * a[3] * a[6] * 4.0, 0.0, f"rows={a[2] * a[3]} D={a[6]}"
+    if name == "mae_cast_bf16":
+        return a[2] * 6.0, 0.0, f"n={a[2]}"
+    if name == "mae_grad_sumsq":
+        return a[1] * 4.0, 0.0, f"n={a[1]}"
+    if name == "mae_clip_adamw":
+        return a[5] * 30.0, 0.0, f"n={a[5]}"  # read p, g, m, v; write p, m, v and the bf16 shadow
+    if name == "mae_augment_u8":
+        B, C, S = a[2], a[3], a[6]
+        return B * C * S * S * 5.0, 0.0, f"B={B} S={S}"  # lower bound: a crop at least as large as the output
+    return None, None, ""
+
+
 def kernel_breakdown(trainer, images, noise, pk):
-    """One instrumented step: CUDA events around every C-ABI call -> time share per kernel family and the
-    roofline of the dominant one (gemm_tn: algorithmic FLOPs of its launches / their summed duration)."""
+    """One instrumented step: CUDA events around every C-ABI call -> time share per kernel family, the roofline of the
+    dominant one (gemm_tn: algorithmic bytes of its launches / their summed duration) and a per-kernel, per-shape roofline
+    table (achieved GB/s and TFLOP/s against the measured peaks)."""
     import torch
 
     from ssrl_vit_mae_jepa_b200._lib import calls
@@ -166,6 +226,7 @@ def kernel_breakdown(trainer, images, noise, pk):
         for name, fn in orig.items():
             setattr(lib_calls, name, fn)
     fam = {}
+    table = {}
     gemm_flops = 0.0
     gemm_bytes = 0.0
     wgrad_flops = 0.0
@@ -173,15 +234,22 @@ def kernel_breakdown(trainer, images, noise, pk):
         ms = s.elapsed_time(e)
         d = fam.setdefault(name, [0.0, 0])
         d[0] += ms; d[1] += 1
+        nbytes, flops, label = algorithmic_cost(name, a)
+        if nbytes is not None:
+            t = table.setdefault((name, label), [0.0, 0, 0.0, 0.0])
+            t[0] += ms; t[1] += 1; t[2] += nbytes; t[3] += flops
         if name == "mae_gemm_tn":
-            M, N, K, epi = a[2], a[3], a[4], a[5]
-            gemm_flops += 2.0 * M * N * K
-            # algorithmic bytes of one launch: A once, weights once, the output(s), and the aux operand
-            out_b = {0: 2, 1: 4, 2: 4, 4: 2}[epi]            # bf16 | bf16 h + bf16 gelu' | fp32 | bf16
-            aux_b = {0: 0, 1: 0, 2: 4, 4: 2}[epi]            # - | - | fp32 residual | bf16 gelu'
-            gemm_bytes += M * K * 2.0 + N * K * 2.0 + M * N * (out_b + aux_b)
+            gemm_flops += flops
+            gemm_bytes += nbytes
         if name == "mae_gemm_wgrad":
-            wgrad_flops += 2.0 * a[1] * a[3] * a[4]
+            wgrad_flops += flops
+    rows = []
+    for (name, label), (ms, n, nbytes, flops) in sorted(table.items(), key=lambda kv: -kv[1][0]):
+        gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        tfs = flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        rows.append({"kernel": name[4:], "shape": label, "launches": n, "us_per_launch": round(ms * 1e3 / n, 1),
+                     "mb_per_launch": round(nbytes / n / 1e6, 2), "gbs": round(gbs, 1), "hbm_frac": round(gbs / pk["hbm_gbs"], 3),
+                     "tflops": round(tfs, 1), "tensor_frac": round(tfs / pk["tf_sustained"], 3)})
     total = sum(v[0] for v in fam.values())
     share = {k: {"ms": round(v[0], 4), "launches": v[1], "share": round(v[0] / total, 4)} for k, v in
              sorted(fam.items(), key=lambda kv: -kv[1][0])}
@@ -200,7 +268,7 @@ def kernel_breakdown(trainer, images, noise, pk):
                            "flops_per_step": gemm_flops}}
     w_ms = fam.get("mae_gemm_wgrad", [0.0, 0])[0]
     extra = {"gemm_wgrad_tflops": (wgrad_flops / (w_ms * 1e-3) / 1e12) if w_ms > 0 else None,
-             "instrumented_step_ms": total}
+             "instrumented_step_ms": total, "kernel_roofline": rows}
     return share, roof, extra
 
 

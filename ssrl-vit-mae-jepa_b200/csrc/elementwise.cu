@@ -1,6 +1,7 @@
 // HBM-bound kernels of the MAE step: token masking (warp bitonic sort), patch gather, token assembly,
 // LayerNorm fwd/bwd, decoder scatter, masked MSE, column sums, casts, clip+AdamW.
 #include "mae_internal.h"
+#include <stdlib.h>
 #include "ptx.cuh"
 
 namespace mae {
@@ -145,11 +146,11 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const __nv_bfloat1
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ long long map_row(long long r, const int64_t* gather_idx, int n_sel, int L_src) {
   if (gather_idx == nullptr) return r;
-  const long long b = r / n_sel;
-  return b * L_src + gather_idx[r];
+  const long long b = (long long)(uint32_t(r) / uint32_t(n_sel));  // rows is an int: 32-bit division
+  return b * L_src + __ldg(gather_idx + r);
 }
 
-template <int NV, int ROWS>
+template <int NV, int ROWS, bool GATHER>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta,
@@ -172,7 +173,16 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   }
   const float invD = 1.0f / D;
   const long long stride = (long long)gridDim.x * wpb;
-  for (long long ra = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); ra < rows; ra += ROWS * stride) {
+  // source rows of the NEXT iteration (the index load of a gathered norm is fetched one iteration ahead, so that it is
+  // not a dependent round trip in front of every row load)
+  long long xr_next[ROWS];
+  const long long ra0 = (long long)blockIdx.x * wpb + (threadIdx.x >> 5);
+#pragma unroll
+  for (int k = 0; k < ROWS; ++k) {
+    const long long r = ra0 + k * stride;
+    xr_next[k] = (GATHER && ra0 < rows) ? map_row(r < rows ? r : ra0, gather_idx, n_sel, L_src) : 0;
+  }
+  for (long long ra = ra0; ra < rows; ra += ROWS * stride) {
     float4 v[ROWS][NV];
     long long rr[ROWS];
     bool ok[ROWS];
@@ -181,11 +191,21 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
       rr[k] = ra + k * stride;
       ok[k] = rr[k] < rows;
       if (!ok[k]) rr[k] = ra;
-      const float* src = x + map_row(rr[k], gather_idx, n_sel, L_src) * D;
+      const float* src = x + (GATHER ? xr_next[k] : rr[k]) * D;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         v[k][j] = make_float4(0, 0, 0, 0);
         if (has[j]) v[k][j] = *reinterpret_cast<const float4*>(src + 128 * j + 4 * lane);
+      }
+    }
+    if (GATHER) {
+      const long long rn = ra + ROWS * stride;
+      if (rn < rows) {
+#pragma unroll
+        for (int k = 0; k < ROWS; ++k) {
+          const long long r = rn + k * stride;
+          xr_next[k] = map_row(r < rows ? r : rn, gather_idx, n_sel, L_src);
+        }
       }
     }
 #pragma unroll
@@ -218,7 +238,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   }
 }
 
-template <int NV, int ROWS, int MINB>
+template <int NV, int ROWS, int MINB, bool GATHER>
 __global__ void __launch_bounds__(256, MINB) layernorm_bwd_kernel(
     const __nv_bfloat16* __restrict__ g, const float* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dx_in,
@@ -245,7 +265,14 @@ __global__ void __launch_bounds__(256, MINB) layernorm_bwd_kernel(
   }
   const float invD = 1.0f / D;
   const long long stride = (long long)gridDim.x * wpb;
-  for (long long ra = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); ra < rows; ra += ROWS * stride) {
+  long long xr_next[ROWS];  // see layernorm_fwd_kernel
+  const long long ra0 = (long long)blockIdx.x * wpb + (threadIdx.x >> 5);
+#pragma unroll
+  for (int k = 0; k < ROWS; ++k) {
+    const long long r = ra0 + k * stride;
+    xr_next[k] = (GATHER && ra0 < rows) ? map_row(r < rows ? r : ra0, gather_idx, n_sel, L_src) : 0;
+  }
+  for (long long ra = ra0; ra < rows; ra += ROWS * stride) {
     long long rrow[ROWS], xr[ROWS];
     bool ok[ROWS];
     uint2 gg[ROWS][NV];
@@ -256,7 +283,7 @@ __global__ void __launch_bounds__(256, MINB) layernorm_bwd_kernel(
       rrow[k] = ra + k * stride;
       ok[k] = rrow[k] < rows;
       if (!ok[k]) rrow[k] = ra;
-      xr[k] = map_row(rrow[k], gather_idx, n_sel, L_src);
+      xr[k] = GATHER ? xr_next[k] : rrow[k];
       mu[k] = mean[rrow[k]]; rs[k] = rstd[rrow[k]];
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
@@ -267,6 +294,16 @@ __global__ void __launch_bounds__(256, MINB) layernorm_bwd_kernel(
           gg[k][j] = *reinterpret_cast<const uint2*>(g + rrow[k] * D + c);
           xv[k][j] = *reinterpret_cast<const float4*>(x + xr[k] * D + c);
           if (dx_in) di[k][j] = *reinterpret_cast<const float4*>(dx_in + xr[k] * D + c);
+        }
+      }
+    }
+    if (GATHER) {
+      const long long rn = ra + ROWS * stride;
+      if (rn < rows) {
+#pragma unroll
+        for (int k = 0; k < ROWS; ++k) {
+          const long long r = rn + k * stride;
+          xr_next[k] = map_row(r < rows ? r : rn, gather_idx, n_sel, L_src);
         }
       }
     }
@@ -777,13 +814,18 @@ extern "C" int mae_layernorm_fwd(const float* x, const float* gamma, const float
   if (!x || !gamma || !beta || !xn || !mean || !rstd) return MAE_ERR_NULL;
   if (D > 1024 || (D % 4) || (gather_idx && (n_sel <= 0 || L_src <= 0))) return MAE_ERR_SHAPE;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(xn);
-  const dim3 grid(grid_for(rows, 8)), block(256);
-  if (D <= 256)
-    mae_launch(layernorm_fwd_kernel<2, 2>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd);
-  else if (D <= 512)
-    mae_launch(layernorm_fwd_kernel<4, 2>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd);
-  else
-    mae_launch(layernorm_fwd_kernel<8, 1>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd);
+  static const int bps = getenv("MAE_LN_FWD_BPS") ? atoi(getenv("MAE_LN_FWD_BPS")) : 16;
+  const dim3 grid(grid_for(rows, 8, 148 * bps)), block(256);
+  if (D <= 256) {
+    if (gather_idx) mae_launch(layernorm_fwd_kernel<2, 2, true>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd);
+    else mae_launch(layernorm_fwd_kernel<2, 2, false>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd);
+  } else if (D <= 512) {
+    if (gather_idx) mae_launch(layernorm_fwd_kernel<4, 2, true>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd);
+    else mae_launch(layernorm_fwd_kernel<4, 2, false>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd);
+  } else {
+    if (gather_idx) mae_launch(layernorm_fwd_kernel<8, 1, true>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd);
+    else mae_launch(layernorm_fwd_kernel<8, 1, false>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd);
+  }
   return MAE_CHECK_LAUNCH();
 }
 
@@ -796,13 +838,18 @@ extern "C" int mae_layernorm_bwd(const void* g, const float* x, const float* mea
   if (D > 1024 || (D % 4) || (gather_idx && (n_sel <= 0 || L_src <= 0))) return MAE_ERR_SHAPE;
   const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(g);
   __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(dx_out_bf16);
-  const dim3 grid(grid_for(rows, 8, 148 * 8)), block(256);
-  if (D <= 256)
-    mae_launch(layernorm_bwd_kernel<2, 2, 3>, grid, block, 0, stream, gp, x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out, ob, dgamma, dbeta);
-  else if (D <= 512)
-    mae_launch(layernorm_bwd_kernel<4, 1, 2>, grid, block, 0, stream, gp, x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out, ob, dgamma, dbeta);
-  else
-    mae_launch(layernorm_bwd_kernel<8, 1, 1>, grid, block, 0, stream, gp, x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out, ob, dgamma, dbeta);
+  static const int bps = getenv("MAE_LN_BWD_BPS") ? atoi(getenv("MAE_LN_BWD_BPS")) : 6;  // 3 resident CTAs per SM: two full waves
+  const dim3 grid(grid_for(rows, 8, 148 * bps)), block(256);
+  if (D <= 256) {
+    if (gather_idx) mae_launch(layernorm_bwd_kernel<2, 2, 3, true>, grid, block, 0, stream, gp, x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out, ob, dgamma, dbeta);
+    else mae_launch(layernorm_bwd_kernel<2, 2, 3, false>, grid, block, 0, stream, gp, x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out, ob, dgamma, dbeta);
+  } else if (D <= 512) {
+    if (gather_idx) mae_launch(layernorm_bwd_kernel<4, 1, 2, true>, grid, block, 0, stream, gp, x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out, ob, dgamma, dbeta);
+    else mae_launch(layernorm_bwd_kernel<4, 1, 2, false>, grid, block, 0, stream, gp, x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out, ob, dgamma, dbeta);
+  } else {
+    if (gather_idx) mae_launch(layernorm_bwd_kernel<8, 1, 1, true>, grid, block, 0, stream, gp, x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out, ob, dgamma, dbeta);
+    else mae_launch(layernorm_bwd_kernel<8, 1, 1, false>, grid, block, 0, stream, gp, x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out, ob, dgamma, dbeta);
+  }
   return MAE_CHECK_LAUNCH();
 }
 

@@ -8,5 +8,6 @@ import json
 d=json.loads(open("gpurun_out/bench_$TAG.log").read().strip().splitlines()[-1])
 print("img/s",round(d["value"]),"ms",round(d["ms_per_step"],3),"e2e",round(d["e2e"]["value"]))
 print({k.replace("mae_",""):v["ms"] for k,v in d["kernel_share"].items() if v["ms"]>0.03})
-print("gemm_tn TF",round(d["roofline"]["achieved"],1),d["extra"])
+print("gemm_tn GB/s",round(d["roofline"]["achieved"],1),{k:v for k,v in d["extra"].items() if k!="kernel_roofline"})
 PY
+python tools/roofline_table.py gpurun_out/bench_$TAG.log > gpurun_out/kernel_roofline_$TAG.md; head -30 gpurun_out/kernel_roofline_$TAG.md
