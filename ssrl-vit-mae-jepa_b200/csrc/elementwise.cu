@@ -111,6 +111,27 @@ __global__ void __launch_bounds__(256) gather_patches_kernel(const float* __rest
   }
 }
 
+// Grid-stride walk over a (batch b, row j < L, float4 column d4 < D4) index space without a division per element: the
+// 64-bit divisions happen once per thread, every further step is three adds with carries.
+struct RowWalk {
+  int d4, j, b;      // current position
+  int dd, dj, db;    // the grid stride decomposed the same way
+  int D4, L;
+  __device__ __forceinline__ RowWalk(long long i0, long long stride, int D4_, int L_) : D4(D4_), L(L_) {
+    d4 = int(i0 % D4); const long long r0 = i0 / D4; j = int(r0 % L); b = int(r0 / L);
+    dd = int(stride % D4); const long long rs = stride / D4; dj = int(rs % L); db = int(rs / L);
+  }
+  __device__ __forceinline__ void next() {
+    d4 += dd;
+    const int c = d4 >= D4;
+    d4 -= c ? D4 : 0;
+    j += dj + c;
+    const int c2 = j >= L;
+    j -= c2 ? L : 0;
+    b += db + c2;
+  }
+};
+
 __global__ void __launch_bounds__(256) assemble_tokens_kernel(const __nv_bfloat16* __restrict__ tok,
                                                              const float* __restrict__ cls,
                                                              const float* __restrict__ pos,
@@ -119,11 +140,12 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const __nv_bfloat1
   pdl_trigger();
   pdl_wait();
   const int D4 = D >> 2;
-  const long long n = (long long)B * num_keep * D4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int d = int(i % D4) * 4;
-    const long long r = i / D4;
-    const int j = int(r % num_keep), b = int(r / num_keep);
+  const long long n = (long long)B * num_keep * D4, stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  RowWalk w(i0, stride, D4, num_keep);
+  for (long long i = i0; i < n; i += stride, w.next()) {
+    const int d = w.d4 * 4, j = w.j, b = w.b;
+    const long long r = (long long)b * num_keep + j;
     const int tokidx = int(idx_keep[r]);
     float4 v;
     if (j == 0) {
@@ -373,12 +395,12 @@ __global__ void __launch_bounds__(256) scatter_decoder_kernel(const __nv_bfloat1
   pdl_trigger();
   pdl_wait();
   const int D4 = D >> 2;
-  const long long n = (long long)B * L * D4;
+  const long long n = (long long)B * L * D4, stride = (long long)gridDim.x * blockDim.x;
   const int n_mask = L - num_keep;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int d = int(i % D4) * 4;
-    const long long r = i / D4;
-    const int jj = int(r % L), b = int(r / L);
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  RowWalk w(i0, stride, D4, L);
+  for (long long i = i0; i < n; i += stride, w.next()) {
+    const int d = w.d4 * 4, jj = w.j, b = w.b;
     int l;
     float4 v;
     if (jj < num_keep) {
@@ -593,8 +615,8 @@ __global__ void __launch_bounds__(128) colsum_bf16_kernel(const __nv_bfloat16* _
 }
 
 __device__ __forceinline__ long long sel_row(long long r, const int64_t* idx, int n_sel, int L_src, int row_offset) {
-  const long long b = r / n_sel, j = r % n_sel;
-  return b * L_src + (idx ? idx[r] : (row_offset + j));
+  const uint32_t b = uint32_t(r) / uint32_t(n_sel), j = uint32_t(r) - b * uint32_t(n_sel);  // B * n_sel is an int
+  return (long long)b * L_src + (idx ? __ldg(idx + r) : (long long)(row_offset + j));
 }
 
 __global__ void __launch_bounds__(256) gather_rows_bf16_kernel(const float* __restrict__ src,
@@ -604,11 +626,14 @@ __global__ void __launch_bounds__(256) gather_rows_bf16_kernel(const float* __re
   pdl_trigger();
   pdl_wait();
   const int D4 = D >> 2;
-  const long long n = (long long)B * n_sel * D4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int d = int(i % D4) * 4;
-    const long long r = i / D4;
-    const float4 v = *reinterpret_cast<const float4*>(src + sel_row(r, idx, n_sel, L_src, row_offset) * D + d);
+  const long long n = (long long)B * n_sel * D4, stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  RowWalk w(i0, stride, D4, n_sel);
+  for (long long i = i0; i < n; i += stride, w.next()) {
+    const int d = w.d4 * 4;
+    const long long r = (long long)w.b * n_sel + w.j;
+    const long long srow = (long long)w.b * L_src + (idx ? idx[r] : (long long)(row_offset + w.j));
+    const float4 v = *reinterpret_cast<const float4*>(src + srow * D + d);
     *reinterpret_cast<uint2*>(out + r * D + d) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
   }
 }
@@ -620,11 +645,13 @@ __global__ void __launch_bounds__(256) zero_rows_kernel(float* __restrict__ dst,
   pdl_trigger();
   pdl_wait();
   const int D4 = D >> 2;
-  const long long n = (long long)B * n_sel * D4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int d = int(i % D4) * 4;
-    const long long r = i / D4;
-    const long long row = (r / n_sel) * L_src + idx[r];
+  const long long n = (long long)B * n_sel * D4, stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  RowWalk w(i0, stride, D4, n_sel);
+  for (long long i = i0; i < n; i += stride, w.next()) {
+    const int d = w.d4 * 4;
+    const long long r = (long long)w.b * n_sel + w.j;
+    const long long row = (long long)w.b * L_src + idx[r];
     *reinterpret_cast<float4*>(dst + row * D + d) = make_float4(0.f, 0.f, 0.f, 0.f);
     if (dst_bf16) *reinterpret_cast<uint2*>(dst_bf16 + row * D + d) = make_uint2(0u, 0u);
   }
@@ -645,14 +672,35 @@ __global__ void __launch_bounds__(256) colsum_rows_f32_kernel(const float* __res
   float4 a[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const long long nrows = (long long)B * n_sel;
-  for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < nrows; r += (long long)gridDim.x * wpb) {
-    const float* row = src + sel_row(r, idx, n_sel, L_src, row_offset) * D;
+  const long long nrows = (long long)B * n_sel, stride = (long long)gridDim.x * wpb;
+  constexpr int RB = 4;  // rows in flight per warp: the index loads, then the row loads, are issued back to back
+  for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < nrows; r += RB * stride) {
+    // rows past the end are clamped to a valid row and weighted 0, so that every load is unconditional and the
+    // compiler keeps all RB index loads, then all RB row loads, in flight together
+    long long rows_[RB];
+    float wt[RB];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int c = 128 * j + 4 * lane;
-      if (c < D) { const float4 v = *reinterpret_cast<const float4*>(row + c); a[j].x += v.x; a[j].y += v.y; a[j].z += v.z; a[j].w += v.w; }
+    for (int k = 0; k < RB; ++k) {
+      const long long rk = r + k * stride;
+      wt[k] = rk < nrows ? 1.f : 0.f;
+      rows_[k] = sel_row(rk < nrows ? rk : r, idx, n_sel, L_src, row_offset);
     }
+    __syncwarp();  // scheduling fence: without it nvcc re-serialises index load -> row load -> add per row
+    float4 v[RB][NV];
+#pragma unroll
+    for (int k = 0; k < RB; ++k)
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c = 128 * j + 4 * lane;
+        v[k][j] = *reinterpret_cast<const float4*>(src + rows_[k] * D + (c < D ? c : 0));
+      }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < RB; ++k)
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        a[j].x += wt[k] * v[k][j].x; a[j].y += wt[k] * v[k][j].y; a[j].z += wt[k] * v[k][j].z; a[j].w += wt[k] * v[k][j].w;
+      }
   }
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
@@ -926,7 +974,7 @@ extern "C" int mae_colsum_rows_f32(const float* src, const int64_t* idx, int B, 
   if (!src || !out) return MAE_ERR_NULL;
   if (D > 1024 || (D % 4)) return MAE_ERR_SHAPE;
   const long long nrows = (long long)B * n_sel;
-  const dim3 grid(grid_for(nrows, 8, 148 * 4)), block(256);
+  const dim3 grid(grid_for(nrows, 8 * 4, 148 * 8)), block(256);
   if (D <= 256) mae_launch(colsum_rows_f32_kernel<2>, grid, block, 0, stream, src, idx, B, n_sel, L_src, row_offset, D, out);
   else if (D <= 512) mae_launch(colsum_rows_f32_kernel<4>, grid, block, 0, stream, src, idx, B, n_sel, L_src, row_offset, D, out);
   else mae_launch(colsum_rows_f32_kernel<8>, grid, block, 0, stream, src, idx, B, n_sel, L_src, row_offset, D, out);
