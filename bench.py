@@ -218,11 +218,14 @@ def kernel_breakdown(trainer, images, noise, pk):
         setattr(lib_calls, name, t)
     was_distributed = trainer.distributed
     trainer.distributed = False  # rank-0-only diagnostic step: it must not enter a collective
+    was_side = trainer.engine.wgrad_side_stream
+    trainer.engine.wgrad_side_stream = False  # per-call events need every launch on the timed stream
     try:
         trainer.train_step(images, noise)
         torch.cuda.synchronize()
     finally:
         trainer.distributed = was_distributed
+        trainer.engine.wgrad_side_stream = was_side
         for name, fn in orig.items():
             setattr(lib_calls, name, fn)
     fam = {}

@@ -188,3 +188,26 @@ def test_vit_b16_stress_config_parity():
     m.engine.clip_adamw(mod_lr)
     torch.cuda.synchronize()
     assert torch.isfinite(m.encoder.vit.blocks[0].attn.qkv.weight).all()
+
+
+def test_wgrad_side_stream_matches_single_stream():
+    """The weight-gradient GEMMs run on a second stream by default (MAE_WGRAD_STREAM=0 turns it off).  Same weights,
+    images and noise through both schedules: every gradient tensor must agree up to the order of the fp32 atomics, also
+    when backward runs several times back to back (buffer-reuse hazards between the two streams would show up here)."""
+    _, m = make_pair()
+    eng = m.engine
+    torch.manual_seed(5)
+    images = torch.randn(64, 3, 96, 96, device="cuda")
+    noise = torch.rand(64, 145, device="cuda")
+    got = {}
+    for side in (False, True):
+        eng.wgrad_side_stream = side
+        for _ in range(3):
+            m.forward_loss(images, noise=noise)
+            eng.backward()
+        torch.cuda.synchronize()
+        got[side] = {n: g.detach().float().clone() for n, g in eng.named_grads().items()}
+    assert eng._side is not None and not eng._wg_pending  # the second stream was used and fully joined
+    for n, a in got[False].items():
+        b = got[True][n]
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6 + 1e-5 * a.abs().max().item()), (n, max_err(a, b))
