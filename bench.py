@@ -153,6 +153,12 @@ def algorithmic_cost(name, a):
     if name == "mae_layernorm_bwd":
         rows, D = a[9], a[10]
         return rows * D * (2.0 + 4 + 4 * nz(a[5]) + 4 + 2 * nz(a[12])) + rows * 8.0, 0.0, f"rows={rows} D={D}"
+    if name == "mae_layernorm_fwd_add":
+        rows, D = a[7], a[8]
+        return rows * D * 12.0 + rows * 8.0, 0.0, f"rows={rows} D={D} (+delta)"
+    if name == "mae_layernorm_bwd_scatter":
+        rows, D = a[9], a[10]
+        return rows * D * (2.0 + 4 + 4 + 4 + 2 * nz(a[12])) + rows * 8.0, 0.0, f"rows={rows} D={D} (scatter)"
     if name == "mae_random_token_mask":
         B, L = a[1], a[2]
         return B * L * 12.0, 0.0, f"B={B} L={L}"

@@ -80,6 +80,21 @@ int mae_layernorm_bwd(const void* g_bf16, const float* x, const float* mean, con
 /* out = epi(A[M,K] * B[N,K]^T): every nn.Linear forward (B = weight (out,in)) and every dgrad (B = weight^T)
  * of timm Block / MAEDecoderTIMM (reference src/models/mae.py:55,59,71,73).  A, B bf16; fp32 accumulation in
  * TMEM via tcgen05.mma; K % 16 == 0, N % 16 == 0. */
+/* The two LayerNorms around the masked-rows-only tail of the last decoder block (get_at_index(idx_mask) at reference
+ * src/models/mae.py:72 commuted backwards through decoder_norm, mlp and norm2 of the last block: the rows it drops are
+ * never computed).
+ * mae_layernorm_fwd_add: row r normalises  x[map(r)] + delta[r]  (delta bf16 (rows,D): the mlp.fc2 output before the
+ *   residual add, x the fp32 stream gathered like mae_layernorm_fwd); the sum is also written to x_out (rows,D) f32.
+ * mae_layernorm_bwd_scatter: mae_layernorm_bwd with the residual gradient dx_in indexed by the compact row r (rows,D)
+ *   instead of the mapped row; dx_out rows are written at the mapped rows.  D <= 256. */
+int mae_layernorm_fwd_add(const float* x, const void* delta_bf16, const float* gamma, const float* beta,
+                          const int64_t* gather_idx, int n_sel, int L_src, int rows, int D, float eps, float* x_out,
+                          void* xn_bf16, float* mean, float* rstd, mae_stream_t stream);
+int mae_layernorm_bwd_scatter(const void* g_bf16, const float* x, const float* mean, const float* rstd,
+                              const float* gamma, const float* dx_in_compact, const int64_t* gather_idx, int n_sel,
+                              int L_src, int rows, int D, float* dx_out, void* dx_out_bf16, float* dgamma,
+                              float* dbeta, mae_stream_t stream);
+
 int mae_gemm_tn(const void* A_bf16, const void* B_bf16, int M, int N, int K, int epi, const float* bias, void* out,
                 void* pre_out_bf16, const void* aux, mae_stream_t stream);
 

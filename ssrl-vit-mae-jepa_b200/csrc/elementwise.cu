@@ -172,14 +172,18 @@ __device__ __forceinline__ long long map_row(long long r, const int64_t* gather_
   return b * L_src + __ldg(gather_idx + r);
 }
 
-template <int NV, int ROWS, bool GATHER>
+// ADD: the normalised row is x[map(r)] + delta[r] (delta bf16, compact rows: a Linear output that has not been added to
+// the residual stream yet); the sum is also written to x_out[r] (fp32, compact) for the backward.
+template <int NV, int ROWS, bool GATHER, bool ADD = false>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta,
                                                            const int64_t* __restrict__ gather_idx, int n_sel,
                                                            int L_src, int rows, int D, float eps,
                                                            __nv_bfloat16* __restrict__ xn, float* __restrict__ mean,
-                                                           float* __restrict__ rstd) {
+                                                           float* __restrict__ rstd,
+                                                           const __nv_bfloat16* __restrict__ delta,
+                                                           float* __restrict__ x_out) {
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -206,6 +210,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   }
   for (long long ra = ra0; ra < rows; ra += ROWS * stride) {
     float4 v[ROWS][NV];
+    uint2 dl[ROWS][NV];
     long long rr[ROWS];
     bool ok[ROWS];
 #pragma unroll
@@ -217,8 +222,22 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         v[k][j] = make_float4(0, 0, 0, 0);
-        if (has[j]) v[k][j] = *reinterpret_cast<const float4*>(src + 128 * j + 4 * lane);
+        dl[k][j] = make_uint2(0u, 0u);
+        if (has[j]) {
+          v[k][j] = *reinterpret_cast<const float4*>(src + 128 * j + 4 * lane);
+          if (ADD) dl[k][j] = *reinterpret_cast<const uint2*>(delta + rr[k] * D + 128 * j + 4 * lane);
+        }
       }
+    }
+    if (ADD) {
+#pragma unroll
+      for (int k = 0; k < ROWS; ++k)
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          v[k][j].x += bf16_lo(dl[k][j].x); v[k][j].y += bf16_hi(dl[k][j].x);
+          v[k][j].z += bf16_lo(dl[k][j].y); v[k][j].w += bf16_hi(dl[k][j].y);
+          if (has[j] && ok[k]) *reinterpret_cast<float4*>(x_out + rr[k] * D + 128 * j + 4 * lane) = v[k][j];
+        }
     }
     if (GATHER) {
       const long long rn = ra + ROWS * stride;
@@ -260,7 +279,9 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   }
 }
 
-template <int NV, int ROWS, int MINB, bool GATHER>
+// DINC: dx_in is indexed by the compact row r (like g), not by the mapped row (the residual gradient of a gathered
+// sub-stream: the masked-rows-only tail of the last decoder block).
+template <int NV, int ROWS, int MINB, bool GATHER, bool DINC = false>
 __global__ void __launch_bounds__(256, MINB) layernorm_bwd_kernel(
     const __nv_bfloat16* __restrict__ g, const float* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dx_in,
@@ -315,7 +336,7 @@ __global__ void __launch_bounds__(256, MINB) layernorm_bwd_kernel(
         if (has[j]) {
           gg[k][j] = *reinterpret_cast<const uint2*>(g + rrow[k] * D + c);
           xv[k][j] = *reinterpret_cast<const float4*>(x + xr[k] * D + c);
-          if (dx_in) di[k][j] = *reinterpret_cast<const float4*>(dx_in + xr[k] * D + c);
+          if (dx_in) di[k][j] = *reinterpret_cast<const float4*>(dx_in + (DINC ? rrow[k] : xr[k]) * D + c);
         }
       }
     }
@@ -865,15 +886,43 @@ extern "C" int mae_layernorm_fwd(const float* x, const float* gamma, const float
   static const int bps = getenv("MAE_LN_FWD_BPS") ? atoi(getenv("MAE_LN_FWD_BPS")) : 16;
   const dim3 grid(grid_for(rows, 8, 148 * bps)), block(256);
   if (D <= 256) {
-    if (gather_idx) mae_launch(layernorm_fwd_kernel<2, 2, true>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd);
-    else mae_launch(layernorm_fwd_kernel<2, 2, false>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd);
+    if (gather_idx) mae_launch(layernorm_fwd_kernel<2, 2, true>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd, (const __nv_bfloat16*)nullptr, (float*)nullptr);
+    else mae_launch(layernorm_fwd_kernel<2, 2, false>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd, (const __nv_bfloat16*)nullptr, (float*)nullptr);
   } else if (D <= 512) {
-    if (gather_idx) mae_launch(layernorm_fwd_kernel<4, 2, true>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd);
-    else mae_launch(layernorm_fwd_kernel<4, 2, false>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd);
+    if (gather_idx) mae_launch(layernorm_fwd_kernel<4, 2, true>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd, (const __nv_bfloat16*)nullptr, (float*)nullptr);
+    else mae_launch(layernorm_fwd_kernel<4, 2, false>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd, (const __nv_bfloat16*)nullptr, (float*)nullptr);
   } else {
-    if (gather_idx) mae_launch(layernorm_fwd_kernel<8, 1, true>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd);
-    else mae_launch(layernorm_fwd_kernel<8, 1, false>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd);
+    if (gather_idx) mae_launch(layernorm_fwd_kernel<8, 1, true>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd, (const __nv_bfloat16*)nullptr, (float*)nullptr);
+    else mae_launch(layernorm_fwd_kernel<8, 1, false>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd, (const __nv_bfloat16*)nullptr, (float*)nullptr);
   }
+  return MAE_CHECK_LAUNCH();
+}
+
+extern "C" int mae_layernorm_fwd_add(const float* x, const void* delta, const float* gamma, const float* beta,
+                                     const int64_t* gather_idx, int n_sel, int L_src, int rows, int D, float eps,
+                                     float* x_out, void* xn, float* mean, float* rstd, cudaStream_t stream) {
+  if (rows <= 0) return MAE_OK;
+  if (!x || !delta || !gamma || !beta || !x_out || !xn || !mean || !rstd) return MAE_ERR_NULL;
+  if (D > 256 || (D % 4) || (gather_idx && (n_sel <= 0 || L_src <= 0))) return MAE_ERR_SHAPE;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(xn);
+  const __nv_bfloat16* dl = reinterpret_cast<const __nv_bfloat16*>(delta);
+  const dim3 grid(grid_for(rows, 8, 148 * 16)), block(256);
+  if (gather_idx) mae_launch(layernorm_fwd_kernel<2, 2, true, true>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd, dl, x_out);
+  else mae_launch(layernorm_fwd_kernel<2, 2, false, true>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd, dl, x_out);
+  return MAE_CHECK_LAUNCH();
+}
+
+extern "C" int mae_layernorm_bwd_scatter(const void* g, const float* x, const float* mean, const float* rstd,
+                                         const float* gamma, const float* dx_in_compact, const int64_t* gather_idx,
+                                         int n_sel, int L_src, int rows, int D, float* dx_out, void* dx_out_bf16,
+                                         float* dgamma, float* dbeta, cudaStream_t stream) {
+  if (rows <= 0) return MAE_OK;
+  if (!g || !x || !mean || !rstd || !gamma || !dx_in_compact || !gather_idx || !dx_out || !dgamma || !dbeta) return MAE_ERR_NULL;
+  if (D > 256 || (D % 4) || n_sel <= 0 || L_src <= 0) return MAE_ERR_SHAPE;
+  const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(g);
+  __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(dx_out_bf16);
+  const dim3 grid(grid_for(rows, 8, 148 * 6)), block(256);
+  mae_launch(layernorm_bwd_kernel<2, 2, 3, true, true>, grid, block, 0, stream, gp, x, mean, rstd, gamma, dx_in_compact, gather_idx, n_sel, L_src, rows, D, dx_out, ob, dgamma, dbeta);
   return MAE_CHECK_LAUNCH();
 }
 

@@ -191,6 +191,9 @@ class MAEEngine:
         # weight-gradient GEMMs run on a second stream: they only feed the optimizer, so they trail the dgrad chain and fill
         # its fill / drain bubbles (measured 8.50 -> 8.23 ms/step); MAE_WGRAD_STREAM=0 keeps everything on one stream
         self.wgrad_side_stream = os.environ.get("MAE_WGRAD_STREAM", "1") != "0"
+        # masked-rows-only tail of the last decoder block: decoder_norm / decoder_pred only read the idx_mask rows, so the
+        # block's norm2 -> mlp -> residual (and their backward) run on those rows alone (MAE_MASKED_TAIL=0: all rows)
+        self.masked_tail = os.environ.get("MAE_MASKED_TAIL", "1") != "0"
         self._side: Optional[torch.cuda.Stream] = None
         self._wg_pending: Dict[int, torch.cuda.Event] = {}
         self._wg_events: List[torch.cuda.Event] = []
@@ -340,6 +343,7 @@ class MAEEngine:
         ws["dec"] = [block_ws(Md, Dd, b.heads) for b in self.dec_blocks]
         ws["x_dec"] = e((Md, Dd), f32)
         ws["xnd"], ws["meand"], ws["rstdd"] = e((Mm, Dd), bf), e((Mm,), f32), e((Mm,), f32)
+        ws["dlt"] = e((Mm, Dd), bf)  # last block's mlp.fc2 output on the masked rows (masked_tail)
         ws["pred"] = e((B, Lm, pd), bf)
         ws["dpred"] = e((B, Lm, pd), bf)
         ws["loss"] = torch.zeros(1, dtype=f32, device=device)
@@ -358,7 +362,14 @@ class MAEEngine:
         self.dims = dict(B=B, L=L, Lk=Lk, Lm=Lm, De=De, Dd=Dd, pd=pd, Me=Me, Md=Md, Mm=Mm)
 
     # ---------------- forward pieces ----------------
-    def _block_fwd(self, w: _BlockW, s: Dict[str, torch.Tensor], x_out: torch.Tensor, M: int, B: int, L: int, st: int):
+    def _use_masked_tail(self) -> bool:
+        return self.masked_tail and len(self.dec_blocks) > 0 and self.dims["Dd"] <= 256
+
+    def _block_fwd(self, w: _BlockW, s: Dict[str, torch.Tensor], x_out: Optional[torch.Tensor], M: int, B: int, L: int,
+                   st: int, tail: bool = False):
+        """One pre-norm transformer block.  ``tail``: the last decoder block; norm2 and the MLP run on the idx_mask rows
+        only (compact, Mm rows) and mlp.fc2 leaves its bf16 output in ``ws["dlt"]`` without the residual add, which
+        :meth:`_decode` folds into decoder_norm (``mae_layernorm_fwd_add``)."""
         D, H, hd = w.dim, w.heads, w.hd
         calls.mae_layernorm_fwd(_ptr(s["x_in"]), self.pf(w.n1w), self.pf(w.n1b), None, 0, 0, M, D, LN_EPS,
                                 _ptr(s["xn1"]), _ptr(s["mean1"]), _ptr(s["rstd1"]), st)
@@ -367,6 +378,16 @@ class MAEEngine:
         calls.mae_attention_fwd(_ptr(s["qkv"]), B, L, H, hd, _ptr(s["att"]), _ptr(s["lse"]), st)
         calls.mae_gemm_tn(_ptr(s["att"]), self.pw(w.projw), M, D, D, EPI_RESID_F32, self.pf(w.projb),
                           _ptr(s["x_mid"]), None, _ptr(s["x_in"]), st)
+        if tail:
+            ws, d = self.ws, self.dims
+            Mt = d["Mm"]
+            calls.mae_layernorm_fwd(_ptr(s["x_mid"]), self.pf(w.n2w), self.pf(w.n2b), _ptr(ws["idx_mask"]), d["Lm"], L, Mt,
+                                    D, LN_EPS, _ptr(s["xn2"]), _ptr(s["mean2"]), _ptr(s["rstd2"]), st)
+            calls.mae_gemm_tn(_ptr(s["xn2"]), self.pw(w.fc1w), Mt, 4 * D, D, EPI_GELU_BF16, self.pf(w.fc1b), _ptr(s["h"]),
+                              _ptr(s["pre"]), None, st)
+            calls.mae_gemm_tn(_ptr(s["h"]), self.pw(w.fc2w), Mt, D, 4 * D, EPI_BF16, self.pf(w.fc2b), _ptr(ws["dlt"]),
+                              None, None, st)
+            return
         calls.mae_layernorm_fwd(_ptr(s["x_mid"]), self.pf(w.n2w), self.pf(w.n2b), None, 0, 0, M, D, LN_EPS,
                                 _ptr(s["xn2"]), _ptr(s["mean2"]), _ptr(s["rstd2"]), st)
         calls.mae_gemm_tn(_ptr(s["xn2"]), self.pw(w.fc1w), M, 4 * D, D, EPI_GELU_BF16, self.pf(w.fc1b), _ptr(s["h"]),
@@ -466,12 +487,21 @@ class MAEEngine:
         calls.mae_scatter_decoder_tokens(_ptr(ws["emb"]), self.pf(o("decoder.mask_token")),
                                          self.pf(o("decoder.decoder_pos_embed")), _ptr(ws["idx_keep"]),
                                          _ptr(ws["idx_mask"]), B, L, Lk, Dd, _ptr(x0), st)
+        tail = self._use_masked_tail()
+        n_dec = len(self.dec_blocks)
         for i, w in enumerate(self.dec_blocks):
-            x_out = ws["dec"][i + 1]["x_in"] if i + 1 < len(self.dec_blocks) else ws["x_dec"]
-            self._block_fwd(w, ws["dec"][i], x_out, d["Md"], B, L, st)
-        calls.mae_layernorm_fwd(_ptr(ws["x_dec"]), self.pf(o("decoder.decoder_norm.weight")),
-                                self.pf(o("decoder.decoder_norm.bias")), _ptr(ws["idx_mask"]), Lm, L, d["Mm"], Dd, LN_EPS,
-                                _ptr(ws["xnd"]), _ptr(ws["meand"]), _ptr(ws["rstdd"]), st)
+            x_out = ws["dec"][i + 1]["x_in"] if i + 1 < n_dec else ws["x_dec"]
+            self._block_fwd(w, ws["dec"][i], x_out, d["Md"], B, L, st, tail=tail and i == n_dec - 1)
+        if tail:
+            # decoder_norm over  x_mid[idx_mask rows] + mlp output ; the summed rows (compact) are kept in x_dec for the backward
+            calls.mae_layernorm_fwd_add(_ptr(ws["dec"][-1]["x_mid"]), _ptr(ws["dlt"]),
+                                        self.pf(o("decoder.decoder_norm.weight")), self.pf(o("decoder.decoder_norm.bias")),
+                                        _ptr(ws["idx_mask"]), Lm, L, d["Mm"], Dd, LN_EPS, _ptr(ws["x_dec"]),
+                                        _ptr(ws["xnd"]), _ptr(ws["meand"]), _ptr(ws["rstdd"]), st)
+        else:
+            calls.mae_layernorm_fwd(_ptr(ws["x_dec"]), self.pf(o("decoder.decoder_norm.weight")),
+                                    self.pf(o("decoder.decoder_norm.bias")), _ptr(ws["idx_mask"]), Lm, L, d["Mm"], Dd, LN_EPS,
+                                    _ptr(ws["xnd"]), _ptr(ws["meand"]), _ptr(ws["rstdd"]), st)
         calls.mae_gemm_tn(_ptr(ws["xnd"]), self.pw(o("decoder.decoder_pred.weight")), d["Mm"], d["pd"], Dd, EPI_BF16,
                           self.pf(o("decoder.decoder_pred.bias")), _ptr(ws["pred"]), None, None, st)
 
@@ -520,21 +550,30 @@ class MAEEngine:
             self._wg_pending[dy] = done  # the side stream is in-order: a later event also covers earlier readers of dy
 
     def _block_bwd(self, w: _BlockW, s: Dict[str, torch.Tensor], dx: torch.Tensor, dxb: torch.Tensor,
-                   dx_out: torch.Tensor, dxb_out: torch.Tensor, M: int, B: int, L: int, st: int) -> None:
-        """dx/dxb: fp32 / bf16 gradient w.r.t. the block output; writes the gradient w.r.t. its input."""
-        ws = self.ws
+                   dx_out: torch.Tensor, dxb_out: torch.Tensor, M: int, B: int, L: int, st: int, tail: bool = False) -> None:
+        """dx/dxb: fp32 / bf16 gradient w.r.t. the block output; writes the gradient w.r.t. its input.  ``tail`` (see
+        :meth:`_block_fwd`): dx/dxb hold the Mm masked rows only (compact); norm2's backward scatters them back."""
+        ws, d = self.ws, self.dims
         D, H, hd = w.dim, w.heads, w.hd
+        Mt = d["Mm"] if tail else M
         # mlp.fc2
-        self._linear_bwd_w(_ptr(dxb), D, _ptr(s["h"]), 4 * D, M, w.fc2w, w.fc2b, st)
+        self._linear_bwd_w(_ptr(dxb), D, _ptr(s["h"]), 4 * D, Mt, w.fc2w, w.fc2b, st)
         self._wg_wait(_ptr(ws["dh"]))
-        calls.mae_gemm_tn(_ptr(dxb), self.pwt(w.fc2w), M, 4 * D, D, EPI_DGELU_BF16, None, _ptr(ws["dh"]), None,
+        calls.mae_gemm_tn(_ptr(dxb), self.pwt(w.fc2w), Mt, 4 * D, D, EPI_DGELU_BF16, None, _ptr(ws["dh"]), None,
                           _ptr(s["pre"]), st)
         # mlp.fc1 + norm2
-        self._linear_bwd_w(_ptr(ws["dh"]), 4 * D, _ptr(s["xn2"]), D, M, w.fc1w, w.fc1b, st)
-        calls.mae_gemm_tn(_ptr(ws["dh"]), self.pwt(w.fc1w), M, D, 4 * D, EPI_BF16, None, _ptr(ws["g"]), None, None, st)
+        self._linear_bwd_w(_ptr(ws["dh"]), 4 * D, _ptr(s["xn2"]), D, Mt, w.fc1w, w.fc1b, st)
+        calls.mae_gemm_tn(_ptr(ws["dh"]), self.pwt(w.fc1w), Mt, D, 4 * D, EPI_BF16, None, _ptr(ws["g"]), None, None, st)
         self._wg_wait(_ptr(dxb_out))
-        calls.mae_layernorm_bwd(_ptr(ws["g"]), _ptr(s["x_mid"]), _ptr(s["mean2"]), _ptr(s["rstd2"]), self.pf(w.n2w),
-                                _ptr(dx), None, 0, 0, M, D, _ptr(dx_out), _ptr(dxb_out), self.pg(w.n2w), self.pg(w.n2b), st)
+        if tail:
+            # the kept rows get no gradient through the MLP; the masked rows: LN'(g) + the (compact) residual gradient
+            calls.mae_zero_rows(_ptr(dx_out), _ptr(dxb_out), _ptr(ws["idx_keep"]), B, d["Lk"], L, D, st)
+            calls.mae_layernorm_bwd_scatter(_ptr(ws["g"]), _ptr(s["x_mid"]), _ptr(s["mean2"]), _ptr(s["rstd2"]),
+                                            self.pf(w.n2w), _ptr(dx), _ptr(ws["idx_mask"]), d["Lm"], L, Mt, D, _ptr(dx_out),
+                                            _ptr(dxb_out), self.pg(w.n2w), self.pg(w.n2b), st)
+        else:
+            calls.mae_layernorm_bwd(_ptr(ws["g"]), _ptr(s["x_mid"]), _ptr(s["mean2"]), _ptr(s["rstd2"]), self.pf(w.n2w),
+                                    _ptr(dx), None, 0, 0, M, D, _ptr(dx_out), _ptr(dxb_out), self.pg(w.n2w), self.pg(w.n2b), st)
         # attn.proj
         self._linear_bwd_w(_ptr(dxb_out), D, _ptr(s["att"]), D, M, w.projw, w.projb, st)
         calls.mae_gemm_tn(_ptr(dxb_out), self.pwt(w.projw), M, D, D, EPI_BF16, None, _ptr(ws["datt"]), None, None, st)
@@ -571,15 +610,25 @@ class MAEEngine:
                            o("decoder.decoder_pred.bias"), st)
         calls.mae_gemm_tn(_ptr(dpred), self.pwt(o("decoder.decoder_pred.weight")), Mm, Dd, pd, EPI_BF16, None,
                           _ptr(ws["g"]), None, None, st)
-        # only the masked rows receive a gradient from the prediction head: zero the kept rows, LN-bwd writes the rest
-        calls.mae_zero_rows(_ptr(dx_a), _ptr(dxb_a), _ptr(ws["idx_keep"]), B, Lk, L, Dd, st)
-        calls.mae_layernorm_bwd(_ptr(ws["g"]), _ptr(ws["x_dec"]), _ptr(ws["meand"]), _ptr(ws["rstdd"]),
-                                self.pf(o("decoder.decoder_norm.weight")), None, _ptr(ws["idx_mask"]), Lm, L, Mm, Dd,
-                                _ptr(dx_a), _ptr(dxb_a), self.pg(o("decoder.decoder_norm.weight")),
-                                self.pg(o("decoder.decoder_norm.bias")), st)
+        tail = self._use_masked_tail()
+        if tail:
+            # decoder_norm saw the compact masked rows (x_dec holds their pre-norm values): compact gradient
+            calls.mae_layernorm_bwd(_ptr(ws["g"]), _ptr(ws["x_dec"]), _ptr(ws["meand"]), _ptr(ws["rstdd"]),
+                                    self.pf(o("decoder.decoder_norm.weight")), None, None, 0, 0, Mm, Dd,
+                                    _ptr(dx_a), _ptr(dxb_a), self.pg(o("decoder.decoder_norm.weight")),
+                                    self.pg(o("decoder.decoder_norm.bias")), st)
+        else:
+            # only the masked rows receive a gradient from the prediction head: zero the kept rows, LN-bwd writes the rest
+            calls.mae_zero_rows(_ptr(dx_a), _ptr(dxb_a), _ptr(ws["idx_keep"]), B, Lk, L, Dd, st)
+            calls.mae_layernorm_bwd(_ptr(ws["g"]), _ptr(ws["x_dec"]), _ptr(ws["meand"]), _ptr(ws["rstdd"]),
+                                    self.pf(o("decoder.decoder_norm.weight")), None, _ptr(ws["idx_mask"]), Lm, L, Mm, Dd,
+                                    _ptr(dx_a), _ptr(dxb_a), self.pg(o("decoder.decoder_norm.weight")),
+                                    self.pg(o("decoder.decoder_norm.bias")), st)
         cur, curb, nxt, nxtb = dx_a, dxb_a, dx_b, dxb_b
-        for i in reversed(range(len(self.dec_blocks))):
-            self._block_bwd(self.dec_blocks[i], ws["dec"][i], cur, curb, nxt, nxtb, Md, B, L, st)
+        n_dec = len(self.dec_blocks)
+        for i in reversed(range(n_dec)):
+            self._block_bwd(self.dec_blocks[i], ws["dec"][i], cur, curb, nxt, nxtb, Md, B, L, st,
+                            tail=tail and i == n_dec - 1)
             cur, curb, nxt, nxtb = nxt, nxtb, cur, curb
         # decoder input = scatter(embed) / mask_token, + frozen pos
         calls.mae_colsum_rows_f32(_ptr(cur), _ptr(ws["idx_mask"]), B, Lm, L, 0, Dd, self.pg(o("decoder.mask_token")), st)

@@ -131,6 +131,53 @@ def test_layernorm_gather_variants():
     assert max_err(dx.view(B, L, D), xr.grad) < 1e-4
 
 
+def test_layernorm_masked_tail_variants():
+    """mae_layernorm_fwd_add (gathered x + compact bf16 delta -> LN, summed rows kept) and mae_layernorm_bwd_scatter
+    (compact residual gradient, output scattered to the mapped rows): the two norms around the masked-rows-only tail of
+    the last decoder block."""
+    B, L, n_sel, D = 5, 145, 109, 192
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B * L, D, generator=g).to(dev)
+    idx = torch.stack([torch.randperm(L, generator=g)[:n_sel].sort().values for _ in range(B)]).to(dev)
+    rows = B * n_sel
+    delta = bf(torch.randn(rows, D, generator=g)).to(dev)
+    gamma, beta = (torch.rand(D, generator=g) + 0.5).to(dev), torch.randn(D, generator=g).to(dev)
+    xn = torch.empty(rows, D, dtype=torch.bfloat16, device=dev)
+    x_out = torch.empty(rows, D, device=dev)
+    mean, rstd = torch.empty(rows, device=dev), torch.empty(rows, device=dev)
+    calls.mae_layernorm_fwd_add(p(x), p(delta), p(gamma), p(beta), p(idx), n_sel, L, rows, D, 1e-6, p(x_out), p(xn), p(mean),
+                                p(rstd), stream())
+    sel = torch.gather(x.view(B, L, D), 1, idx.unsqueeze(-1).expand(-1, -1, D)).reshape(rows, D) + delta.float()
+    assert torch.equal(x_out, sel)
+    ref = F.layer_norm(sel, (D,), gamma, beta, 1e-6)
+    assert max_err(xn, ref) <= 2 ** -7 * ref.abs().max().item() + 1e-6
+    assert max_err(mean, sel.mean(1)) < 1e-5
+    # non-gathered flavour (x already compact)
+    x2 = torch.randn(rows, D, generator=g).to(dev)
+    calls.mae_layernorm_fwd_add(p(x2), p(delta), p(gamma), p(beta), None, 0, 0, rows, D, 1e-6, p(x_out), p(xn), p(mean),
+                                p(rstd), stream())
+    assert torch.equal(x_out, x2 + delta.float())
+    # backward: compact dy and compact residual gradient, x gathered, dx scattered to the mapped rows
+    calls.mae_layernorm_fwd(p(x), p(gamma), p(beta), p(idx), n_sel, L, rows, D, 1e-6, p(xn), p(mean), p(rstd), stream())
+    dy = bf(torch.randn(rows, D, generator=g)).to(dev)
+    din = torch.randn(rows, D, generator=g).to(dev)
+    dx = torch.full((B * L, D), 7.0, device=dev)
+    dxb = torch.full((B * L, D), 7.0, dtype=torch.bfloat16, device=dev)
+    dg, db = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+    calls.mae_layernorm_bwd_scatter(p(dy), p(x), p(mean), p(rstd), p(gamma), p(din), p(idx), n_sel, L, rows, D, p(dx), p(dxb),
+                                    p(dg), p(db), stream())
+    xr = x.clone().view(B, L, D).requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    xs = torch.gather(xr, 1, idx.unsqueeze(-1).expand(-1, -1, D))
+    F.layer_norm(xs, (D,), gr, br, 1e-6).backward(dy.float().view(B, n_sel, D))
+    want = torch.full((B, L, D), 7.0, device=dev)  # rows that are not selected stay untouched
+    want.scatter_(1, idx.unsqueeze(-1).expand(-1, -1, D),
+                  torch.gather(xr.grad, 1, idx.unsqueeze(-1).expand(-1, -1, D)) + din.view(B, n_sel, D))
+    assert max_err(dx.view(B, L, D), want) < 1e-4
+    assert torch.equal(dxb, bf(dx))
+    assert rel_err(dg, gr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
+
+
 GEMM_SHAPES = [(128, 64, 64), (128, 144, 144), (300, 432, 144), (1000, 576, 192), (777, 144, 576), (517, 192, 768),
                (128, 768, 192), (2500, 192, 192), (64, 144, 192), (40000, 576, 192)]
 
