@@ -194,6 +194,9 @@ class MAEEngine:
         # masked-rows-only tail of the last decoder block: decoder_norm / decoder_pred only read the idx_mask rows, so the
         # block's norm2 -> mlp -> residual (and their backward) run on those rows alone (MAE_MASKED_TAIL=0: all rows)
         self.masked_tail = os.environ.get("MAE_MASKED_TAIL", "1") != "0"
+        # the small optimizer-only launches (W^T refresh, mask-token column sum, kept-row clearing) also on the side stream
+        self.side_extras = os.environ.get("MAE_SIDE_EXTRAS", "1") != "0"
+        self._side_skip = False
         self._side: Optional[torch.cuda.Stream] = None
         self._wg_pending: Dict[int, torch.cuda.Event] = {}
         self._wg_events: List[torch.cuda.Event] = []
@@ -291,6 +294,7 @@ class MAEEngine:
         """bf16 copies of W (same layout) and W^T; skipped when the fused optimizer already refreshed them."""
         if self._shadow_version == self.flat._version:
             return
+        self._wg_wait(self.flat_bf16_t.data_ptr())  # a W^T refresh still running on the side stream goes first
         calls.mae_cast_bf16(self.flat.data_ptr(), self.flat_bf16.data_ptr(), self.n_total, stream)
         calls.mae_transpose_cast_bf16(self.flat.data_ptr(), self.flat_bf16_t.data_ptr(), self.t_table.data_ptr(),
                                       self.t_table.shape[0], self.t_max_rows, self.t_max_cols, stream)
@@ -460,7 +464,9 @@ class MAEEngine:
         ws, d = self.ws, self.dims
         B, Lk, De, pd, Me = d["B"], d["Lk"], d["De"], d["pd"], d["Me"]
         o, ep = self._o, self.EP
+        self._wg_wait(self.flat_bf16_t.data_ptr())
         self._wg_wait(_ptr(nxtb))
+        self._wg_wait(_ptr(nxt))
         calls.mae_layernorm_bwd(g_ptr, _ptr(ws["x_enc"]), _ptr(ws["meanf"]), _ptr(ws["rstdf"]),
                                 self.pf(o(ep + "norm.weight")), None, None, 0, 0, Me, De, _ptr(nxt), _ptr(nxtb),
                                 self.pg(o(ep + "norm.weight")), self.pg(o(ep + "norm.bias")), st)
@@ -528,26 +534,40 @@ class MAEEngine:
             self._wg_pending.clear()
         self._wg_next_event = 0
 
+    def _side_begin(self, st: int, extra: bool = False) -> int:
+        """Stream for work that only feeds the optimizer: the side stream (ordered behind everything enqueued on the main
+        stream so far), or ``st`` itself when the two-stream schedule is off."""
+        if not self.wgrad_side_stream or (extra and not self.side_extras):
+            self._side_skip = True
+            return st
+        self._side_skip = False
+        dev = self.flat.device
+        if self._side is None:
+            self._side = torch.cuda.Stream(dev, priority=int(os.environ.get("MAE_WGRAD_PRIO", "0")))
+        ready = self._wg_event()
+        ready.record(torch.cuda.current_stream(dev))
+        self._side.wait_event(ready)
+        return self._side.cuda_stream
+
+    def _side_end(self, *buf_ptrs: int) -> None:
+        """Marks the buffers the side-stream launch just enqueued still reads (or writes): :meth:`_wg_wait` on one of them
+        orders the main stream behind it.  The side stream is in-order, so a later event also covers earlier launches."""
+        if not self.wgrad_side_stream or self._side_skip:
+            return
+        done = self._wg_event()
+        done.record(self._side)
+        for ptr in buf_ptrs:
+            self._wg_pending[ptr] = done
+
     def _linear_bwd_w(self, dy: int, n_out: int, x: int, n_in: int, M: int, w_off: int, b_off: int, st: int) -> None:
         """dW (n_out, n_in) += dY^T X and db += colsum(dY), bias gradient fused into the same launch.  The wider
         operand rides the MMA M axis (chunks of 128), the narrower one the MMA N axis (chunks of <= 256)."""
-        done = None
-        if self.wgrad_side_stream:
-            dev = self.flat.device
-            if self._side is None:
-                self._side = torch.cuda.Stream(dev, priority=int(os.environ.get("MAE_WGRAD_PRIO", "0")))
-            ready = self._wg_event()
-            ready.record(torch.cuda.current_stream(dev))  # dY (and the zeroed gradient buffer) are complete here
-            self._side.wait_event(ready)
-            st = self._side.cuda_stream
-            done = self._wg_event()
+        st = self._side_begin(st)
         if n_in <= n_out:
             calls.mae_gemm_wgrad(dy, n_out, x, n_in, M, self.pg(w_off), n_in, 1, self.pg(b_off), 0, st)
         else:
             calls.mae_gemm_wgrad(x, n_in, dy, n_out, M, self.pg(w_off), 1, n_in, self.pg(b_off), 1, st)
-        if done is not None:
-            done.record(self._side)
-            self._wg_pending[dy] = done  # the side stream is in-order: a later event also covers earlier readers of dy
+        self._side_end(dy)
 
     def _block_bwd(self, w: _BlockW, s: Dict[str, torch.Tensor], dx: torch.Tensor, dxb: torch.Tensor,
                    dx_out: torch.Tensor, dxb_out: torch.Tensor, M: int, B: int, L: int, st: int, tail: bool = False) -> None:
@@ -565,9 +585,9 @@ class MAEEngine:
         self._linear_bwd_w(_ptr(ws["dh"]), 4 * D, _ptr(s["xn2"]), D, Mt, w.fc1w, w.fc1b, st)
         calls.mae_gemm_tn(_ptr(ws["dh"]), self.pwt(w.fc1w), Mt, D, 4 * D, EPI_BF16, None, _ptr(ws["g"]), None, None, st)
         self._wg_wait(_ptr(dxb_out))
+        self._wg_wait(_ptr(dx_out))
         if tail:
-            # the kept rows get no gradient through the MLP; the masked rows: LN'(g) + the (compact) residual gradient
-            calls.mae_zero_rows(_ptr(dx_out), _ptr(dxb_out), _ptr(ws["idx_keep"]), B, d["Lk"], L, D, st)
+            # kept rows were zeroed by backward() (side stream); masked rows: LN'(g) + the (compact) residual gradient
             calls.mae_layernorm_bwd_scatter(_ptr(ws["g"]), _ptr(s["x_mid"]), _ptr(s["mean2"]), _ptr(s["rstd2"]),
                                             self.pf(w.n2w), _ptr(dx), _ptr(ws["idx_mask"]), d["Lm"], L, Mt, D, _ptr(dx_out),
                                             _ptr(dxb_out), self.pg(w.n2w), self.pg(w.n2b), st)
@@ -603,6 +623,7 @@ class MAEEngine:
             dpred = ws["dpred"]
         else:
             dpred = dpred.to(torch.bfloat16).contiguous()
+        self._wg_wait(self.flat_bf16_t.data_ptr())  # W^T refresh launched by clip_adamw on the side stream
         self.grads.zero_()
         dx_a, dx_b, dxb_a, dxb_b = ws["dx_a"], ws["dx_b"], ws["dxb_a"], ws["dxb_b"]
         # decoder_pred + decoder_norm (gradient lands only on the masked rows of the decoder stream)
@@ -612,6 +633,11 @@ class MAEEngine:
                           _ptr(ws["g"]), None, None, st)
         tail = self._use_masked_tail()
         if tail:
+            # kept rows of the last block's mid-stream gradient are zero (no gradient through its MLP): cleared early, off
+            # the critical path; norm2's backward (which fills the masked rows) waits for it through dxb_b
+            st2 = self._side_begin(st, extra=True)
+            calls.mae_zero_rows(_ptr(dx_b), _ptr(dxb_b), _ptr(ws["idx_keep"]), B, Lk, L, Dd, st2)
+            self._side_end(_ptr(dxb_b))
             # decoder_norm saw the compact masked rows (x_dec holds their pre-norm values): compact gradient
             calls.mae_layernorm_bwd(_ptr(ws["g"]), _ptr(ws["x_dec"]), _ptr(ws["meand"]), _ptr(ws["rstdd"]),
                                     self.pf(o("decoder.decoder_norm.weight")), None, None, 0, 0, Mm, Dd,
@@ -631,7 +657,9 @@ class MAEEngine:
                             tail=tail and i == n_dec - 1)
             cur, curb, nxt, nxtb = nxt, nxtb, cur, curb
         # decoder input = scatter(embed) / mask_token, + frozen pos
-        calls.mae_colsum_rows_f32(_ptr(cur), _ptr(ws["idx_mask"]), B, Lm, L, 0, Dd, self.pg(o("decoder.mask_token")), st)
+        st2 = self._side_begin(st, extra=True)
+        calls.mae_colsum_rows_f32(_ptr(cur), _ptr(ws["idx_mask"]), B, Lm, L, 0, Dd, self.pg(o("decoder.mask_token")), st2)
+        self._side_end(_ptr(cur))
         calls.mae_gather_rows_bf16(_ptr(cur), _ptr(ws["idx_keep"]), B, Lk, L, 0, Dd, _ptr(ws["demb"]), st)
         self._linear_bwd_w(_ptr(ws["demb"]), Dd, _ptr(ws["xnf"]), De, Me, o("decoder.decoder_embed.weight"),
                            o("decoder.decoder_embed.bias"), st)
@@ -650,6 +678,7 @@ class MAEEngine:
         """Lightning clip-by-norm + AdamW over the flat buffers; refreshes the bf16 shadows.  Returns the
         (device) pre-clip gradient norm."""
         st = torch.cuda.current_stream(self.flat.device).cuda_stream
+        self._wg_join()  # (a no-op after backward(); orders a pending W^T refresh before the weights change again)
         self.step_count += 1
         nparts = 1024
         calls.mae_grad_sumsq(self.grads.data_ptr(), self.n_opt, self.partials.data_ptr(), nparts, st)
@@ -657,8 +686,11 @@ class MAEEngine:
                              self.exp_avg_sq.data_ptr(), self.flat_bf16.data_ptr(), self.n_opt, float(lr), betas[0],
                              betas[1], eps, weight_decay, max_norm, self.step_count, self.partials.data_ptr(), nparts,
                              self.grad_norm.data_ptr(), st)
+        # W^T shadows are read by the dgrad GEMMs only: off the next forward's critical path
+        st2 = self._side_begin(st, extra=True)
         calls.mae_transpose_cast_bf16(self.flat.data_ptr(), self.flat_bf16_t.data_ptr(), self.t_table.data_ptr(),
-                                      self.t_table.shape[0], self.t_max_rows, self.t_max_cols, st)
+                                      self.t_table.shape[0], self.t_max_rows, self.t_max_cols, st2)
+        self._side_end(self.flat_bf16_t.data_ptr())
         self._shadow_version = self.flat._version
         return self.grad_norm
 
