@@ -202,3 +202,43 @@ def test_cli_flags_match_reference():
     assert (a.config, a.resume_from, a.output_dir_suffix) == ("configs/mae.yaml", None, "mae_pretrain")
     b = train_mae.parse_args(["--encoder_ckpt", "x.pt"])
     assert (b.config, b.encoder_ckpt, b.classifier_ckpt, b.output_dir_suffix) == ("configs/mae.yaml", "x.pt", None, "mae_finetune")
+
+
+def test_bench_algorithmic_cost_covers_every_entry_point_and_renders(tmp_path):
+    """bench.py's per-kernel roofline table: every compute entry point of the C ABI has a byte / FLOP formula (a new kernel
+    without one would silently drop out of the table), spot values follow SURVEY §8d, and tools/roofline_table.py renders a
+    bench line."""
+    import importlib.util
+    import json
+    import subprocess
+    import sys
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for name, sig in _lib.SIGNATURES.items():
+        if name in ("mae_version", "mae_error_string", "mae_transpose_cast_bf16"):
+            continue
+        args = [3 if t is ctypes.c_int or t is ctypes.c_longlong else (1.0 if t is ctypes.c_float else 4096) for t in sig]
+        if name == "mae_gemm_tn":
+            args[5] = 0  # a valid epilogue id
+        nbytes, flops, label = bench.algorithmic_cost(name, args)
+        assert nbytes is not None and nbytes > 0 and label, name
+    # decoder qkv GEMM of configs/mae.yaml at B=2000: A + W + C bytes, 2 M N K flops
+    nbytes, flops, _ = bench.algorithmic_cost("mae_gemm_tn", [0, 0, 290000, 576, 192, 0, 0, 0, 0, 0, 0])
+    assert nbytes == 290000 * 192 * 2 + 576 * 192 * 2 + 290000 * 576 * 2 and flops == 2 * 290000 * 576 * 192
+    # decoder attention: 4 L^2 hd flops per (sample, head) forward
+    _, flops, _ = bench.algorithmic_cost("mae_attention_fwd", [0, 2000, 145, 6, 32, 0, 0, 0])
+    assert flops == 4.0 * 2000 * 6 * 145 * 145 * 32
+    line = {"ms_per_step": 8.0, "value": 250000.0, "unit": "images/s",
+            "roofline": {"peak": 6553.0, "peak_source": "measured"}, "step_roofline": {"peak": 1393.7},
+            "extra": {"instrumented_step_ms": 8.1, "kernel_roofline": [
+                {"kernel": "gemm_tn", "shape": "M=1 N=1 K=1 epi=0", "launches": 2, "us_per_launch": 10.0, "mb_per_launch": 1.0,
+                 "gbs": 100.0, "hbm_frac": 0.02, "tflops": 1.0, "tensor_frac": 0.001},
+                {"kernel": "layernorm_fwd", "shape": "rows=1 D=4", "launches": 1, "us_per_launch": 5.0, "mb_per_launch": 0.5,
+                 "gbs": 100.0, "hbm_frac": 0.02, "tflops": 0.0, "tensor_frac": 0.0}]}}
+    path = tmp_path / "b.json"
+    path.write_text("noise\n" + json.dumps(line) + "\n")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "roofline_table.py"), str(path)], capture_output=True,
+                         text=True, check=True).stdout
+    assert "| gemm_tn | M=1 N=1 K=1 epi=0 | 2 |" in out and "| layernorm_fwd |" in out and "– | –" in out
