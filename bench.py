@@ -173,6 +173,9 @@ def algorithmic_cost(name, a):
     if name == "mae_scatter_decoder_tokens":
         B, L, nk, D = a[5], a[6], a[7], a[8]
         return B * nk * D * 2.0 + B * L * D * 4.0, 0.0, f"B={B} L={L} D={D}"
+    if name == "mae_scatter_decoder_tokens_ln":
+        B, L, nk, D = a[5], a[6], a[7], a[8]
+        return B * nk * D * 2.0 + B * L * D * 6.0 + B * L * 8.0, 0.0, f"B={B} L={L} D={D} (+norm1)"
     if name == "mae_masked_mse":
         B, C, patch, nm = a[3], a[4], a[6], a[7]
         return B * nm * C * patch * patch * (2.0 + 4 + 2 * nz(a[11]) + 4 * nz(a[12])), 0.0, f"B={B} masked={nm}"

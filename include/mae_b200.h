@@ -123,6 +123,14 @@ int mae_scatter_decoder_tokens(const void* emb_bf16, const float* mask_token, co
  * loss (1) f32 = mean((pred-target)^2) (deterministic two-stage reduction through `partials`, >= 4096 floats);
  * optional dpred bf16 = 2*(pred-target)/numel; optional target f32 (B,n_mask,C*p*p).
  * norm_pix != 0 normalises each target patch by its own mean/var (opt-in; the reference does not). */
+/* mae_scatter_decoder_tokens fused with the first decoder block's norm1 (timm Block.norm1 on the freshly assembled
+ * stream): additionally writes xn bf16 (B*L,D) and the row statistics mean / rstd (B*L) like mae_layernorm_fwd, so the
+ * stream is not read back by a separate launch.  D <= 256. */
+int mae_scatter_decoder_tokens_ln(const void* emb_bf16, const float* mask_token, const float* dec_pos,
+                                  const int64_t* idx_keep, const int64_t* idx_mask, int B, int L, int num_keep, int D,
+                                  const float* gamma, const float* beta, float eps, float* x_dec, void* xn_bf16,
+                                  float* mean, float* rstd, mae_stream_t stream);
+
 int mae_masked_mse(const void* pred_bf16, const float* images, const int64_t* idx_mask, int B, int C, int img,
                    int patch, int n_mask, int norm_pix, float* loss, float* partials, void* dpred_bf16,
                    float* target, mae_stream_t stream);

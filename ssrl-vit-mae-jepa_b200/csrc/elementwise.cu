@@ -438,6 +438,98 @@ __global__ void __launch_bounds__(256) scatter_decoder_kernel(const __nv_bfloat1
   }
 }
 
+// scatter_decoder_kernel fused with the first decoder block's norm1: one warp per token (two tokens per iteration); the
+// row is assembled in registers (embedded kept token or mask token, + pos), written to the fp32 stream, normalised and
+// written as bf16 with its statistics: the stream is not read back by a separate LayerNorm launch.
+template <int NV>
+__global__ void __launch_bounds__(256, 3) scatter_decoder_ln_kernel(
+    const __nv_bfloat16* __restrict__ emb, const float* __restrict__ mask_token, const float* __restrict__ dec_pos,
+    const int64_t* __restrict__ idx_keep, const int64_t* __restrict__ idx_mask, int B, int L, int num_keep, int D,
+    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* __restrict__ x_dec,
+    __nv_bfloat16* __restrict__ xn, float* __restrict__ mean, float* __restrict__ rstd) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int ROWS = 2;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int n_mask = L - num_keep;
+  float4 gm[NV], bt[NV], mt[NV];
+  bool has[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = 128 * j + 4 * lane;
+    has[j] = c < D;
+    gm[j] = bt[j] = mt[j] = make_float4(0, 0, 0, 0);
+    if (has[j]) {
+      gm[j] = *reinterpret_cast<const float4*>(gamma + c);
+      bt[j] = *reinterpret_cast<const float4*>(beta + c);
+      mt[j] = *reinterpret_cast<const float4*>(mask_token + c);
+    }
+  }
+  const float invD = 1.0f / D;
+  const long long rows = (long long)B * L, stride = (long long)gridDim.x * wpb;
+  for (long long ra = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); ra < rows; ra += ROWS * stride) {
+    float4 v[ROWS][NV], pp[ROWS][NV];
+    long long orow[ROWS];  // destination row b * L + l
+    bool ok[ROWS];
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) {
+      long long r = ra + k * stride;
+      ok[k] = r < rows;
+      if (!ok[k]) r = ra;
+      const uint32_t b = uint32_t(r) / uint32_t(L), jj = uint32_t(r) - b * uint32_t(L);  // B * L is an int
+      const bool kept = jj < uint32_t(num_keep);
+      const long long src = kept ? (long long)b * num_keep + jj : (long long)b * n_mask + (jj - num_keep);
+      const int l = int(__ldg((kept ? idx_keep : idx_mask) + src));
+      orow[k] = (long long)b * L + l;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c = 128 * j + 4 * lane;
+        v[k][j] = mt[j];
+        pp[k][j] = make_float4(0, 0, 0, 0);
+        if (has[j]) {
+          pp[k][j] = *reinterpret_cast<const float4*>(dec_pos + (long long)l * D + c);
+          if (kept) {
+            const uint2 e = *reinterpret_cast<const uint2*>(emb + src * D + c);
+            v[k][j] = make_float4(bf16_lo(e.x), bf16_hi(e.x), bf16_lo(e.y), bf16_hi(e.y));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) {
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        v[k][j].x += pp[k][j].x; v[k][j].y += pp[k][j].y; v[k][j].z += pp[k][j].z; v[k][j].w += pp[k][j].w;
+        sum += v[k][j].x + v[k][j].y + v[k][j].z + v[k][j].w;  // lanes past D hold zeros
+      }
+      const float mu = warp_sum(sum) * invD;
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (has[j]) {
+          const float a = v[k][j].x - mu, b2 = v[k][j].y - mu, c2 = v[k][j].z - mu, d2 = v[k][j].w - mu;
+          sq += a * a + b2 * b2 + c2 * c2 + d2 * d2;
+        }
+      const float rs = rsqrtf(warp_sum(sq) * invD + eps);
+      if (!ok[k]) continue;
+      float* xd = x_dec + orow[k] * D;
+      __nv_bfloat16* dst = xn + orow[k] * D;
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (has[j]) {
+          const int c = 128 * j + 4 * lane;
+          *reinterpret_cast<float4*>(xd + c) = v[k][j];
+          uint2 o;
+          o.x = pack_bf16x2((v[k][j].x - mu) * rs * gm[j].x + bt[j].x, (v[k][j].y - mu) * rs * gm[j].y + bt[j].y);
+          o.y = pack_bf16x2((v[k][j].z - mu) * rs * gm[j].z + bt[j].z, (v[k][j].w - mu) * rs * gm[j].w + bt[j].w);
+          *reinterpret_cast<uint2*>(dst + c) = o;
+        }
+      if (lane == 0) { mean[orow[k]] = mu; rstd[orow[k]] = rs; }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // masked MSE: one warp per masked patch; the target is read straight from the image
 // ---------------------------------------------------------------------------------------------
@@ -957,6 +1049,20 @@ extern "C" int mae_scatter_decoder_tokens(const void* emb, const float* mask_tok
   if (!emb || !mask_token || !dec_pos || !idx_keep || !idx_mask || !x_dec) return MAE_ERR_NULL;
   if (D % 4 || num_keep < 1 || num_keep > L) return MAE_ERR_SHAPE;
   mae_launch(scatter_decoder_kernel, dim3(grid_for((long long)B * L * (D / 4), 256)), dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(emb), mask_token, dec_pos, idx_keep, idx_mask, B, L, num_keep, D, x_dec);
+  return MAE_CHECK_LAUNCH();
+}
+
+extern "C" int mae_scatter_decoder_tokens_ln(const void* emb, const float* mask_token, const float* dec_pos,
+                                             const int64_t* idx_keep, const int64_t* idx_mask, int B, int L, int num_keep,
+                                             int D, const float* gamma, const float* beta, float eps, float* x_dec,
+                                             void* xn, float* mean, float* rstd, cudaStream_t stream) {
+  if (B <= 0) return MAE_OK;
+  if (!emb || !mask_token || !dec_pos || !idx_keep || !idx_mask || !gamma || !beta || !x_dec || !xn || !mean || !rstd)
+    return MAE_ERR_NULL;
+  if (D % 4 || D > 256 || num_keep < 1 || num_keep > L) return MAE_ERR_SHAPE;
+  mae_launch(scatter_decoder_ln_kernel<2>, dim3(grid_for((long long)B * L, 8, 148 * 16)), dim3(256), 0, stream,
+             reinterpret_cast<const __nv_bfloat16*>(emb), mask_token, dec_pos, idx_keep, idx_mask, B, L, num_keep, D, gamma,
+             beta, eps, x_dec, reinterpret_cast<__nv_bfloat16*>(xn), mean, rstd);
   return MAE_CHECK_LAUNCH();
 }
 

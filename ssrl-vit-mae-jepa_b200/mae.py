@@ -196,6 +196,9 @@ class MAEEngine:
         self.masked_tail = os.environ.get("MAE_MASKED_TAIL", "1") != "0"
         # the small optimizer-only launches (W^T refresh, mask-token column sum, kept-row clearing) also on the side stream
         self.side_extras = os.environ.get("MAE_SIDE_EXTRAS", "1") != "0"
+        # decoder-input assembly fused with the first decoder block's norm1: correct, but measured slower than the two
+        # launches it replaces (8.27 vs 8.16 ms/step: 80 registers, dependent index -> pos loads), so opt-in only
+        self.scatter_ln = os.environ.get("MAE_SCATTER_LN", "0") == "1"
         self._side_skip = False
         self._side: Optional[torch.cuda.Stream] = None
         self._wg_pending: Dict[int, torch.cuda.Event] = {}
@@ -370,13 +373,14 @@ class MAEEngine:
         return self.masked_tail and len(self.dec_blocks) > 0 and self.dims["Dd"] <= 256
 
     def _block_fwd(self, w: _BlockW, s: Dict[str, torch.Tensor], x_out: Optional[torch.Tensor], M: int, B: int, L: int,
-                   st: int, tail: bool = False):
+                   st: int, tail: bool = False, skip_norm1: bool = False):
         """One pre-norm transformer block.  ``tail``: the last decoder block; norm2 and the MLP run on the idx_mask rows
         only (compact, Mm rows) and mlp.fc2 leaves its bf16 output in ``ws["dlt"]`` without the residual add, which
         :meth:`_decode` folds into decoder_norm (``mae_layernorm_fwd_add``)."""
         D, H, hd = w.dim, w.heads, w.hd
-        calls.mae_layernorm_fwd(_ptr(s["x_in"]), self.pf(w.n1w), self.pf(w.n1b), None, 0, 0, M, D, LN_EPS,
-                                _ptr(s["xn1"]), _ptr(s["mean1"]), _ptr(s["rstd1"]), st)
+        if not skip_norm1:  # (the decoder's first block gets xn1 / mean1 / rstd1 from mae_scatter_decoder_tokens_ln)
+            calls.mae_layernorm_fwd(_ptr(s["x_in"]), self.pf(w.n1w), self.pf(w.n1b), None, 0, 0, M, D, LN_EPS,
+                                    _ptr(s["xn1"]), _ptr(s["mean1"]), _ptr(s["rstd1"]), st)
         calls.mae_gemm_tn(_ptr(s["xn1"]), self.pw(w.qkvw), M, 3 * D, D, EPI_BF16, self.pf(w.qkvb), _ptr(s["qkv"]),
                           None, None, st)
         calls.mae_attention_fwd(_ptr(s["qkv"]), B, L, H, hd, _ptr(s["att"]), _ptr(s["lse"]), st)
@@ -490,14 +494,23 @@ class MAEEngine:
         calls.mae_gemm_tn(_ptr(ws["xnf"]), self.pw(o("decoder.decoder_embed.weight")), d["Me"], Dd, De, EPI_BF16,
                           self.pf(o("decoder.decoder_embed.bias")), _ptr(ws["emb"]), None, None, st)
         x0 = ws["dec"][0]["x_in"] if self.dec_blocks else ws["x_dec"]
-        calls.mae_scatter_decoder_tokens(_ptr(ws["emb"]), self.pf(o("decoder.mask_token")),
-                                         self.pf(o("decoder.decoder_pos_embed")), _ptr(ws["idx_keep"]),
-                                         _ptr(ws["idx_mask"]), B, L, Lk, Dd, _ptr(x0), st)
-        tail = self._use_masked_tail()
         n_dec = len(self.dec_blocks)
+        fused_ln = self.scatter_ln and n_dec > 0 and Dd <= 256
+        if fused_ln:
+            w0, s0 = self.dec_blocks[0], ws["dec"][0]
+            calls.mae_scatter_decoder_tokens_ln(_ptr(ws["emb"]), self.pf(o("decoder.mask_token")),
+                                                self.pf(o("decoder.decoder_pos_embed")), _ptr(ws["idx_keep"]),
+                                                _ptr(ws["idx_mask"]), B, L, Lk, Dd, self.pf(w0.n1w), self.pf(w0.n1b), LN_EPS,
+                                                _ptr(x0), _ptr(s0["xn1"]), _ptr(s0["mean1"]), _ptr(s0["rstd1"]), st)
+        else:
+            calls.mae_scatter_decoder_tokens(_ptr(ws["emb"]), self.pf(o("decoder.mask_token")),
+                                             self.pf(o("decoder.decoder_pos_embed")), _ptr(ws["idx_keep"]),
+                                             _ptr(ws["idx_mask"]), B, L, Lk, Dd, _ptr(x0), st)
+        tail = self._use_masked_tail()
         for i, w in enumerate(self.dec_blocks):
             x_out = ws["dec"][i + 1]["x_in"] if i + 1 < n_dec else ws["x_dec"]
-            self._block_fwd(w, ws["dec"][i], x_out, d["Md"], B, L, st, tail=tail and i == n_dec - 1)
+            self._block_fwd(w, ws["dec"][i], x_out, d["Md"], B, L, st, tail=tail and i == n_dec - 1,
+                            skip_norm1=fused_ln and i == 0)
         if tail:
             # decoder_norm over  x_mid[idx_mask rows] + mlp output ; the summed rows (compact) are kept in x_dec for the backward
             calls.mae_layernorm_fwd_add(_ptr(ws["dec"][-1]["x_mid"]), _ptr(ws["dlt"]),

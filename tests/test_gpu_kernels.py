@@ -178,6 +178,33 @@ def test_layernorm_masked_tail_variants():
     assert rel_err(dg, gr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
 
 
+def test_scatter_decoder_tokens_ln_matches_two_launches():
+    """mae_scatter_decoder_tokens_ln = mae_scatter_decoder_tokens followed by mae_layernorm_fwd: the stream bit for bit,
+    the normalised rows and statistics like the separate LayerNorm launch (up to FMA contraction)."""
+    B, L, nk, D = 7, 145, 36, 192
+    g = torch.Generator().manual_seed(29)
+    perm = torch.stack([torch.cat([torch.zeros(1, dtype=torch.int64), torch.randperm(L - 1, generator=g) + 1]) for _ in range(B)])
+    idx_keep, idx_mask = perm[:, :nk].contiguous().to(dev), perm[:, nk:].contiguous().to(dev)
+    emb = bf(torch.randn(B * nk, D, generator=g)).to(dev)
+    mt, pos = torch.randn(D, generator=g).to(dev), torch.randn(L, D, generator=g).to(dev)
+    gamma, beta = (torch.rand(D, generator=g) + 0.5).to(dev), torch.randn(D, generator=g).to(dev)
+    x1, x2 = torch.empty(B * L, D, device=dev), torch.empty(B * L, D, device=dev)
+    xn1, xn2 = (torch.empty(B * L, D, dtype=torch.bfloat16, device=dev) for _ in range(2))
+    m1, r1, m2, r2 = (torch.empty(B * L, device=dev) for _ in range(4))
+    calls.mae_scatter_decoder_tokens(p(emb), p(mt), p(pos), p(idx_keep), p(idx_mask), B, L, nk, D, p(x1), stream())
+    calls.mae_layernorm_fwd(p(x1), p(gamma), p(beta), None, 0, 0, B * L, D, 1e-6, p(xn1), p(m1), p(r1), stream())
+    calls.mae_scatter_decoder_tokens_ln(p(emb), p(mt), p(pos), p(idx_keep), p(idx_mask), B, L, nk, D, p(gamma), p(beta), 1e-6,
+                                        p(x2), p(xn2), p(m2), p(r2), stream())
+    assert torch.equal(x1, x2)
+    # same arithmetic in the same order; only the compiler's FMA contraction may differ between the two kernels
+    assert max_err(m1, m2) < 1e-6 and rel_err(r1, r2) < 1e-6
+    assert max_err(xn1, xn2) <= 2 ** -7 * xn1.float().abs().max().item() and (xn1 != xn2).float().mean().item() < 1e-3
+    ref = torch.empty(B, L, D, device=dev)
+    ref.scatter_(1, idx_keep.unsqueeze(-1).expand(-1, -1, D), emb.float().view(B, nk, D))
+    ref.scatter_(1, idx_mask.unsqueeze(-1).expand(-1, -1, D), mt.expand(B, L - nk, D).contiguous())
+    assert torch.equal(x2.view(B, L, D), ref + pos)
+
+
 GEMM_SHAPES = [(128, 64, 64), (128, 144, 144), (300, 432, 144), (1000, 576, 192), (777, 144, 576), (517, 192, 768),
                (128, 768, 192), (2500, 192, 192), (64, 144, 192), (40000, 576, 192)]
 
