@@ -119,57 +119,101 @@ __global__ void __launch_bounds__(NT * 16) attn_fwd_kernel(const __nv_bfloat16* 
   for (int ks = 0; ks < KS; ++ks) frag_a<ST>(aq[ks], qA, q0, ks * 16);
   const float sl2 = scale * 1.4426950408889634f;
 
-  // pass 1: row max only (no exponentials); key columns >= L exist only in the last tiles, so only those mask
-  float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll 2
-  for (int nt = 0; nt < NT; ++nt) {
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
-    mma_rows<ST, KS>(s, aq, kR, nt * 8);
-    if (nt * 8 + 8 > L) {  // warp-uniform
-      const int c = nt * 8 + t * 2;
-      if (c >= L) { s[0] = -INFINITY; s[2] = -INFINITY; }
-      if (c + 1 >= L) { s[1] = -INFINITY; s[3] = -INFINITY; }
-    }
-    m0 = fmaxf(m0, fmaxf(s[0], s[1]));
-    m1 = fmaxf(m1, fmaxf(s[2], s[3]));
-  }
-  float M0 = m0, M1 = m1;
-  M0 = fmaxf(M0, __shfl_xor_sync(0xffffffffu, M0, 1)); M0 = fmaxf(M0, __shfl_xor_sync(0xffffffffu, M0, 2));
-  M1 = fmaxf(M1, __shfl_xor_sync(0xffffffffu, M1, 1)); M1 = fmaxf(M1, __shfl_xor_sync(0xffffffffu, M1, 2));
-
-  // pass 2: recompute S per 16-key block, P = exp(S - max), row sums and O += P.V; normalised at the end
   float o[DNP][4];
 #pragma unroll
   for (int dn = 0; dn < DNP; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
-  const float ms0 = M0 * sl2, ms1 = M1 * sl2;
-  float l0 = 0.f, l1 = 0.f;
-#pragma unroll 2
-  for (int kk = 0; kk < NT / 2; ++kk) {
-    float p[2][4];
+  float M0, M1, l0 = 0.f, l1 = 0.f;
+  if constexpr (NT <= 8) {
+    // short sequences (encoder: 36 tokens, NT = 6): the whole 16 x (8 NT) score slab stays in registers (4 NT floats), so
+    // Q.K^T is computed once: scores -> row max -> exp -> P.V.  Masked key columns are set to -inf (exp2 gives 0).
+    float sc[NT][4];
+    float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const int nt = 2 * kk + hf;
-      p[hf][0] = p[hf][1] = p[hf][2] = p[hf][3] = 0.f;
-      mma_rows<ST, KS>(p[hf], aq, kR, nt * 8);
-      p[hf][0] = ex2_approx(p[hf][0] * sl2 - ms0); p[hf][1] = ex2_approx(p[hf][1] * sl2 - ms0);
-      p[hf][2] = ex2_approx(p[hf][2] * sl2 - ms1); p[hf][3] = ex2_approx(p[hf][3] * sl2 - ms1);
+    for (int nt = 0; nt < NT; ++nt) {
+      sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+      mma_rows<ST, KS>(sc[nt], aq, kR, nt * 8);
       if (nt * 8 + 8 > L) {  // warp-uniform
         const int c = nt * 8 + t * 2;
-        if (c >= L) { p[hf][0] = 0.f; p[hf][2] = 0.f; }
-        if (c + 1 >= L) { p[hf][1] = 0.f; p[hf][3] = 0.f; }
+        if (c >= L) { sc[nt][0] = -INFINITY; sc[nt][2] = -INFINITY; }
+        if (c + 1 >= L) { sc[nt][1] = -INFINITY; sc[nt][3] = -INFINITY; }
       }
-      l0 += p[hf][0] + p[hf][1];
-      l1 += p[hf][2] + p[hf][3];
+      m0 = fmaxf(m0, fmaxf(sc[nt][0], sc[nt][1]));
+      m1 = fmaxf(m1, fmaxf(sc[nt][2], sc[nt][3]));
     }
-    uint32_t a[4];
-    a[0] = pack_bf16x2(p[0][0], p[0][1]); a[1] = pack_bf16x2(p[0][2], p[0][3]);
-    a[2] = pack_bf16x2(p[1][0], p[1][1]); a[3] = pack_bf16x2(p[1][2], p[1][3]);
+    M0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); M0 = fmaxf(M0, __shfl_xor_sync(0xffffffffu, M0, 2));
+    M1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); M1 = fmaxf(M1, __shfl_xor_sync(0xffffffffu, M1, 2));
+    const float ms0 = M0 * sl2, ms1 = M1 * sl2;
 #pragma unroll
-    for (int dp = 0; dp < DNP / 2; ++dp) {
-      uint32_t bv[4];
-      frag_b_cols<ST>(bv, vA, kk * 16, dp * 16);
-      mma_16816(o[2 * dp], a, bv[0], bv[1]);
-      if (2 * dp + 1 < DN) mma_16816(o[2 * dp + 1], a, bv[2], bv[3]);
+    for (int kk = 0; kk < NT / 2; ++kk) {
+      float p[2][4];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int nt = 2 * kk + hf;
+        p[hf][0] = ex2_approx(sc[nt][0] * sl2 - ms0); p[hf][1] = ex2_approx(sc[nt][1] * sl2 - ms0);
+        p[hf][2] = ex2_approx(sc[nt][2] * sl2 - ms1); p[hf][3] = ex2_approx(sc[nt][3] * sl2 - ms1);
+        l0 += p[hf][0] + p[hf][1];
+        l1 += p[hf][2] + p[hf][3];
+      }
+      uint32_t a[4];
+      a[0] = pack_bf16x2(p[0][0], p[0][1]); a[1] = pack_bf16x2(p[0][2], p[0][3]);
+      a[2] = pack_bf16x2(p[1][0], p[1][1]); a[3] = pack_bf16x2(p[1][2], p[1][3]);
+#pragma unroll
+      for (int dp = 0; dp < DNP / 2; ++dp) {
+        uint32_t bv[4];
+        frag_b_cols<ST>(bv, vA, kk * 16, dp * 16);
+        mma_16816(o[2 * dp], a, bv[0], bv[1]);
+        if (2 * dp + 1 < DN) mma_16816(o[2 * dp + 1], a, bv[2], bv[3]);
+      }
+    }
+  } else {
+    // pass 1: row max only (no exponentials); key columns >= L exist only in the last tiles, so only those mask
+    float m0 = -INFINITY, m1 = -INFINITY;
+  #pragma unroll 2
+    for (int nt = 0; nt < NT; ++nt) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_rows<ST, KS>(s, aq, kR, nt * 8);
+      if (nt * 8 + 8 > L) {  // warp-uniform
+        const int c = nt * 8 + t * 2;
+        if (c >= L) { s[0] = -INFINITY; s[2] = -INFINITY; }
+        if (c + 1 >= L) { s[1] = -INFINITY; s[3] = -INFINITY; }
+      }
+      m0 = fmaxf(m0, fmaxf(s[0], s[1]));
+      m1 = fmaxf(m1, fmaxf(s[2], s[3]));
+    }
+    M0 = m0; M1 = m1;
+    M0 = fmaxf(M0, __shfl_xor_sync(0xffffffffu, M0, 1)); M0 = fmaxf(M0, __shfl_xor_sync(0xffffffffu, M0, 2));
+    M1 = fmaxf(M1, __shfl_xor_sync(0xffffffffu, M1, 1)); M1 = fmaxf(M1, __shfl_xor_sync(0xffffffffu, M1, 2));
+
+    // pass 2: recompute S per 16-key block, P = exp(S - max), row sums and O += P.V; normalised at the end
+    const float ms0 = M0 * sl2, ms1 = M1 * sl2;
+  #pragma unroll 2
+    for (int kk = 0; kk < NT / 2; ++kk) {
+      float p[2][4];
+  #pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int nt = 2 * kk + hf;
+        p[hf][0] = p[hf][1] = p[hf][2] = p[hf][3] = 0.f;
+        mma_rows<ST, KS>(p[hf], aq, kR, nt * 8);
+        p[hf][0] = ex2_approx(p[hf][0] * sl2 - ms0); p[hf][1] = ex2_approx(p[hf][1] * sl2 - ms0);
+        p[hf][2] = ex2_approx(p[hf][2] * sl2 - ms1); p[hf][3] = ex2_approx(p[hf][3] * sl2 - ms1);
+        if (nt * 8 + 8 > L) {  // warp-uniform
+          const int c = nt * 8 + t * 2;
+          if (c >= L) { p[hf][0] = 0.f; p[hf][2] = 0.f; }
+          if (c + 1 >= L) { p[hf][1] = 0.f; p[hf][3] = 0.f; }
+        }
+        l0 += p[hf][0] + p[hf][1];
+        l1 += p[hf][2] + p[hf][3];
+      }
+      uint32_t a[4];
+      a[0] = pack_bf16x2(p[0][0], p[0][1]); a[1] = pack_bf16x2(p[0][2], p[0][3]);
+      a[2] = pack_bf16x2(p[1][0], p[1][1]); a[3] = pack_bf16x2(p[1][2], p[1][3]);
+  #pragma unroll
+      for (int dp = 0; dp < DNP / 2; ++dp) {
+        uint32_t bv[4];
+        frag_b_cols<ST>(bv, vA, kk * 16, dp * 16);
+        mma_16816(o[2 * dp], a, bv[0], bv[1]);
+        if (2 * dp + 1 < DN) mma_16816(o[2 * dp + 1], a, bv[2], bv[3]);
+      }
     }
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
