@@ -5,7 +5,8 @@
 // (sample, head) problem is 36..145 rows, far below a 128-row tcgen05 tile, and S/P never leave registers.
 //
 // Register pressure is kept low so that several CTAs are resident per SM (the load phase of one overlaps the
-// math of another): the forward makes two passes over the keys (pass 1: online row max / sum, pass 2: recompute
+// math of another): the forward keeps the scores of short rows (<= 64 keys) in registers and otherwise makes two passes
+// over the keys (pass 1: row max, pass 2: recompute
 // S per 16-key block, P = exp(S - max), O += P.V); the backward uses the saved log-sum-exp, so every 16-wide
 // block of P is recomputed independently.  Backward recomputes S once per orientation so that every gradient
 // is produced by the warp that owns its rows (no cross-warp reduction, no atomics, no smem round trip for P/dS):
