@@ -211,3 +211,27 @@ def test_wgrad_side_stream_matches_single_stream():
     for n, a in got[False].items():
         b = got[True][n]
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-6 + 1e-5 * a.abs().max().item()), (n, max_err(a, b))
+
+
+def test_masked_tail_matches_all_rows_schedule():
+    """The last decoder block's norm2 / MLP / residual and decoder_norm on the idx_mask rows only (default) against the
+    all-rows schedule (MAE_MASKED_TAIL=0): same loss, predictions and gradients up to the bf16 rounding of the block's
+    mlp.fc2 output, which the masked tail stores before decoder_norm adds it to the stream."""
+    _, m = make_pair()
+    eng = m.engine
+    torch.manual_seed(9)
+    images = torch.randn(48, 3, 96, 96, device="cuda")
+    noise = torch.rand(48, 145, device="cuda")
+    got = {}
+    for tail in (False, True):
+        eng.masked_tail = tail
+        loss, pred, _ = m.forward_loss(images, noise=noise)
+        eng.backward()
+        torch.cuda.synchronize()
+        got[tail] = (loss.item(), pred.detach().float().cpu().clone(),
+                     {n: g.detach().float().cpu().clone() for n, g in eng.named_grads().items()})
+    eng.masked_tail = True
+    (l0, p0, g0), (l1, p1, g1) = got[False], got[True]
+    report("masked_tail", loss_all_rows=l0, loss_tail=l1, pred_rel=rel_err(p1, p0))
+    assert abs(l1 - l0) / abs(l0) < 1e-3 and rel_err(p1, p0) < 1e-2
+    check_grads("masked_tail_grad", g1, g0)
