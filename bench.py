@@ -120,6 +120,9 @@ def run_reference(args):
     ips, cores, ms, done = cpu_reference_run(args.steps, max(args.warmup, 1), batch=64, time_budget_s=120.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s",
+        # same metric string as the GPU arm (the driver pairs the two lines on it); this arm has no device: it is the
+        # reference's CPU path timed with the host clock around whole steps
+        "timed_with": "host perf_counter around whole CPU steps (no device in this arm)",
         "n_gpus": args.gpus, "steps": done, "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs/mae.yaml MAE pretrain step, mask 0.75; CPU sample = batch 64 per step"},
@@ -380,14 +383,24 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_u8_value = world * B * e2e_steps / (t.item() * 1e-3)
 
+    # replicas must stay bit-identical: every rank applied the same averaged gradient with the same optimizer state
+    replica_maxdiff = None
+    if world > 1:
+        flat = mod.model.engine.flat
+        mx, mn = flat.clone(), flat.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        replica_maxdiff = (mx - mn).abs().max().item()
+
     if rank == 0:
         pk = peaks()
         share, roof, extra = kernel_breakdown(tr, pool[0], None, pk)
+        extra["replica_param_maxdiff"] = replica_maxdiff  # N > 1: max |param(rank i) - param(rank j)| after all steps; must be 0.0
         extra["e2e_uint8_gpu_augment"] = {"value": e2e_u8_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 96 * 96,
                                           "note": "uint8 host batches + GPU RandomResizedCrop/flip/normalize inside the timed loop"}
         step_tf = value / world * FLOPS_PER_IMAGE / 1e12
         line = {
-            "metric": METRIC, "value": value, "unit": "images/s",
+            "metric": METRIC, "value": value, "unit": "images/s", "timed_with": "CUDA events on the launching stream, max over ranks",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "configs/mae.yaml MAE pretrain step (96px, 8px patches, 144-d x4 enc, 192-d x2 dec), "

@@ -77,9 +77,6 @@ int mae_layernorm_bwd(const void* g_bf16, const float* x, const float* mean, con
                       const float* dx_in, const int64_t* gather_idx, int n_sel, int L_src, int rows, int D,
                       float* dx_out, void* dx_out_bf16, float* dgamma, float* dbeta, mae_stream_t stream);
 
-/* out = epi(A[M,K] * B[N,K]^T): every nn.Linear forward (B = weight (out,in)) and every dgrad (B = weight^T)
- * of timm Block / MAEDecoderTIMM (reference src/models/mae.py:55,59,71,73).  A, B bf16; fp32 accumulation in
- * TMEM via tcgen05.mma; K % 16 == 0, N % 16 == 0. */
 /* The two LayerNorms around the masked-rows-only tail of the last decoder block (get_at_index(idx_mask) at reference
  * src/models/mae.py:72 commuted backwards through decoder_norm, mlp and norm2 of the last block: the rows it drops are
  * never computed).
@@ -95,6 +92,9 @@ int mae_layernorm_bwd_scatter(const void* g_bf16, const float* x, const float* m
                               int L_src, int rows, int D, float* dx_out, void* dx_out_bf16, float* dgamma,
                               float* dbeta, mae_stream_t stream);
 
+/* out = epi(A[M,K] * B[N,K]^T): every nn.Linear forward (B = weight (out,in)) and every dgrad (B = weight^T)
+ * of timm Block / MAEDecoderTIMM (reference src/models/mae.py:55,59,71,73).  A, B bf16; fp32 accumulation in
+ * TMEM via tcgen05.mma; K % 16 == 0, N % 16 == 0. */
 int mae_gemm_tn(const void* A_bf16, const void* B_bf16, int M, int N, int K, int epi, const float* bias, void* out,
                 void* pre_out_bf16, const void* aux, mae_stream_t stream);
 
@@ -118,11 +118,6 @@ int mae_scatter_decoder_tokens(const void* emb_bf16, const float* mask_token, co
                                const int64_t* idx_keep, const int64_t* idx_mask, int B, int L, int num_keep, int D,
                                float* x_dec, mae_stream_t stream);
 
-/* patchify + get_at_index(idx_mask-1) + MSELoss (reference src/models/mae.py:90-92, src/training/mae.py:40,48):
- * pred bf16 (B,n_mask,C*patch*patch); target read straight from the images in (py,px,c) order.
- * loss (1) f32 = mean((pred-target)^2) (deterministic two-stage reduction through `partials`, >= 4096 floats);
- * optional dpred bf16 = 2*(pred-target)/numel; optional target f32 (B,n_mask,C*p*p).
- * norm_pix != 0 normalises each target patch by its own mean/var (opt-in; the reference does not). */
 /* mae_scatter_decoder_tokens fused with the first decoder block's norm1 (timm Block.norm1 on the freshly assembled
  * stream): additionally writes xn bf16 (B*L,D) and the row statistics mean / rstd (B*L) like mae_layernorm_fwd, so the
  * stream is not read back by a separate launch.  D <= 256. */
@@ -131,6 +126,11 @@ int mae_scatter_decoder_tokens_ln(const void* emb_bf16, const float* mask_token,
                                   const float* gamma, const float* beta, float eps, float* x_dec, void* xn_bf16,
                                   float* mean, float* rstd, mae_stream_t stream);
 
+/* patchify + get_at_index(idx_mask-1) + MSELoss (reference src/models/mae.py:90-92, src/training/mae.py:40,48):
+ * pred bf16 (B,n_mask,C*patch*patch); target read straight from the images in (py,px,c) order.
+ * loss (1) f32 = mean((pred-target)^2) (deterministic two-stage reduction through `partials`, >= 4096 floats);
+ * optional dpred bf16 = 2*(pred-target)/numel; optional target f32 (B,n_mask,C*p*p).
+ * norm_pix != 0 normalises each target patch by its own mean/var (opt-in; the reference does not). */
 int mae_masked_mse(const void* pred_bf16, const float* images, const int64_t* idx_mask, int B, int C, int img,
                    int patch, int n_mask, int norm_pix, float* loss, float* partials, void* dpred_bf16,
                    float* target, mae_stream_t stream);

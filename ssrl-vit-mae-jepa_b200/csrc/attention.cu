@@ -410,12 +410,8 @@ template <int HD, int NT>
 static int launch_fwd(const void* qkv, int B, int L, int H, void* out, float* lse, cudaStream_t st) {
   constexpr int Lp = NT * 8, ST = (HD <= 32 ? 32 : 64) + 8;
   const size_t smem = size_t(3 * Lp * ST) * 2;
-  static bool done = false;
-  if (!done) {
-    if (cudaFuncSetAttribute(attn_fwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
-      return MAE_ERR_LAUNCH;
-    done = true;
-  }
+  static bool done[kMaxDevices] = {};
+  if (!ensure_dyn_smem(attn_fwd_kernel<HD, NT>, smem, done)) return MAE_ERR_LAUNCH;
   mae_launch(attn_fwd_kernel<HD, NT>, dim3(B * H), dim3(NT * 16), smem, st, reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                         reinterpret_cast<__nv_bfloat16*>(out), lse, L, H,
                                                         1.0f / sqrtf(float(HD)));
@@ -427,12 +423,8 @@ static int launch_bwd(const void* qkv, const void* out, const void* dout, const 
                       void* dqkv, cudaStream_t st) {
   constexpr int Lp = NT * 8, ST = (HD <= 32 ? 32 : 64) + 8;
   const size_t smem = size_t(4 * Lp * ST) * 2 + size_t(2 * Lp) * 4;
-  static bool done = false;
-  if (!done) {
-    if (cudaFuncSetAttribute(attn_bwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
-      return MAE_ERR_LAUNCH;
-    done = true;
-  }
+  static bool done[kMaxDevices] = {};
+  if (!ensure_dyn_smem(attn_bwd_kernel<HD, NT>, smem, done)) return MAE_ERR_LAUNCH;
   mae_launch(attn_bwd_kernel<HD, NT>, dim3(B * H), dim3(NT * 16), smem, st, reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(out),
       reinterpret_cast<const __nv_bfloat16*>(dout), lse, reinterpret_cast<__nv_bfloat16*>(dqkv), L, H,
       1.0f / sqrtf(float(HD)));

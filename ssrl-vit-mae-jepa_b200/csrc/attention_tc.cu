@@ -409,15 +409,9 @@ int attn_fwd_tc(const void* qkv, int B, int L, int H, void* out, float* lse, cud
   if (rc) return rc;
   rc = make_tmap_bf16_3d(&mo, out, D, L, B, D, kTcLp);
   if (rc) return rc;
-  static bool done = false;
-  if (!done) {
-    if (cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TcSmem::total) + 1024) != cudaSuccess)
-      return MAE_ERR_LAUNCH;
-    done = true;
-  }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static bool done[kMaxDevices] = {};
+  if (!ensure_dyn_smem(attn_fwd_tc_kernel, TcSmem::total + 1024, done)) return MAE_ERR_LAUNCH;
+  const int sms = num_sms();
   const int nitems = B * (H / 2);
   const int grid = nitems < sms ? nitems : sms;
   mae_launch(attn_fwd_tc_kernel, dim3(grid), dim3(kTcThreads), size_t(TcSmem::total) + 1024, st, mq, mo, lse, B, L, H,
@@ -768,15 +762,9 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
   if (rc) return rc;
   rc = make_tmap_bf16_3d(&md, dout, D, L, B, D, kTcLp, 32);
   if (rc) return rc;
-  static bool done = false;
-  if (!done) {
-    if (cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TcbSmem::total) + 1024) != cudaSuccess)
-      return MAE_ERR_LAUNCH;
-    done = true;
-  }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static bool done[kMaxDevices] = {};
+  if (!ensure_dyn_smem(attn_bwd_tc_kernel, TcbSmem::total + 1024, done)) return MAE_ERR_LAUNCH;
+  const int sms = num_sms();
   const int nitems = B * H;
   const int grid = nitems < sms ? nitems : sms;
   mae_launch(attn_bwd_tc_kernel, dim3(grid), dim3(kTcThreads), size_t(TcbSmem::total) + 1024, st, mq, md,

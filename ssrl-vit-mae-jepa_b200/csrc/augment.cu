@@ -198,12 +198,8 @@ extern "C" int mae_augment_u8(const uint8_t* images, const int* params, int B, i
   if (C <= 0 || Hs <= 0 || Ws <= 0 || S <= 0 || S > 512 || (S & 3) || Hs > 3 * S || Ws > 3 * S) return MAE_ERR_SHAPE;
   const size_t smem = size_t(2) * (2 + kAugMaxTaps) * S * sizeof(int) + ((size_t(Hs) * Ws + 15) & ~size_t(15)) + size_t(Hs) * S;
   if (smem > 200 * 1024) return MAE_ERR_SHAPE;
-  static bool attr_done = false;
-  if (!attr_done && smem > 48 * 1024) {
-    if (cudaFuncSetAttribute(augment_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-      return MAE_ERR_LAUNCH;
-    attr_done = true;
-  }
+  static bool attr_done[mae::kMaxDevices] = {};
+  if (smem > 48 * 1024 && !mae::ensure_dyn_smem(augment_u8_kernel, 200 * 1024, attr_done)) return MAE_ERR_LAUNCH;
   mae_launch(augment_u8_kernel, dim3(B * C), dim3(256), smem, stream, images, params, C, Hs, Ws, S, out);
   return MAE_CHECK_LAUNCH();
 }

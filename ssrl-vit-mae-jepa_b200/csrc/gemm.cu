@@ -60,16 +60,6 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, int rows, int cols, int ld
   return r == CUDA_SUCCESS ? MAE_OK : MAE_ERR_DRIVER;
 }
 
-static int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
-}
-
 // ---------------------------------------------------------------------------------------------
 // gemm_tn
 // ---------------------------------------------------------------------------------------------
@@ -690,12 +680,8 @@ static int pick_bn(int N) {
 template <int EPI>
 static int launch_gemm_tn(const GemmTnParams& p, size_t smem, const CUtensorMap& ma, const CUtensorMap& mb,
                           const CUtensorMap& mo, const CUtensorMap& mo2, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return MAE_ERR_LAUNCH;
-    attr_done = true;
-  }
+  static bool attr_done[kMaxDevices] = {};
+  if (!ensure_dyn_smem(gemm_tn_kernel<EPI>, 227 * 1024, attr_done)) return MAE_ERR_LAUNCH;
   const int total = p.mtiles * p.nchunks;
   const int grid = total < num_sms() ? total : num_sms();
   mae_launch(gemm_tn_kernel<EPI>, dim3(grid), dim3(kGemmThreads), smem, st, p, ma, mb, mo, mo2);
@@ -1073,12 +1059,8 @@ extern "C" int mae_gemm_wgrad(const void* P, int Pc, const void* Q, int Qc, int 
   rc = make_tmap_bf16(&mq, Q, M, Qc, Qc, WR);
   if (rc) return rc;
   const size_t smem = size_t(p.nstages) * stage + sizeof(GemmSmemHdr) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-      return MAE_ERR_LAUNCH;
-    attr_done = true;
-  }
+  static bool attr_done[kMaxDevices] = {};
+  if (!ensure_dyn_smem(gemm_wgrad_kernel, 227 * 1024, attr_done)) return MAE_ERR_LAUNCH;
   mae_launch(gemm_wgrad_kernel, dim3(pgroups, msplit, qchunks), dim3(kWgradThreads), smem, stream, p, mp, mq);
   return cudaGetLastError() == cudaSuccess ? MAE_OK : MAE_ERR_LAUNCH;
 }

@@ -33,4 +33,34 @@ inline cudaError_t mae_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// Per-device state.  A process may drive several GPUs (one engine per device): the SM count and the opt-in for more than
+// 48 KB of dynamic shared memory (cudaFuncSetAttribute is per device) are cached per CUDA device, not per process.
+namespace mae {
+constexpr int kMaxDevices = 64;
+inline int cur_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+  return d;
+}
+inline int num_sms() {
+  static int n[kMaxDevices] = {};
+  const int d = cur_device();
+  if (!n[d]) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || v <= 0) v = 148;
+    n[d] = v;
+  }
+  return n[d];
+}
+// `done` is a function-local `static bool[kMaxDevices]` of the caller: one flag per (kernel instantiation, device).
+template <typename K>
+inline bool ensure_dyn_smem(K kernel, size_t bytes, bool (&done)[kMaxDevices]) {
+  const int d = cur_device();
+  if (done[d]) return true;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)) != cudaSuccess) return false;
+  done[d] = true;
+  return true;
+}
+}  // namespace mae
+
 #define MAE_CHECK_LAUNCH() (cudaGetLastError() == cudaSuccess ? MAE_OK : MAE_ERR_LAUNCH)

@@ -185,7 +185,7 @@ class MAEEngine:
         self.model = model
         self.flat: Optional[torch.Tensor] = None
         self._ws_key = None
-        self._shadow_version = -1
+        self._shadow_fresh, self._shadow_version = False, None
         self.step_count = 0
         self.norm_pix_loss = False
         # weight-gradient GEMMs run on a second stream: they only feed the optimizer, so they trail the dgrad chain and fill
@@ -266,7 +266,7 @@ class MAEEngine:
                 rows.append([self.offsets[n], p.shape[0], p.shape[1], self.offsets[n]])
         self.t_table = torch.tensor(rows, dtype=torch.int64, device=device)
         self.t_max_rows, self.t_max_cols = max(r[1] for r in rows), max(r[2] for r in rows)
-        self._shadow_version = -1
+        self._shadow_fresh, self._shadow_version = False, None
         self._index_blocks()
 
     def _o(self, name: str) -> int:
@@ -293,15 +293,25 @@ class MAEEngine:
         dh = m.decoder.decoder_blocks[0].attn.num_heads if len(m.decoder.decoder_blocks) else 1
         self.dec_blocks = [blk(f"decoder.decoder_blocks.{i}.", dd, dh) for i in range(len(m.decoder.decoder_blocks))]
 
+    def _param_versions(self):
+        """Version counters of the flat buffer and of every parameter view.  Each ``nn.Parameter`` carries its own counter
+        (``p.data = flat[...]`` detaches it from ``flat``'s), so ``p.copy_`` / ``load_state_dict`` / ``torch.optim`` steps
+        bump the parameter's counter and leave ``flat._version`` untouched."""
+        return (self.flat._version, tuple(p._version for _, p in self._param_list))
+
     def _refresh_shadow(self, stream: int) -> None:
-        """bf16 copies of W (same layout) and W^T; skipped when the fused optimizer already refreshed them."""
-        if self._shadow_version == self.flat._version:
+        """bf16 copies of W (same layout) and W^T.  Skipped only for the first forward after the fused optimizer, which
+        refreshed both itself, and only if no parameter was written through torch since (version counters).  Every
+        other forward rebuilds them (two small launches, ~20 us): writes that bypass the counters (``p.data.add_``,
+        kernels on raw pointers) are then always seen, e.g. a torch AdamW fine-tune or ``load_state_dict``."""
+        if self._shadow_fresh and self._shadow_version == self._param_versions():
+            self._shadow_fresh = False
             return
         self._wg_wait(self.flat_bf16_t.data_ptr())  # a W^T refresh still running on the side stream goes first
         calls.mae_cast_bf16(self.flat.data_ptr(), self.flat_bf16.data_ptr(), self.n_total, stream)
         calls.mae_transpose_cast_bf16(self.flat.data_ptr(), self.flat_bf16_t.data_ptr(), self.t_table.data_ptr(),
                                       self.t_table.shape[0], self.t_max_rows, self.t_max_cols, stream)
-        self._shadow_version = self.flat._version
+        self._shadow_fresh = False
 
     # pointers into the flat buffers (element offsets -> byte addresses)
     def pf(self, off: int) -> int:
@@ -704,7 +714,7 @@ class MAEEngine:
         calls.mae_transpose_cast_bf16(self.flat.data_ptr(), self.flat_bf16_t.data_ptr(), self.t_table.data_ptr(),
                                       self.t_table.shape[0], self.t_max_rows, self.t_max_cols, st2)
         self._side_end(self.flat_bf16_t.data_ptr())
-        self._shadow_version = self.flat._version
+        self._shadow_fresh, self._shadow_version = True, self._param_versions()
         return self.grad_norm
 
     def named_grads(self) -> Dict[str, torch.Tensor]:

@@ -111,3 +111,38 @@ def test_mean_pool_random_init_vit_with_trainable_pos_embed():
     opt.step()
     l2 = mod.training_step((x.cuda(), y.cuda()), 0)
     assert torch.isfinite(l2) and l2.item() != loss.item()
+
+
+def test_torch_optimizer_updates_reach_the_kernels():
+    """Weights changed through torch (AdamW steps on the flat-buffer views, then ``load_state_dict``) must be what the
+    kernels compute with: the bf16 W / W^T shadows are rebuilt unless the fused optimizer just refreshed them.  The head
+    stays frozen, so every change of the logits comes from the encoder weights; the oracle takes the same AdamW steps."""
+    oc, mod = _pair(freeze=False)
+    for p_ in oc.parameters():
+        p_.requires_grad = True
+    for p_ in list(mod.model.head.parameters()) + list(oc.head.parameters()):
+        p_.requires_grad = False
+    x, y = _data(seed=8)
+    xc, yc = x.cuda(), y.cuda()
+    opt = torch.optim.AdamW([p_ for p_ in mod.model.parameters() if p_.requires_grad], lr=2e-3, weight_decay=0.0)
+    opt_o = torch.optim.AdamW([p_ for p_ in oc.parameters() if p_.requires_grad], lr=2e-3, weight_decay=0.0)
+    with torch.no_grad():
+        f0 = mod.model.encoder.forward_features(xc).clone()
+    for _ in range(4):
+        opt.zero_grad(set_to_none=True); opt_o.zero_grad(set_to_none=True)
+        mod.training_step((xc, yc), 0).backward()
+        F.cross_entropy(oc(x), y).backward()
+        opt.step(); opt_o.step()
+    with torch.no_grad():
+        f1 = mod.model.encoder.forward_features(xc).clone()
+        f_ref = oc.encoder.forward_features(x)
+    moved = rel_err(f1.cpu(), f0.cpu())
+    report("cls_torch_adamw", moved=moved, rel_vs_oracle=rel_err(f1.cpu(), f_ref))
+    assert moved > 5e-2                                   # 4 steps at lr 2e-3 move the features a lot ...
+    assert rel_err(f1.cpu(), f_ref) < 0.5 * moved         # ... and the kernels follow the oracle, not the step-0 weights
+    # load_state_dict after a forward: the next forward must use the loaded weights
+    sd0 = {k: v.clone() for k, v in oc.encoder.state_dict().items()}
+    mod.model.encoder.load_state_dict({k: torch.zeros_like(v) if k == "blocks.3.mlp.fc2.weight" else v for k, v in sd0.items()})
+    with torch.no_grad():
+        f2 = mod.model.encoder.forward_features(xc)
+    assert rel_err(f2.cpu(), f1.cpu()) > 1e-3

@@ -146,6 +146,39 @@ def test_full_size_batch_properties():
     assert torch.isfinite(l) and l.item() < l0.item()  # same batch: the loss must go down
 
 
+def test_full_size_batch_matches_oracle():
+    """BASELINE config #2 at its real size (B=2000, the batch bench.py times): loss, predictions and every gradient
+    tensor against the oracle.  The oracle runs on the same GPU in plain fp32 (TF32 off for matmul and cuDNN, no
+    autocast, "highest"), i.e. the same restatement the CPU tests pin, only on a device that finishes 290 k decoder
+    rows in well under a second.  Gradients here reduce over 72 k / 290 k rows through split-M weight-gradient GEMMs and
+    fp32 atomics, which the B<=64 CPU-oracle tests cannot exercise.
+    Tolerances: indices bit-exact; loss rel 2e-3; pred max-abs 3e-2; gradients cosine >= 0.999, rel-L2 <= 3e-2."""
+    B = 2000
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        o, m = make_pair(seed=73)
+        o = o.to("cuda")
+        g = torch.Generator(device="cuda").manual_seed(2000)
+        images = torch.randn(B, 3, 96, 96, device="cuda", generator=g)
+        noise = torch.rand(B, 145, device="cuda", generator=g)
+        loss, pred, _ = m.forward_loss(images, noise=noise)
+        m.engine.backward()
+        torch.cuda.synchronize()
+        l_ref, p_ref, _, g_ref = O.loss_and_grads(o, images, noise)
+        k_ref, m_ref = O.random_token_mask_from_noise(noise, 0.75)
+        ws = m.engine.ws
+        assert torch.equal(ws["idx_keep"], k_ref) and torch.equal(ws["idx_mask"], m_ref)
+        lrel = abs(loss.item() - l_ref.item()) / l_ref.item()
+        e, r = max_err(pred, p_ref), rel_err(pred, p_ref)
+        report("e2e_b2000", loss=loss.item(), ref=l_ref.item(), loss_rel=lrel, pred_max=e, pred_rel=r)
+        assert lrel < 2e-3 and e < 3e-2 and r < 1e-2
+        check_grads("e2e_b2000_grad", m.engine.named_grads(), {n: v.cpu() for n, v in g_ref.items()})
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+
+
 VITB = {"general": {"image_size": 224, "patch_size": 16, "in_chans": 3},
         "encoder": {"embed_dim": 768, "depth": 12, "num_heads": 12},
         "decoder": {"decoder_embed_dim": 512, "decoder_depth": 8, "decoder_num_heads": 16}}

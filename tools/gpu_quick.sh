@@ -1,7 +1,8 @@
 #!/bin/bash
 # quick check: full gpu test-suite + bench summary
 TAG=${1:-q}
-timeout 900 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/t_all.log 2>&1; echo "tests rc=$?"; tail -n 4 gpurun_out/t_all.log
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/t_all_$TAG.log 2>&1; echo "tests rc=$?"; tail -n 6 gpurun_out/t_all_$TAG.log
 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/bench_$TAG.log 2>&1; echo "bench rc=$?"
 python - <<PY
 import json
