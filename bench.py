@@ -143,6 +143,11 @@ def algorithmic_cost(name, a):
         out_b = {0: 2, 1: 4, 2: 4, 4: 2}[epi]            # bf16 | bf16 h + bf16 gelu' | fp32 | bf16
         aux_b = {0: 0, 1: 0, 2: 4, 4: 2}[epi]            # - | - | fp32 residual | bf16 gelu'
         return M * K * 2.0 + N * K * 2.0 + M * N * (out_b + aux_b), 2.0 * M * N * K, f"M={M} N={N} K={K} epi={epi}"
+    if name == "mae_mlp_fwd":
+        rows, D = a[4], a[5]
+        # read x, write xn + stats, h, gelu', x_out; weights once
+        return rows * D * (4.0 + 2 + 4) + rows * 8.0 + rows * 4 * D * 4.0 + 2 * 4 * D * D * 2.0, 2.0 * rows * D * 4 * D * 2, \
+            f"rows={rows} D={D}" + (" (gather)" if a[1] else "")
     if name == "mae_gemm_wgrad":
         Pc, Qc, M = a[1], a[3], a[4]
         return M * (Pc + Qc) * 2.0 + Pc * Qc * 4.0, 2.0 * M * Pc * Qc, f"M={M} P={Pc} Q={Qc}"

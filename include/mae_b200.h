@@ -98,6 +98,18 @@ int mae_layernorm_bwd_scatter(const void* g_bf16, const float* x, const float* m
 int mae_gemm_tn(const void* A_bf16, const void* B_bf16, int M, int N, int K, int epi, const float* bias, void* out,
                 void* pre_out_bf16, const void* aux, mae_stream_t stream);
 
+/* Second half of a timm Block, forward, in ONE launch:  x_out = x + fc2(GELU(fc1(LayerNorm(x))))  (timm Block.norm2 /
+ * Block.mlp as built at reference src/models/mae.py:28-36 and run at :54-55,71; replaces mae_layernorm_fwd +
+ * mae_gemm_tn(EPI_GELU) + mae_gemm_tn(EPI_RESID) and their HBM round trips of xn / h / the residual).
+ * x f32; if gather_idx != NULL, row r=(b,j) reads source row b*L_src + gather_idx[b*n_sel+j] and every output is
+ * compact (rows,*) (the masked-rows-only tail of the last decoder block).  w1 bf16 (4D,D), w2 bf16 (D,4D), biases f32.
+ * Saved for the backward: xn bf16 (rows,D), mean/rstd f32 (rows), h = GELU(pre) bf16 (rows,4D), dgelu = GELU'(pre) bf16
+ * (rows,4D) (pre = bf16(fc1 output), exactly as EPI_GELU).  x_out f32 (rows,D).  64 <= D <= 192, D % 16 == 0. */
+int mae_mlp_fwd(const float* x, const int64_t* gather_idx, int n_sel, int L_src, int rows, int D, const float* gamma,
+                const float* beta, float eps, const void* w1_bf16, const float* b1, const void* w2_bf16, const float* b2,
+                void* xn_bf16, float* mean, float* rstd, void* h_bf16, void* dgelu_bf16, float* x_out,
+                mae_stream_t stream);
+
 /* out[p*so_p + q*so_q] += sum_m P[m,p] * Q[m,q]: weight gradients (autograd of the Linears above).
  * P bf16 (M,Pc), Q bf16 (M,Qc), Qc % 16 == 0, Pc % 8 == 0.  fp32 atomics: zero `out` first.
  * If colsum != NULL the same launch also accumulates the bias gradient: colsum[c] += sum_m P[m,c]

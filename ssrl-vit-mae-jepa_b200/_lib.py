@@ -24,6 +24,7 @@ SIGNATURES = {
     "mae_layernorm_fwd_add": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp],
     "mae_layernorm_bwd_scatter": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "mae_gemm_tn": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "mae_mlp_fwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "mae_gemm_wgrad": [_vp, _i, _vp, _i, _i, _vp, _ll, _ll, _vp, _i, _vp],
     "mae_attention_fwd": [_vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "mae_attention_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],

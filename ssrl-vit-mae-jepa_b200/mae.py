@@ -199,6 +199,11 @@ class MAEEngine:
         # decoder-input assembly fused with the first decoder block's norm1: correct, but measured slower than the two
         # launches it replaces (8.27 vs 8.16 ms/step: 80 registers, dependent index -> pos loads), so opt-in only
         self.scatter_ln = os.environ.get("MAE_SCATTER_LN", "0") == "1"
+        # norm2 + fc1 + GELU + fc2 + residual as one tcgen05 kernel for D <= 192 (csrc/mlp_fused.cu).  Correct (GPU tests run
+        # it against the three launches and torch), moves 35 % fewer HBM bytes, but measured slower: the GELU table look-up
+        # epilogue is instruction-issue bound (~13 instructions per element at 16 epilogue warps), and LayerNorm / output
+        # epilogue run as serial phases of the same warps (profiles/r02_mlp_fused.md).  Opt-in: MAE_FUSED_MLP=1
+        self.fused_mlp = os.environ.get("MAE_FUSED_MLP", "0") == "1"
         self._side_skip = False
         self._side: Optional[torch.cuda.Stream] = None
         self._wg_pending: Dict[int, torch.cuda.Event] = {}
@@ -382,6 +387,9 @@ class MAEEngine:
     def _use_masked_tail(self) -> bool:
         return self.masked_tail and len(self.dec_blocks) > 0 and self.dims["Dd"] <= 256
 
+    def _use_fused_mlp(self, D: int) -> bool:
+        return self.fused_mlp and 64 <= D <= 192 and D % 16 == 0
+
     def _block_fwd(self, w: _BlockW, s: Dict[str, torch.Tensor], x_out: Optional[torch.Tensor], M: int, B: int, L: int,
                    st: int, tail: bool = False, skip_norm1: bool = False):
         """One pre-norm transformer block.  ``tail``: the last decoder block; norm2 and the MLP run on the idx_mask rows
@@ -396,6 +404,20 @@ class MAEEngine:
         calls.mae_attention_fwd(_ptr(s["qkv"]), B, L, H, hd, _ptr(s["att"]), _ptr(s["lse"]), st)
         calls.mae_gemm_tn(_ptr(s["att"]), self.pw(w.projw), M, D, D, EPI_RESID_F32, self.pf(w.projb),
                           _ptr(s["x_mid"]), None, _ptr(s["x_in"]), st)
+        if self._use_fused_mlp(D):
+            # norm2 -> fc1 -> GELU -> fc2 -> + residual in one launch (csrc/mlp_fused.cu); the tail variant gathers the
+            # idx_mask rows on the way in and leaves the compact fp32 sums  x_mid[idx_mask] + mlp(...)  in x_dec
+            ws, d = self.ws, self.dims
+            if tail:
+                calls.mae_mlp_fwd(_ptr(s["x_mid"]), _ptr(ws["idx_mask"]), d["Lm"], L, d["Mm"], D, self.pf(w.n2w),
+                                  self.pf(w.n2b), LN_EPS, self.pw(w.fc1w), self.pf(w.fc1b), self.pw(w.fc2w), self.pf(w.fc2b),
+                                  _ptr(s["xn2"]), _ptr(s["mean2"]), _ptr(s["rstd2"]), _ptr(s["h"]), _ptr(s["pre"]),
+                                  _ptr(ws["x_dec"]), st)
+            else:
+                calls.mae_mlp_fwd(_ptr(s["x_mid"]), None, 0, 0, M, D, self.pf(w.n2w), self.pf(w.n2b), LN_EPS,
+                                  self.pw(w.fc1w), self.pf(w.fc1b), self.pw(w.fc2w), self.pf(w.fc2b), _ptr(s["xn2"]),
+                                  _ptr(s["mean2"]), _ptr(s["rstd2"]), _ptr(s["h"]), _ptr(s["pre"]), _ptr(x_out), st)
+            return
         if tail:
             ws, d = self.ws, self.dims
             Mt = d["Mm"]
@@ -521,7 +543,12 @@ class MAEEngine:
             x_out = ws["dec"][i + 1]["x_in"] if i + 1 < n_dec else ws["x_dec"]
             self._block_fwd(w, ws["dec"][i], x_out, d["Md"], B, L, st, tail=tail and i == n_dec - 1,
                             skip_norm1=fused_ln and i == 0)
-        if tail:
+        if tail and self._use_fused_mlp(Dd):
+            # the fused MLP kernel already left the compact sums in x_dec: plain LayerNorm over Mm rows
+            calls.mae_layernorm_fwd(_ptr(ws["x_dec"]), self.pf(o("decoder.decoder_norm.weight")),
+                                    self.pf(o("decoder.decoder_norm.bias")), None, 0, 0, d["Mm"], Dd, LN_EPS,
+                                    _ptr(ws["xnd"]), _ptr(ws["meand"]), _ptr(ws["rstdd"]), st)
+        elif tail:
             # decoder_norm over  x_mid[idx_mask rows] + mlp output ; the summed rows (compact) are kept in x_dec for the backward
             calls.mae_layernorm_fwd_add(_ptr(ws["dec"][-1]["x_mid"]), _ptr(ws["dlt"]),
                                         self.pf(o("decoder.decoder_norm.weight")), self.pf(o("decoder.decoder_norm.bias")),

@@ -255,6 +255,65 @@ def test_gemm_tn_epilogues():
     assert e2 <= 2 ** -6 * dh_ref.abs().max().item()
 
 
+def _mlp_fwd(x, idx, n_sel, L_src, rows, D, gamma, beta, W1, b1, W2, b2):
+    xn = torch.empty(rows, D, dtype=torch.bfloat16, device=dev)
+    mean, rstd = torch.empty(rows, device=dev), torch.empty(rows, device=dev)
+    h = torch.empty(rows, 4 * D, dtype=torch.bfloat16, device=dev)
+    dact = torch.empty(rows, 4 * D, dtype=torch.bfloat16, device=dev)
+    y = torch.empty(rows, D, device=dev)
+    calls.mae_mlp_fwd(p(x), p(idx), n_sel, L_src, rows, D, p(gamma), p(beta), 1e-6, p(W1), p(b1), p(W2), p(b2), p(xn), p(mean),
+                      p(rstd), p(h), p(dact), p(y), stream())
+    return xn, mean, rstd, h, dact, y
+
+
+@pytest.mark.parametrize("rows,D,gather", [(1000, 192, False), (777, 144, False), (128, 64, False), (40000, 192, False),
+                                           (20001, 144, False), (5 * 109, 192, True), (300 * 109, 192, True), (2 * 109, 96, True)])
+def test_mlp_fwd_fused(rows, D, gather):
+    """mae_mlp_fwd (LayerNorm -> fc1 -> GELU -> fc2 -> + residual in one launch) against fp32 torch, step by step on the
+    kernel's own intermediate outputs (so each stage is checked to its own rounding), and against the three-launch path
+    (mae_layernorm_fwd + mae_gemm_tn EPI_GELU + mae_gemm_tn EPI_RESID) it replaces."""
+    g = torch.Generator().manual_seed(rows + D)
+    L_src, n_sel = (145, 109) if gather else (0, 0)
+    nsrc = (rows // n_sel) * L_src if gather else rows
+    x = (torch.randn(nsrc, D, generator=g) * 1.5 + 0.3).to(dev)
+    idx = None
+    if gather:
+        B = rows // n_sel
+        idx = torch.stack([torch.randperm(L_src, generator=g)[:n_sel] for _ in range(B)]).to(dev)  # (B, n_sel) int64
+        src_rows = (torch.arange(B, device=dev)[:, None] * L_src + idx).reshape(-1)
+        xs = x[src_rows]
+    else:
+        xs = x
+    gamma, beta = (1 + 0.1 * torch.randn(D, generator=g)).to(dev), (0.1 * torch.randn(D, generator=g)).to(dev)
+    W1, b1 = bf(torch.randn(4 * D, D, generator=g) / math.sqrt(D)).to(dev), (0.5 * torch.randn(4 * D, generator=g)).to(dev)
+    W2, b2 = bf(torch.randn(D, 4 * D, generator=g) / math.sqrt(4 * D)).to(dev), torch.randn(D, generator=g).to(dev)
+    xn, mean, rstd, h, dact, y = _mlp_fwd(x, idx, n_sel, L_src, rows, D, gamma, beta, W1, b1, W2, b2)
+    # LayerNorm (fp32 statistics, bf16 output)
+    mu = xs.mean(1)
+    rs = (xs.var(1, unbiased=False) + 1e-6).rsqrt()
+    assert max_err(mean, mu) < 1e-5 and rel_err(rstd, rs) < 1e-5
+    xn_ref = F.layer_norm(xs, (D,), gamma, beta, 1e-6)
+    assert max_err(xn, xn_ref) <= 2 ** -8 * xn_ref.abs().max().item() + 1e-6   # one bf16 rounding
+    # fc1 + GELU / GELU' on the kernel's own xn (pre = bf16(xn W1^T + b1))
+    pre_ref = bf(xn.float() @ W1.float().t() + b1).float().requires_grad_(True)
+    h_ref = F.gelu(pre_ref)
+    h_ref.sum().backward()
+    assert max_err(h, h_ref) <= 2 ** -7 * pre_ref.abs().max().item()
+    assert max_err(dact, pre_ref.grad) <= 2 ** -7 * 1.2 + 2e-2
+    # fc2 + bias + residual on the kernel's own h (fp32 accumulate, fp32 out)
+    y_ref = xs + h.float() @ W2.float().t() + b2
+    e = max_err(y, y_ref)
+    assert e < 2e-4 * max(1.0, y_ref.abs().max().item())
+    # the three launches it replaces
+    xn3 = torch.empty_like(xn); m3 = torch.empty_like(mean); r3 = torch.empty_like(rstd)
+    calls.mae_layernorm_fwd(p(x), p(gamma), p(beta), p(idx), n_sel, L_src, rows, D, 1e-6, p(xn3), p(m3), p(r3), stream())
+    h3, d3 = gemm_tn(xn3, W1, 1, b1)
+    y3, _ = gemm_tn(h3, W2, 2, b2, aux=xs.contiguous())
+    report("mlp_fwd_fused", rows=rows, D=D, gather=int(gather), y_err=e, xn_vs3=max_err(xn, xn3), h_vs3=rel_err(h, h3),
+           y_vs3=rel_err(y, y3))
+    assert rel_err(xn, xn3) < 1e-3 and rel_err(h, h3) < 5e-3 and rel_err(dact, d3) < 5e-3 and rel_err(y, y3) < 2e-3
+
+
 WGRAD_SHAPES = [(64, 128, 64), (1000, 432, 144), (1000, 144, 144), (5000, 768, 192), (70000, 576, 144), (333, 192, 192),
                 (218000, 192, 192), (3000, 2304, 768), (1000, 768, 512), (900, 512, 304)]
 

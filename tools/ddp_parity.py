@@ -6,7 +6,7 @@ ranks' noise concatenated in rank order.  Because the loss is a mean over equall
 equals the single-process gradient (reference `src/training/mae.py:45-50`, `configs/mae.yaml:27`), so after S steps:
   * all ranks hold bit-identical parameters (max |diff| must be exactly 0.0),
   * they equal the single-process parameters up to the summation order of the fp32 gradient reductions
-    (printed as rel-L2 per tensor; worst must be <= 1e-5 of the weight norm),
+    (rel-L2 per tensor, the zero-gradient K third of attn.qkv.bias excluded; worst must be <= 1e-5),
   * the mean of the per-rank losses equals the single-process loss (rel <= 1e-5).
 Prints one JSON line on rank 0 and exits non-zero on failure."""
 import argparse
@@ -67,8 +67,14 @@ def main() -> int:
         sd, sd1 = mod.model.state_dict(), mod1.model.state_dict()
         worst, worst_name = 0.0, ""
         for n in sd:
-            d = (sd[n].double() - sd1[n].double()).norm().item() / (sd1[n].double().norm().item() + 1e-30)
-            if sd1[n].double().norm().item() > 1e-6 and d > worst:
+            a, b = sd[n].double().flatten(), sd1[n].double().flatten()
+            if n.endswith("attn.qkv.bias"):
+                # softmax is invariant to a bias on the keys: the K third of qkv.bias has a mathematically ZERO gradient,
+                # what both runs compute there is rounding noise, which AdamW normalises to +-lr.  Compare Q and V only.
+                k = a.numel() // 3
+                a, b = torch.cat([a[:k], a[2 * k:]]), torch.cat([b[:k], b[2 * k:]])
+            d = (a - b).norm().item() / (b.norm().item() + 1e-30)
+            if b.norm().item() > 1e-6 and d > worst:
                 worst, worst_name = d, n
         loss_rel = max(abs(x - y) / abs(y) for x, y in zip(losses, losses1))
         ok = replica_maxdiff == 0.0 and worst <= 1e-5 and loss_rel <= 1e-5
