@@ -39,7 +39,11 @@ def main(argv=None):
     with open(output_dir / "config.yaml", "w") as f:
         yaml.safe_dump(cfg, f)
     train_loader, val_loader = get_train_dataloaders(cfg)
-    if args.encoder_ckpt is not None:
+    if args.classifier_ckpt is not None:
+        # weight initialisation from a full classifier checkpoint, like the reference's load_from_checkpoint(strict=False)
+        # (scripts/training/train_mae.py:85-91): takes precedence over --encoder_ckpt, training starts at epoch 0
+        module = ViTClassifierTrainModule.load_from_checkpoint(args.classifier_ckpt, map_location="cpu", strict=False)
+    elif args.encoder_ckpt is not None:
         mae = MaskedAutoencoder(model_cfg["general"], model_cfg["encoder"], model_cfg["decoder"])
         load_encoder_weights(mae.encoder, args.encoder_ckpt)
         module = ViTClassifierTrainModule(pretrained_encoder=mae.encoder.vit, model_cfg=model_cfg, training_cfg=train_cfg)
@@ -55,7 +59,7 @@ def main(argv=None):
     ckpt_last = ModelCheckpoint(ckpt_dir, "last", every_n_epochs=1)
     trainer = LiteTrainer(max_epochs=train_cfg["total_epochs"], callbacks=[ckpt_best, ckpt_last], gradient_clip_val=1.0,
                           limit_batches=args.limit_batches)
-    trainer.fit(module, train_loader, val_loader, ckpt_path=args.classifier_ckpt)
+    trainer.fit(module, train_loader, val_loader)
     model_path = output_dir / log_cfg["model_path"]
     torch.save(module.model.state_dict(), model_path)
     print(f"training complete; weights: {model_path}; best checkpoint: {ckpt_best.best_model_path}")

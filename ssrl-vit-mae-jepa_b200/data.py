@@ -2,9 +2,10 @@
 ``get_train_dataloaders``, ``get_test_dataloader``) and transforms (RandomResizedCrop(96, 0.8-1.0) + flip for
 training, Resize/CenterCrop for evaluation, ToTensor, Normalize(0.5, 0.5)).
 
-STL-10 cannot be downloaded in this environment (no network), so when the dataset is not already on disk under
-``data/`` -- or when ``MAE_SYNTHETIC_DATA=1`` -- a deterministic synthetic STL-10-shaped dataset (same sizes,
-value range [-1, 1] after normalisation, 10 classes) is used instead; everything downstream is unchanged.
+STL-10 is read from ``MAE_DATA_DIR`` (default ``data/``) and downloaded on first use like the reference.  This
+environment has no network, so the tests and benchmarks opt in to a deterministic synthetic STL-10-shaped dataset (same
+sizes, value range [-1, 1] after normalisation, 10 classes) with ``MAE_SYNTHETIC_DATA=1``; without that variable a missing
+dataset raises (no silent training on noise).
 
 ``<section>.gpu_augment: true`` in the YAML switches the loaders to raw uint8 batches; the trainer then applies the same
 transforms on the GPU (``GpuAugment`` -> ``mae_augment_u8``, bit-exact Pillow bilinear), which removes the CPU
@@ -17,7 +18,7 @@ import os
 from typing import Optional, Tuple
 
 import torch
-from torch.utils.data import DataLoader, Dataset, Subset, random_split
+from torch.utils.data import DataLoader, Dataset, Subset
 
 DATA_DIR = os.environ.get("MAE_DATA_DIR", "data")
 SPLIT_SIZES = {"unlabeled": 100_000, "train": 5_000, "test": 8_000}
@@ -136,6 +137,9 @@ class GpuAugment:
 
 
 def _real_stl10(split: str, train: bool, raw_uint8: bool = False):
+    """torchvision STL-10 with the reference's transforms, downloaded on first use exactly like the reference
+    (``src/data.py:60-65``).  The synthetic stand-in is used ONLY on the explicit opt-in ``MAE_SYNTHETIC_DATA=1``: a wrong
+    ``MAE_DATA_DIR``, a corrupt archive or a missing torchvision raises instead of silently training on noise."""
     if os.environ.get("MAE_SYNTHETIC_DATA") == "1":
         return None
     try:
@@ -143,17 +147,18 @@ def _real_stl10(split: str, train: bool, raw_uint8: bool = False):
         from torchvision.datasets import STL10
 
         if raw_uint8:
-            return RawSTL10(STL10(DATA_DIR, split=split, transform=None, download=False))
-
+            return RawSTL10(STL10(DATA_DIR, split=split, transform=None, download=True))
         if train:
             tf = transforms.Compose([transforms.RandomResizedCrop(96, scale=(0.8, 1.0)), transforms.RandomHorizontalFlip(),
                                      transforms.ToTensor(), transforms.Normalize((0.5,) * 3, (0.5,) * 3)])
         else:
             tf = transforms.Compose([transforms.Resize(96), transforms.CenterCrop(96), transforms.ToTensor(),
                                      transforms.Normalize((0.5,) * 3, (0.5,) * 3)])
-        return STL10(DATA_DIR, split=split, transform=tf, download=False)
-    except Exception:  # noqa: BLE001 - dataset not on disk / torchvision missing -> synthetic
-        return None
+        return STL10(DATA_DIR, split=split, transform=tf, download=True)
+    except Exception as e:  # noqa: BLE001
+        raise RuntimeError(f"STL-10 split '{split}' is not available under '{DATA_DIR}' and could not be downloaded ({e!r}); "
+                           "point MAE_DATA_DIR at the dataset, or set MAE_SYNTHETIC_DATA=1 to train on the synthetic "
+                           "STL-10-shaped stand-in on purpose") from e
 
 
 def _dataset(split: str, train: bool, synthetic_size: int | None = None, raw_uint8: bool = False):
@@ -161,8 +166,16 @@ def _dataset(split: str, train: bool, synthetic_size: int | None = None, raw_uin
     if ds is None:
         size = synthetic_size or int(os.environ.get("MAE_SYNTHETIC_SIZE", SPLIT_SIZES[split]))
         ds = SyntheticSTL10(split, train=train, size=size, raw_uint8=raw_uint8)
-        print(f"[data] STL-10 '{split}' split not found under '{DATA_DIR}': using {len(ds)} synthetic STL-10-shaped samples")
+        print(f"[data] MAE_SYNTHETIC_DATA=1: '{split}' split = {len(ds)} synthetic STL-10-shaped samples")
     return ds
+
+
+def _labels_of(ds) -> "np.ndarray":
+    import numpy as np
+
+    if isinstance(ds, SyntheticSTL10):
+        return np.arange(len(ds)) % 10
+    return np.asarray(ds.labels)
 
 
 def _loader(ds, batch_size: int, shuffle: bool, num_workers: int) -> DataLoader:
@@ -171,41 +184,49 @@ def _loader(ds, batch_size: int, shuffle: bool, num_workers: int) -> DataLoader:
 
 
 def get_pretrain_dataloaders(cfg: dict) -> Tuple[DataLoader, DataLoader]:
-    """Unlabeled split -> (train, val) loaders; keys ``pretrain.{batch_size,val_split,data_fraction,num_workers}``, ``seed``."""
+    """Unlabeled split -> (train, val) loaders; keys ``pretrain.{batch_size,val_split,data_fraction,num_workers}``, ``seed``
+    (reference ``src/data.py:45-106``).  The validation subset reads the SAME indices through a second dataset object
+    carrying the evaluation transform (the reference ends up validating with the eval transform, ``src/data.py:81``),
+    while training keeps RandomResizedCrop + flip."""
     pre, seed = cfg["pretrain"], cfg.get("seed", 73)
-    full = _dataset("unlabeled", train=True, raw_uint8=bool(pre.get("gpu_augment", False)))
+    raw = bool(pre.get("gpu_augment", False))
+    full_train = _dataset("unlabeled", train=True, raw_uint8=raw)
+    full_eval = full_train if raw else _dataset("unlabeled", train=False, raw_uint8=raw)  # raw uint8: the trainer picks the transform
+    n_full = len(full_train)
     frac = pre.get("data_fraction", 1.0)
-    if frac < 1.0:
-        full = Subset(full, range(int(len(full) * frac)))
-    n_val = int(len(full) * pre.get("val_split", 0.1))
-    train_ds, val_ds = random_split(full, [len(full) - n_val, n_val], generator=torch.Generator().manual_seed(seed))
+    n = int(n_full * frac) if frac < 1.0 else n_full
+    n_val = int(n * pre.get("val_split", 0.1))
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(seed)).tolist()  # == random_split's permutation
+    train_ds, val_ds = Subset(full_train, perm[:n - n_val]), Subset(full_eval, perm[n - n_val:])
     bs, nw = pre.get("batch_size", 512), pre.get("num_workers", 4)
     print(f"[data] unlabeled pretrain split: {len(train_ds)} train, {n_val} val")
     return _loader(train_ds, bs, True, nw), _loader(val_ds, bs, False, nw)
 
 
 def get_train_dataloaders(cfg: dict) -> Tuple[DataLoader, DataLoader]:
-    """Labeled train split -> (train, val): ``train.samples_per_class`` images per class for training, the rest for
-    validation (reference ``src/data.py:109-164``)."""
+    """Labeled train split -> (train, val): per class, the indices are shuffled with ``numpy.random.default_rng(seed)``
+    and the first ``train.samples_per_class`` go to training, the rest to validation -- the same membership as the
+    reference (``src/data.py:128-139``); validation reads through the evaluation transform."""
+    import numpy as np
+
     tr, seed = cfg["train"], cfg.get("seed", 73)
-    full = _dataset("train", train=True, raw_uint8=bool(tr.get("gpu_augment", False)))
+    raw = bool(tr.get("gpu_augment", False))
+    full_train = _dataset("train", train=True, raw_uint8=raw)
+    full_eval = full_train if raw else _dataset("train", train=False, raw_uint8=raw)
+    labels = _labels_of(full_train)
     per_class = int(tr.get("samples_per_class", 400))
-    g = torch.Generator().manual_seed(seed)
-    order = torch.randperm(len(full), generator=g).tolist()
-    labels = [full[i][1] if isinstance(full, SyntheticSTL10) else int(full.labels[i]) for i in order]  # RawSTL10 has .labels too
-    taken, train_idx, val_idx = {}, [], []
-    for i, y in zip(order, labels):
-        if taken.get(y, 0) < per_class:
-            taken[y] = taken.get(y, 0) + 1
-            train_idx.append(i)
-        else:
-            val_idx.append(i)
-    bs, nw = tr.get("batch_size", 512), tr.get("num_workers", 4)
+    train_idx, val_idx = [], []
+    for c in np.unique(labels):
+        cls_idx = np.where(labels == c)[0]
+        np.random.default_rng(seed).shuffle(cls_idx)
+        train_idx.extend(int(i) for i in cls_idx[:per_class])
+        val_idx.extend(int(i) for i in cls_idx[per_class:])
+    bs, nw = tr.get("batch_size", 256), tr.get("num_workers", 4)
     print(f"[data] labeled split: {len(train_idx)} train, {len(val_idx)} val")
-    return _loader(Subset(full, train_idx), bs, True, nw), _loader(Subset(full, val_idx or train_idx[:1]), bs, False, nw)
+    return _loader(Subset(full_train, train_idx), bs, True, nw), _loader(Subset(full_eval, val_idx or train_idx[:1]), bs, False, nw)
 
 
 def get_test_dataloader(cfg: dict) -> DataLoader:
     te = cfg.get("test", {})
-    return _loader(_dataset("test", train=False, raw_uint8=bool(te.get("gpu_augment", False))), te.get("batch_size", 512), False,
+    return _loader(_dataset("test", train=False, raw_uint8=bool(te.get("gpu_augment", False))), te.get("batch_size", 256), False,
                    te.get("num_workers", 4))

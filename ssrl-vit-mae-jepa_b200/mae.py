@@ -230,12 +230,8 @@ class MAEEngine:
                 return False
         return True
 
-    def _ensure_flat(self, device: torch.device) -> None:
-        if self._flat_is_current(device):
-            return
-        if device.type != "cuda":
-            raise RuntimeError("MaskedAutoencoder runs only on CUDA (sm_100a); there is no CPU fallback")
-        _lib.load()
+    def _compute_layout(self) -> None:
+        """Element offsets of every parameter inside the flat buffers (host-only bookkeeping: no device memory)."""
         params = self._ordered_params()
         self._param_list = params
         off, self.offsets, self.n_opt = 0, {}, None
@@ -247,6 +243,16 @@ class MAEEngine:
         self.n_total = off
         if self.n_opt is None:
             self.n_opt = off
+        self._index_blocks()
+
+    def _ensure_flat(self, device: torch.device) -> None:
+        if self._flat_is_current(device):
+            return
+        if device.type != "cuda":
+            raise RuntimeError("MaskedAutoencoder runs only on CUDA (sm_100a); there is no CPU fallback")
+        _lib.load()
+        self._compute_layout()
+        params, off = self._param_list, self.n_total
         flat = torch.zeros(off, dtype=torch.float32, device=device)
         old_m = getattr(self, "exp_avg", None)
         for n, p in params:
@@ -272,7 +278,6 @@ class MAEEngine:
         self.t_table = torch.tensor(rows, dtype=torch.int64, device=device)
         self.t_max_rows, self.t_max_cols = max(r[1] for r in rows), max(r[2] for r in rows)
         self._shadow_fresh, self._shadow_version = False, None
-        self._index_blocks()
 
     def _o(self, name: str) -> int:
         return self.offsets[name]
@@ -494,7 +499,18 @@ class MAEEngine:
         calls.mae_layernorm_fwd(_ptr(ws["x_enc"]), self.pf(o(ep + "norm.weight")), self.pf(o(ep + "norm.bias")),
                                 None, 0, 0, d["Me"], De, LN_EPS, _ptr(ws["xnf"]), _ptr(ws["meanf"]), _ptr(ws["rstdf"]), st)
 
-    def _encoder_bwd(self, g_ptr: int, cur, curb, nxt, nxtb, st: int, first_block: int = 0, stem: bool = True):
+    def grad_bucket_boundaries(self) -> List[int]:
+        """Offsets into ``self.grads`` that cut it into one bucket per transformer block, in parameter order: encoder
+        bucket 0 = stem + block 0, the last encoder bucket also holds ``vit.norm``; decoder bucket 0 = mask token +
+        ``decoder_embed`` + block 0, the last one also holds ``decoder_norm`` / ``decoder_pred``.  Backward completes them
+        from the last to the first (see :meth:`backward`)."""
+        b = [0] + [w.n1w for w in self.enc_blocks[1:]]
+        if self.dec_blocks:
+            b += [self._o("decoder.mask_token")] + [w.n1w for w in self.dec_blocks[1:]]
+        return b + [self.n_opt]
+
+    def _encoder_bwd(self, g_ptr: int, cur, curb, nxt, nxtb, st: int, first_block: int = 0, stem: bool = True,
+                     bucket_cb=None):
         """Backward of ``vit.norm`` + encoder blocks [first_block:] (+ cls_token / patch-embed when ``stem``), given
         the bf16 gradient ``g`` w.r.t. the normalised encoder output.  The result lands in ``cur``-style buffers."""
         ws, d = self.ws, self.dims
@@ -510,12 +526,16 @@ class MAEEngine:
         for i in reversed(range(first_block, len(self.enc_blocks))):
             self._block_bwd(self.enc_blocks[i], ws["enc"][i], cur, curb, nxt, nxtb, Me, B, Lk, st)
             cur, curb, nxt, nxtb = nxt, nxtb, cur, curb
+            if bucket_cb is not None and i >= 1:
+                bucket_cb(i)  # everything that writes this block's gradients is enqueued (main + side stream)
         if stem and first_block == 0:
             # tokens = cat(cls, patch_embed(kept patches)) + frozen pos
             calls.mae_colsum_rows_f32(_ptr(cur), None, B, 1, Lk, 0, De, self.pg(o(ep + "cls_token")), st)
             calls.mae_gather_rows_bf16(_ptr(cur), None, B, Lk - 1, Lk, 1, De, _ptr(ws["dtok"]), st)
             self._linear_bwd_w(_ptr(ws["dtok"]), De, _ptr(ws["patches"]), pd, B * (Lk - 1),
                                o(ep + "patch_embed.proj.weight"), o(ep + "patch_embed.proj.bias"), st)
+        if bucket_cb is not None and first_block == 0:
+            bucket_cb(0)
         self._wg_join()
         return cur
 
@@ -660,9 +680,10 @@ class MAEEngine:
 
     def backward(self, dpred: Optional[torch.Tensor] = None, bucket_cb=None) -> None:
         """Gradients of all trainable parameters into ``self.grads`` (zeroed first).  ``dpred`` defaults to
-        the MSE gradient produced by the fused loss kernel in :meth:`forward`.  ``bucket_cb("decoder")`` /
-        ``bucket_cb("encoder")`` fire as soon as that half of the flat gradient buffer is complete (the
-        data-parallel trainer starts the bucket's all-reduce there, overlapping the rest of backward)."""
+        the MSE gradient produced by the fused loss kernel in :meth:`forward`.  ``bucket_cb(i)`` fires, from the last
+        bucket of :meth:`grad_bucket_boundaries` to the first, as soon as every launch that writes bucket ``i`` has been
+        enqueued -- on the main stream or on the weight-gradient side stream (``self._side``): the data-parallel trainer
+        starts the bucket's all-reduce behind both, so all but the stem + first-block bucket overlap the rest of backward."""
         ws, d = self.ws, self.dims
         B, L, Lk, Lm, De, Dd, pd = d["B"], d["L"], d["Lk"], d["Lm"], d["De"], d["Dd"], d["pd"]
         Me, Md, Mm = d["Me"], d["Md"], d["Mm"]
@@ -702,10 +723,13 @@ class MAEEngine:
                                     self.pg(o("decoder.decoder_norm.bias")), st)
         cur, curb, nxt, nxtb = dx_a, dxb_a, dx_b, dxb_b
         n_dec = len(self.dec_blocks)
+        n_enc = len(self.enc_blocks)
         for i in reversed(range(n_dec)):
             self._block_bwd(self.dec_blocks[i], ws["dec"][i], cur, curb, nxt, nxtb, Md, B, L, st,
                             tail=tail and i == n_dec - 1)
             cur, curb, nxt, nxtb = nxt, nxtb, cur, curb
+            if bucket_cb is not None and i >= 1:
+                bucket_cb(n_enc + i)
         # decoder input = scatter(embed) / mask_token, + frozen pos
         st2 = self._side_begin(st, extra=True)
         calls.mae_colsum_rows_f32(_ptr(cur), _ptr(ws["idx_mask"]), B, Lm, L, 0, Dd, self.pg(o("decoder.mask_token")), st2)
@@ -714,13 +738,10 @@ class MAEEngine:
         self._linear_bwd_w(_ptr(ws["demb"]), Dd, _ptr(ws["xnf"]), De, Me, o("decoder.decoder_embed.weight"),
                            o("decoder.decoder_embed.bias"), st)
         if bucket_cb is not None:
-            self._wg_join()  # the decoder half of the gradient buffer is complete behind this point
-            bucket_cb("decoder")
+            bucket_cb(n_enc)  # mask token + decoder_embed + decoder block 0
         calls.mae_gemm_tn(_ptr(ws["demb"]), self.pwt(o("decoder.decoder_embed.weight")), Me, De, Dd, EPI_BF16, None,
                           _ptr(ws["g"]), None, None, st)
-        self._encoder_bwd(_ptr(ws["g"]), cur, curb, nxt, nxtb, st)
-        if bucket_cb is not None:
-            bucket_cb("encoder")
+        self._encoder_bwd(_ptr(ws["g"]), cur, curb, nxt, nxtb, st, bucket_cb=bucket_cb)
 
     # ---------------- optimizer ----------------
     def clip_adamw(self, lr: float, weight_decay: float = 0.05, betas=(0.9, 0.999), eps: float = 1e-8,

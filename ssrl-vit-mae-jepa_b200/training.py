@@ -2,10 +2,9 @@
 
 ``MAEPretrainModule`` keeps the reference constructor ``(model_cfg, training_cfg)``, attributes, and the
 ``forward / training_step / validation_step / configure_optimizers / on_train_epoch_start`` methods
-(reference ``src/training/mae.py:14-83``).  When ``pytorch_lightning`` is importable it subclasses
-``pl.LightningModule`` exactly like the reference; this image does not ship it, so a tiny stand-in base
-with the handful of members the module touches (``save_hyperparameters``, ``log``, ``current_epoch``) is
-used instead.
+(reference ``src/training/mae.py:14-83``) and subclasses ``pl.LightningModule`` exactly like the reference: the real
+``pytorch_lightning`` when it is installed, else the stand-in under ``shims/`` with the members the module touches
+(``save_hyperparameters``, ``log``, ``current_epoch``, ``load_from_checkpoint``).
 
 ``FusedTrainer`` is the B200 fast path for the same step: forward + masked MSE + backward + (bucketed
 NCCL all-reduce overlapped with the encoder backward) + clip(1.0) + AdamW, all through the C ABI, with no
@@ -22,28 +21,12 @@ from torch.optim.lr_scheduler import LambdaLR
 
 from .mae import MaskedAutoencoder
 
-try:  # pragma: no cover - not installed in this image
-    import pytorch_lightning as pl
+from .shims import install as _install_shims
 
-    _Base = pl.LightningModule
-except Exception:  # noqa: BLE001
+_install_shims()  # appended to sys.path: only found when the real packages are absent
+import pytorch_lightning as pl  # noqa: E402  (the real package, or shims/pytorch_lightning)
 
-    class _Base(torch.nn.Module):  # minimal LightningModule surface used by the reference module
-        def __init__(self):
-            super().__init__()
-            self.current_epoch = 0
-            self.logged: Dict[str, Any] = {}
-            self.hparams: Dict[str, Any] = {}
-
-        def save_hyperparameters(self, ignore=(), **kw):
-            import inspect
-
-            frame = inspect.currentframe().f_back
-            skip = {"self", "__class__", *([ignore] if isinstance(ignore, str) else ignore)}
-            self.hparams = {k: v for k, v in frame.f_locals.items() if k not in skip}
-
-        def log(self, name: str, value, **kw):
-            self.logged[name] = value
+_Base = pl.LightningModule
 
 
 def mask_ratio_for_epoch(epoch: int, start: float, end: float, ramp_epochs: int) -> float:
@@ -161,6 +144,7 @@ class FusedTrainer:
         self.distributed = (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) \
             if distributed is None else distributed
         self._buckets: Optional[GradBuckets] = None
+        self._comm_trigger = None
 
     def set_epoch(self, epoch: int) -> None:
         self.epoch = epoch
@@ -173,9 +157,26 @@ class FusedTrainer:
     def _ensure_buckets(self) -> GradBuckets:
         eng = self.engine
         if self._buckets is None or self._buckets.flat.data_ptr() != eng.grads.data_ptr():
-            split = eng.offsets["decoder.mask_token"]  # encoder params [0, split), decoder params [split, n_opt)
-            self._buckets = GradBuckets(eng.grads, [0, split, eng.n_opt])
+            # one bucket per transformer block (6 for configs/mae.yaml), completed back to front by backward(): only the
+            # stem + first encoder block bucket (1.1 MB) is still in flight when backward ends
+            self._buckets = GradBuckets(eng.grads, eng.grad_bucket_boundaries())
         return self._buckets
+
+    def _launch_bucket(self, i: int) -> None:
+        """Starts bucket ``i``'s all-reduce behind everything enqueued so far on the compute stream AND on the engine's
+        weight-gradient side stream, without making the compute stream wait for the side stream."""
+        eng, dev = self.engine, self.engine.flat.device
+        if self._comm_trigger is None:
+            self._comm_trigger = torch.cuda.Stream(dev) if dev.type == "cuda" else False
+        if self._comm_trigger is False:  # CPU tensors (gloo tests)
+            self._buckets.launch(i)
+            return
+        cs = self._comm_trigger
+        cs.wait_stream(torch.cuda.current_stream(dev))
+        if eng._side is not None:
+            cs.wait_stream(eng._side)
+        with torch.cuda.stream(cs):
+            self._buckets.launch(i)
 
     def train_step(self, images: torch.Tensor, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One optimisation step; returns the 0-dim device loss tensor (no host sync)."""
@@ -183,9 +184,9 @@ class FusedTrainer:
         _, _, loss = eng.forward(images, noise, self.model.mask_ratio)
         if self.distributed:
             eng._ensure_flat(images.device)
-            buckets = self._ensure_buckets()
-            eng.backward(bucket_cb=lambda which: buckets.launch(1 if which == "decoder" else 0))
-            buckets.finish()
+            self._ensure_buckets()
+            eng.backward(bucket_cb=self._launch_bucket)
+            self._buckets.finish()  # the compute stream waits for every bucket's collective
         else:
             eng.backward()
         eng.clip_adamw(self.current_lr(), weight_decay=self.module.weight_decay, max_norm=self.max_norm)
