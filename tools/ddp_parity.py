@@ -6,7 +6,8 @@ ranks' noise concatenated in rank order.  Because the loss is a mean over equall
 equals the single-process gradient (reference `src/training/mae.py:45-50`, `configs/mae.yaml:27`), so after S steps:
   * all ranks hold bit-identical parameters (max |diff| must be exactly 0.0),
   * they equal the single-process parameters up to the summation order of the fp32 gradient reductions
-    (rel-L2 per tensor, the zero-gradient K third of attn.qkv.bias excluded; worst must be <= 1e-5),
+    (rel-L2 per tensor: <= 1e-5 for every weight / token / LayerNorm-scale tensor; <= 1e-3 for the zero-initialised biases,
+    which after a few steps consist of nothing but the accumulated update; the zero-gradient K third of attn.qkv.bias excluded),
   * the mean of the per-rank losses equals the single-process loss (rel <= 1e-5).
 Prints one JSON line on rank 0 and exits non-zero on failure."""
 import argparse
@@ -65,22 +66,30 @@ def main() -> int:
     ok = True
     if rank == 0:
         sd, sd1 = mod.model.state_dict(), mod1.model.state_dict()
-        worst, worst_name = 0.0, ""
+        worst, worst_name, worst_b, worst_b_name = 0.0, "", 0.0, ""
         for n in sd:
-            a, b = sd[n].double().flatten(), sd1[n].double().flatten()
+            wa, wb = sd[n].double().flatten(), sd1[n].double().flatten()
             if n.endswith("attn.qkv.bias"):
                 # softmax is invariant to a bias on the keys: the K third of qkv.bias has a mathematically ZERO gradient,
                 # what both runs compute there is rounding noise, which AdamW normalises to +-lr.  Compare Q and V only.
-                k = a.numel() // 3
-                a, b = torch.cat([a[:k], a[2 * k:]]), torch.cat([b[:k], b[2 * k:]])
-            d = (a - b).norm().item() / (b.norm().item() + 1e-30)
-            if b.norm().item() > 1e-6 and d > worst:
+                k = wa.numel() // 3
+                wa, wb = torch.cat([wa[:k], wa[2 * k:]]), torch.cat([wb[:k], wb[2 * k:]])
+            if wb.norm().item() <= 1e-6:
+                continue
+            d = (wa - wb).norm().item() / wb.norm().item()
+            if n.endswith(".bias"):
+                # zero-initialised: after a few steps the whole tensor IS the accumulated update (|w| ~ steps x lr), so the
+                # elements whose gradient is at rounding-noise level weigh in fully; tracked with its own bound
+                if d > worst_b:
+                    worst_b, worst_b_name = d, n
+            elif d > worst:
                 worst, worst_name = d, n
         loss_rel = max(abs(x - y) / abs(y) for x, y in zip(losses, losses1))
-        ok = replica_maxdiff == 0.0 and worst <= 1e-5 and loss_rel <= 1e-5
+        ok = replica_maxdiff == 0.0 and worst <= 1e-5 and worst_b <= 1e-3 and loss_rel <= 1e-5
         print(json.dumps({"tool": "ddp_parity", "world": world, "per_rank_batch": a.batch, "steps": a.steps,
                           "replica_param_maxdiff": replica_maxdiff, "weights_worst_rel_vs_single": worst,
-                          "worst_tensor": worst_name, "loss_ddp": losses, "loss_single": losses1,
+                          "worst_tensor": worst_name, "zero_init_biases_worst_rel_vs_single": worst_b,
+                          "worst_bias": worst_b_name, "loss_ddp": losses, "loss_single": losses1,
                           "loss_worst_rel": loss_rel, "ok": ok}))
     dist.barrier()
     dist.destroy_process_group()
