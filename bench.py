@@ -175,6 +175,12 @@ def algorithmic_cost(name, a):
     if name == "mae_gather_patches":
         B, C, patch, nk = a[2], a[3], a[5], a[6]
         return B * (nk - 1) * C * patch * patch * 6.0, 0.0, f"B={B} kept={nk - 1}"
+    if name == "mae_patch_embed_tokens":
+        B, C, patch, nk, D = a[2], a[3], a[5], a[6], a[7]
+        pd = C * patch * patch
+        rows = B * (nk - 1)
+        # read the kept patches (fp32), write the im2col rows (bf16) and the fp32 stream incl. class-token rows; weight once
+        return rows * pd * 6.0 + B * nk * D * 4.0 + D * pd * 2.0, 2.0 * rows * D * pd, f"B={B} kept={nk - 1} D={D}"
     if name == "mae_assemble_tokens":
         B, nk, D = a[4], a[5], a[6]
         return B * nk * D * 6.0, 0.0, f"B={B} kept={nk} D={D}"

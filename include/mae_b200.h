@@ -57,6 +57,16 @@ int mae_random_token_mask(const float* noise, int B, int L, int num_keep, int64_
 int mae_gather_patches(const float* images, const int64_t* idx_keep, int B, int C, int img, int patch, int num_keep,
                        void* patches_bf16, mae_stream_t stream);
 
+/* Patch embedding of the kept tokens in ONE launch (timm PatchEmbed -> cat(cls_token) -> + pos_embed -> get_at_index,
+ * reference src/models/mae.py:54-55; replaces mae_gather_patches + mae_gemm_tn + mae_assemble_tokens): the im2col rows are
+ * gathered straight into the A tile of a tcgen05 GEMM (W (D, C*patch*patch) bf16 resident in shared memory) and the
+ * epilogue writes  x (B,num_keep,D) f32 = bf16(patch . W^T + bias) + pos[idx_keep], class-token rows (cls + pos) included.
+ * patches_bf16 (B*(num_keep-1), C*patch*patch) is written as by mae_gather_patches (the weight gradient reads it).
+ * patch % 4 == 0, C*patch*patch <= 256 and % 16 == 0, D <= 256 and % 16 == 0. */
+int mae_patch_embed_tokens(const float* images, const int64_t* idx_keep, int B, int C, int img, int patch, int num_keep,
+                           int D, const void* w_bf16, const float* bias, const float* cls, const float* pos,
+                           void* patches_bf16, float* x, mae_stream_t stream);
+
 /* cat(cls_token, tokens) + pos_embed restricted to kept tokens (lightly MaskedVisionTransformerTIMM.
  * preprocess + get_at_index; reference src/models/mae.py:55): x (B,num_keep,D) f32. */
 int mae_assemble_tokens(const void* tok_bf16, const float* cls, const float* pos, const int64_t* idx_keep, int B,

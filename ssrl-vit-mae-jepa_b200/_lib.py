@@ -18,6 +18,7 @@ _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 SIGNATURES = {
     "mae_random_token_mask": [_vp, _i, _i, _i, _vp, _vp, _vp],
     "mae_gather_patches": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "mae_patch_embed_tokens": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "mae_assemble_tokens": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "mae_layernorm_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp],
     "mae_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],

@@ -204,6 +204,8 @@ class MAEEngine:
         # epilogue is instruction-issue bound (~13 instructions per element at 16 epilogue warps), and LayerNorm / output
         # epilogue run as serial phases of the same warps (profiles/r02_mlp_fused.md).  Opt-in: MAE_FUSED_MLP=1
         self.fused_mlp = os.environ.get("MAE_FUSED_MLP", "0") == "1"
+        # patch gather + patch-embed GEMM + bias / pos / class-token assembly in one launch (MAE_FUSED_PATCH_EMBED=0: three)
+        self.fused_patch_embed = os.environ.get("MAE_FUSED_PATCH_EMBED", "1") != "0"
         self._side_skip = False
         self._side: Optional[torch.cuda.Stream] = None
         self._wg_pending: Dict[int, torch.cuda.Event] = {}
@@ -485,14 +487,22 @@ class MAEEngine:
         pe = self._vit().patch_embed
         B, Lk, De = d["B"], d["Lk"], d["De"]
         o, ep = self._o, self.EP
-        calls.mae_gather_patches(images.data_ptr(), idx_keep.data_ptr(), B, pe.in_chans, pe.img_size, pe.patch_size, Lk,
-                                 _ptr(ws["patches"]), st)
-        calls.mae_gemm_tn(_ptr(ws["patches"]), self.pw(o(ep + "patch_embed.proj.weight")), B * (Lk - 1), De,
-                          d["pd"], EPI_BF16, self.pf(o(ep + "patch_embed.proj.bias")), _ptr(ws["tok"]), None,
-                          None, st)
         x0 = ws["enc"][0]["x_in"] if self.enc_blocks else ws["x_enc"]
-        calls.mae_assemble_tokens(_ptr(ws["tok"]), self.pf(o(ep + "cls_token")), self.pf(o(ep + "pos_embed")),
-                                  idx_keep.data_ptr(), B, Lk, De, _ptr(x0), st)
+        if self.fused_patch_embed and d["pd"] <= 256 and De <= 256 and pe.patch_size % 4 == 0 and \
+                (d["pd"] // 64 + (d["pd"] % 64 > 0)) * (De * 128 + 2 * 16384) <= 220 * 1024:
+            # gather -> tcgen05 GEMM -> + bias, + pos, class-token rows: one launch (csrc/patch_embed.cu)
+            calls.mae_patch_embed_tokens(images.data_ptr(), idx_keep.data_ptr(), B, pe.in_chans, pe.img_size, pe.patch_size,
+                                         Lk, De, self.pw(o(ep + "patch_embed.proj.weight")),
+                                         self.pf(o(ep + "patch_embed.proj.bias")), self.pf(o(ep + "cls_token")),
+                                         self.pf(o(ep + "pos_embed")), _ptr(ws["patches"]), _ptr(x0), st)
+        else:
+            calls.mae_gather_patches(images.data_ptr(), idx_keep.data_ptr(), B, pe.in_chans, pe.img_size, pe.patch_size, Lk,
+                                     _ptr(ws["patches"]), st)
+            calls.mae_gemm_tn(_ptr(ws["patches"]), self.pw(o(ep + "patch_embed.proj.weight")), B * (Lk - 1), De,
+                              d["pd"], EPI_BF16, self.pf(o(ep + "patch_embed.proj.bias")), _ptr(ws["tok"]), None,
+                              None, st)
+            calls.mae_assemble_tokens(_ptr(ws["tok"]), self.pf(o(ep + "cls_token")), self.pf(o(ep + "pos_embed")),
+                                      idx_keep.data_ptr(), B, Lk, De, _ptr(x0), st)
         for i, w in enumerate(self.enc_blocks):
             x_out = ws["enc"][i + 1]["x_in"] if i + 1 < len(self.enc_blocks) else ws["x_enc"]
             self._block_fwd(w, ws["enc"][i], x_out, d["Me"], B, Lk, st)

@@ -84,6 +84,37 @@ def test_gather_patches_and_assemble():
     assert max_err(x, full) < 1e-6
 
 
+@pytest.mark.parametrize("B,C,img,patch,Lk,D", [(7, 3, 96, 8, 36, 144), (300, 3, 96, 8, 36, 144), (5, 3, 96, 8, 73, 144),
+                                                (9, 3, 32, 4, 17, 64), (4, 1, 64, 16, 9, 128), (2000, 3, 96, 8, 36, 144)])
+def test_patch_embed_tokens_fused(B, C, img, patch, Lk, D):
+    """mae_patch_embed_tokens (gather -> tcgen05 GEMM -> + bias, + pos, class-token rows in one launch): the im2col rows
+    bit for bit against F.unfold, and the fp32 stream bit for bit against the three launches it replaces
+    (mae_gather_patches + mae_gemm_tn + mae_assemble_tokens: same bf16 operands, same accumulation, same rounding points)."""
+    g = torch.Generator().manual_seed(B + D)
+    L = (img // patch) ** 2 + 1
+    pd = C * patch * patch
+    images = torch.randn(B, C, img, img, generator=g).to(dev)
+    k = torch.stack([torch.cat([torch.zeros(1, dtype=torch.int64), 1 + torch.randperm(L - 1, generator=g)[:Lk - 1]])
+                     for _ in range(B)]).to(dev)
+    W, bias = bf(torch.randn(D, pd, generator=g) / math.sqrt(pd)).to(dev), torch.randn(D, generator=g).to(dev)
+    cls, pos = torch.randn(D, generator=g).to(dev), torch.randn(L, D, generator=g).to(dev)
+    patches = torch.zeros(B * (Lk - 1), pd, dtype=torch.bfloat16, device=dev)
+    x = torch.full((B, Lk, D), float("nan"), device=dev)
+    calls.mae_patch_embed_tokens(p(images), p(k), B, C, img, patch, Lk, D, p(W), p(bias), p(cls), p(pos), p(patches), p(x),
+                                 stream())
+    unf = F.unfold(images, kernel_size=patch, stride=patch).transpose(1, 2)  # (B, L-1, pd) in conv-weight order (c,py,px)
+    ref = torch.gather(unf, 1, (k[:, 1:] - 1).unsqueeze(-1).expand(-1, -1, pd)).reshape(-1, pd)
+    assert torch.equal(patches, bf(ref))
+    p3 = torch.empty_like(patches)
+    calls.mae_gather_patches(p(images), p(k), B, C, img, patch, Lk, p(p3), stream())
+    tok, _ = gemm_tn(p3, W, 0, bias)
+    x3 = torch.empty(B, Lk, D, device=dev)
+    calls.mae_assemble_tokens(p(tok), p(cls), p(pos), p(k), B, Lk, D, p(x3), stream())
+    assert torch.equal(x, x3), max_err(x, x3)
+    full = torch.cat([cls.expand(B, 1, D), bf(ref.float() @ W.float().t() + bias).float().view(B, Lk - 1, D)], 1) + pos[k]
+    assert max_err(x, full) <= 2 ** -7 * full.abs().max().item()  # vs fp32 torch: one bf16 rounding of the conv output
+
+
 @pytest.mark.parametrize("rows,D", [(1000, 144), (777, 192), (5, 16), (300, 256), (500, 512), (401, 768), (97, 1024)])
 def test_layernorm_fwd_bwd(rows, D):
     g = torch.Generator().manual_seed(rows)
