@@ -32,6 +32,23 @@ PRETRAIN = {"mask_ratio_start": 0.75, "mask_ratio_end": 0.75, "mask_ramp_epochs"
             "warmup_epochs": 20, "batch_size": 2000, "base_learning_rate": 1.5e-4, "weight_decay": 0.05}
 
 
+VITB_CFG = {  # BASELINE.json configs[4]: ViT-B/16 MAE stress config (decoder = MAE paper's 512-d x 8 x 16 heads)
+    "general": {"image_size": 224, "patch_size": 16, "in_chans": 3},
+    "encoder": {"embed_dim": 768, "depth": 12, "num_heads": 12},
+    "decoder": {"decoder_embed_dim": 512, "decoder_depth": 8, "decoder_num_heads": 16},
+}
+WORKLOADS = {
+    # name: (model cfg, image size, default batch / GPU, algorithmic FLOPs per image fwd+bwd, label)
+    "mae": (CFG, 96, 2000, FLOPS_PER_IMAGE,
+            "configs/mae.yaml MAE pretrain step (96px, 8px patches, 144-d x4 enc, 192-d x2 dec)"),
+    "vitb16": (VITB_CFG, 224, 256, 57_468_000_000,
+               "ViT-B/16 MAE stress config (224px, 196 patches, 768-d x12 x12h enc, 512-d x8 x16h dec)"),
+}
+# classifier (BASELINE.json configs[3]): encoder forward_features over all 145 tokens + CLS head; fwd 345.3 MFLOP / image
+# (4 blocks x 84.3 M + patch embed 8.0 M), x3 with the backward of a full fine-tune
+CLS_FLOPS_FWD = 4 * (2 * 145 * 144 * 432 + 4 * 6 * 145 * 145 * 24 + 2 * 145 * 144 * 144 + 4 * 145 * 144 * 576) + 2 * 144 * 192 * 144
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -207,6 +224,8 @@ def algorithmic_cost(name, a):
         return a[1] * 4.0, 0.0, f"n={a[1]}"
     if name == "mae_clip_adamw":
         return a[5] * 30.0, 0.0, f"n={a[5]}"  # read p, g, m, v; write p, m, v and the bf16 shadow
+    if name == "mae_augment_params":
+        return a[1] * 20.0, 0.0, f"B={a[1]}"
     if name == "mae_augment_u8":
         B, C, S = a[2], a[3], a[6]
         return B * C * S * S * 5.0, 0.0, f"B={B} S={S}"  # lower bound: a crop at least as large as the output
@@ -286,7 +305,7 @@ def kernel_breakdown(trainer, images, noise, pk):
     if g_ms > 0:
         gbs = gemm_bytes / (g_ms * 1e-3) / 1e9
         tfs = gemm_flops / (g_ms * 1e-3) / 1e12
-        roof = {"kernel": "gemm_tn_kernel (tcgen05 + TMA; the 53 forward/dgrad GEMM launches of one step, K = 144..768)",
+        roof = {"kernel": f"gemm_tn_kernel (tcgen05 + TMA; the {n_gemm} forward/dgrad GEMM launches of one step)",
                 "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
                 # ncu dram__bytes_read.sum + dram__bytes_write.sum over the 53 gemm_tn launches of one step of this build
                 # (profiles/r01r_gemm_tn_dram_traffic.csv: 6.98 GB read + 4.43 GB written), per launch like the figure below
@@ -320,15 +339,16 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
+    wl_cfg, IMG, wl_batch, wl_flops, wl_label = WORKLOADS[args.workload]
+    B = args.batch or wl_batch
     torch.manual_seed(73 + rank)  # rank-distinct noise / data streams
-    mod = P.MAEPretrainModule(CFG, dict(PRETRAIN, batch_size=B)).to(dev)
+    mod = P.MAEPretrainModule(wl_cfg, dict(PRETRAIN, batch_size=B)).to(dev)
     if world > 1:  # identical replicas
         for p in mod.parameters():
             dist.broadcast(p.data, 0)
     tr = P.FusedTrainer(mod)
     tr.set_epoch(0)
-    pool = [torch.randn(B, 3, 96, 96, device=dev) for _ in range(3)]  # 221 MB each: > 126 MB L2 between reuses
+    pool = [torch.randn(B, 3, IMG, IMG, device=dev) for _ in range(3)]  # mae: 221 MB each (> 126 MB L2 between reuses)
 
     def barrier():
         if world > 1:
@@ -359,7 +379,7 @@ def run_ours(args):
 
     # end to end through the public API: pinned host batches -> (prefetching) H2D -> step -> D2H of the loss,
     # every step.  The copy of batch i+1 overlaps step i on a side stream; it is still inside the timed region.
-    host = [torch.randn(B, 3, 96, 96).pin_memory() for _ in range(2)]
+    host = [torch.randn(B, 3, IMG, IMG).pin_memory() for _ in range(2)]
     e2e_steps = max(3, min(args.steps, 10))
     pf = P.training.DevicePrefetcher((host[i % 2] for i in range(e2e_steps + 2)), dev)
     for _ in range(2):
@@ -378,15 +398,15 @@ def run_ours(args):
 
     # the same end-to-end loop fed with raw uint8 batches (what torchvision's STL10 stores): 4x less H2D traffic, the
     # reference's RandomResizedCrop + flip + ToTensor + Normalize run on the GPU (mae_augment_u8)
-    aug = P.data.GpuAugment(size=96, train=True)
-    host8 = [torch.randint(0, 256, (B, 3, 96, 96), dtype=torch.uint8).pin_memory() for _ in range(2)]
-    pf8 = P.training.DevicePrefetcher((host8[i % 2] for i in range(e2e_steps + 2)), dev)
+    aug = P.data.GpuAugment(size=IMG, train=True)  # boxes / flips drawn on the device (mae_augment_params)
+    host8 = [torch.randint(0, 256, (B, 3, IMG, IMG), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    pf8 = P.training.DevicePrefetcher((host8[i % 2] for i in range(e2e_steps + 2)), dev, transform=aug)
     for _ in range(2):
-        tr.train_step(aug(next(pf8))).item()
+        tr.train_step(next(pf8)).item()
     barrier()
     ev0.record()
     for _ in range(e2e_steps):
-        tr.train_step(aug(next(pf8))).item()
+        tr.train_step(next(pf8)).item()
     ev1.record()
     barrier()
     t = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
@@ -407,26 +427,26 @@ def run_ours(args):
         pk = peaks()
         share, roof, extra = kernel_breakdown(tr, pool[0], None, pk)
         extra["replica_param_maxdiff"] = replica_maxdiff  # N > 1: max |param(rank i) - param(rank j)| after all steps; must be 0.0
-        extra["e2e_uint8_gpu_augment"] = {"value": e2e_u8_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 96 * 96,
-                                          "note": "uint8 host batches + GPU RandomResizedCrop/flip/normalize inside the timed loop"}
-        step_tf = value / world * FLOPS_PER_IMAGE / 1e12
+        extra["e2e_uint8_gpu_augment"] = {"value": e2e_u8_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * IMG * IMG,
+                                          "note": "uint8 host batches; crop boxes / flips drawn on the device, RandomResizedCrop/flip/normalize on the prefetch stream, all inside the timed loop"}
+        step_tf = value / world * wl_flops / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "timed_with": "CUDA events on the launching stream, max over ranks",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "configs/mae.yaml MAE pretrain step (96px, 8px patches, 144-d x4 enc, 192-d x2 dec), "
-                                   f"batch {B}/GPU, mask 0.75, fwd+bwd+clip+AdamW", "global_batch": B * world,
-                       "parallelism": f"dp{world}", "l2_policy": "3 rotating 221 MB input batches (> 126 MB L2)"},
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 96 * 96 * 4,
+            "config": {"workload": f"{wl_label}, batch {B}/GPU, mask 0.75, fwd+bwd+clip+AdamW", "global_batch": B * world,
+                       "parallelism": f"dp{world}",
+                       "l2_policy": f"3 rotating {B * 3 * IMG * IMG * 4 / 1e6:.0f} MB input batches (> 126 MB L2)"},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * IMG * IMG * 4,
                     "d2h_bytes_per_step": 4, "steps": e2e_steps},
             "gpu_launches": launches, "clocks": clocks, "final_loss": float(loss.item()),
             "roofline": roof,
             "step_roofline": {"bound": "tensor", "achieved": step_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                              "frac": step_tf / pk["tf_sustained"], "flops_per_image": FLOPS_PER_IMAGE,
+                              "frac": step_tf / pk["tf_sustained"], "flops_per_image": wl_flops,
                               "peak_source": pk["source"]},
             "kernel_share": share, "extra": extra,
         }
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and args.workload == "mae":
             ips, cores, cms, done = cpu_reference_run(10, 2, batch=64, time_budget_s=20.0)
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                                     "sample": f"{done} steps of batch 64, oracle port, fp32 highest, {cms:.0f} ms/step"}
@@ -436,12 +456,77 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_classifier(args):
+    """BASELINE.json configs[3]: downstream classifier on the 144-d ViT (reference src/models/classifier.py:47-57,
+    scripts/training/train_mae.py:205-215), batch 2000: full fine-tune (value) and frozen-encoder probe (extra), each step =
+    training_step + backward + clip 1.0 + torch AdamW through the product classes.  Extra bench line; single GPU."""
+    import torch
+    import torch.nn.functional as F  # noqa: F401
+
+    import ssrl_vit_mae_jepa_b200 as P
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B = args.batch or 2000
+    torch.manual_seed(73)
+    cfg = dict(CFG, head={"embed_dim": 144, "pool": "cls"})
+    pool = [torch.randn(B, 3, 96, 96, device=dev) for _ in range(3)]
+    labels = torch.randint(0, 10, (B,), device=dev)
+    out = {}
+    for mode, freeze in (("full_finetune", False), ("frozen_probe", True)):
+        mae = P.MaskedAutoencoder(CFG["general"], CFG["encoder"], CFG["decoder"])
+        mod = P.ViTClassifierTrainModule(pretrained_encoder=mae.encoder.vit, model_cfg=cfg,
+                                         training_cfg={"freeze_encoder": freeze, "learning_rate": 1e-4}).to(dev)
+        opt = mod.configure_optimizers()["optimizer"]
+        params = [p for p in mod.parameters() if p.requires_grad]
+
+        def step(x):
+            opt.zero_grad(set_to_none=True)
+            loss = mod.training_step((x, labels), 0)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+            return loss
+
+        for i in range(max(args.warmup, 5)):
+            step(pool[i % 3])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            loss = step(pool[i % 3])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        out[mode] = {"images_per_s": B / (ms * 1e-3), "ms_per_step": ms, "loss": float(loss.item())}
+    pk = peaks()
+    v = out["full_finetune"]["images_per_s"]
+    tf_ft, tf_probe = v * 3 * CLS_FLOPS_FWD / 1e12, out["frozen_probe"]["images_per_s"] * CLS_FLOPS_FWD / 1e12
+    print(json.dumps({
+        "metric": "ViT classifier images/sec (fwd+bwd+AdamW, device-timed)", "value": v, "unit": "images/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": out["full_finetune"]["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "timed_with": "CUDA events on the launching stream",
+        "config": {"workload": f"train_mae full fine-tune of the 144-d ViT classifier (all 145 tokens, CLS head), batch {B}",
+                   "global_batch": B, "parallelism": "dp1"},
+        "step_roofline": {"bound": "tensor", "achieved": tf_ft, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                          "frac": tf_ft / pk["tf_sustained"], "flops_per_image": 3 * CLS_FLOPS_FWD, "peak_source": pk["source"]},
+        "extra": {"frozen_probe": dict(out["frozen_probe"], tflops=tf_probe, tensor_frac=tf_probe / pk["tf_sustained"],
+                                       flops_per_image=CLS_FLOPS_FWD),
+                  "full_finetune": out["full_finetune"]},
+    }), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=2000)
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's, 2000 for configs/mae.yaml)")
+    ap.add_argument("--workload", default="mae", choices=["mae", "vitb16", "classifier"],
+                    help="mae = the headline (BASELINE.json configs[1..2]); vitb16 / classifier = extra lines for configs[4] / [3]")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -449,6 +534,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "classifier":
+        run_classifier(args)
     else:
         run_ours(args)
 

@@ -205,6 +205,14 @@ int mae_clip_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, l
 int mae_augment_u8(const uint8_t* images, const int* params, int B, int C, int Hs, int Ws, int S, float* out,
                    mae_stream_t stream);
 
+/* Crop boxes + flips for mae_augment_u8 drawn ON THE DEVICE: torchvision RandomResizedCrop.get_params (reference
+ * src/data.py:18-21: scale (0.8, 1.0), default ratio (3/4, 4/3)) + RandomHorizontalFlip's coin for B samples of an
+ * H x W image -> params (B,5) int32 rows (top, left, height, width, flip).  Counter-based generator: the result is a pure
+ * function of (seed, counter, sample index), see csrc/augment.cu; train == 0 gives the identity box (evaluation).
+ * Keeps the host out of the per-step input pipeline (no RNG calls, no pinned staging copy). */
+int mae_augment_params(int* params, int B, int H, int W, float scale_lo, float scale_hi, float ratio_lo, float ratio_hi,
+                       unsigned long long seed, unsigned long long counter, int train, mae_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

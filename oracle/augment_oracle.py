@@ -134,6 +134,57 @@ def get_params(height: int, width: int, scale: Sequence[float], ratio: Sequence[
     return (height - h) // 2, (width - w) // 2, h, w
 
 
+def get_params_from_uniforms(height: int, width: int, scale: Sequence[float], ratio: Sequence[float],
+                             u: np.ndarray) -> Tuple[int, int, int, int, int]:
+    """``get_params`` (above) + the flip coin with the random numbers made explicit: ``u`` holds 23 fp32 uniforms in
+    [0, 1): ``u[2a], u[2a+1]`` = area / log-ratio draw of attempt ``a``, ``u[20], u[21]`` = top / left, ``u[22]`` = flip.
+    Same arithmetic as torchvision: fp32 ``uniform_`` (``u * (to - from) + from``) and fp32 ``exp``, Python doubles
+    and ``round`` after ``.item()``.  Oracle of ``mae_augment_params`` (whose generator is counter-based, so the uniforms
+    are reproducible on the host)."""
+    area = height * width
+    s0, s1 = np.float32(scale[0]), np.float32(scale[1])
+    l0, l1 = np.log(np.float32(ratio[0])), np.log(np.float32(ratio[1]))
+    flip = int(np.float32(u[22]) < np.float32(0.5))
+    for a in range(10):
+        sf = np.float32(np.float32(u[2 * a]) * np.float32(s1 - s0)) + s0
+        lr = np.float32(np.float32(u[2 * a + 1]) * np.float32(l1 - l0)) + l0
+        target_area = area * float(np.float32(sf))
+        aspect_ratio = float(np.exp(np.float32(lr)))
+        w = int(round(math.sqrt(target_area * aspect_ratio)))
+        h = int(round(math.sqrt(target_area / aspect_ratio)))
+        if 0 < w <= width and 0 < h <= height:
+            i = int(float(np.float32(u[20])) * (height - h + 1))
+            j = int(float(np.float32(u[21])) * (width - w + 1))
+            return i, j, h, w, flip
+    in_ratio = float(width) / float(height)
+    if in_ratio < min(ratio):
+        w = width
+        h = int(round(w / min(ratio)))
+    elif in_ratio > max(ratio):
+        h = height
+        w = int(round(h * max(ratio)))
+    else:
+        w, h = width, height
+    return (height - h) // 2, (width - w) // 2, h, w, flip
+
+
+def splitmix64(x: np.ndarray) -> np.ndarray:
+    """The 64-bit mixer of the device generator (uint64 arrays, wrapping arithmetic)."""
+    with np.errstate(over="ignore"):
+        x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+        x = ((x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)).astype(np.uint64)
+        x = ((x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)).astype(np.uint64)
+        return x ^ (x >> np.uint64(31))
+
+
+def device_uniforms(n: int, seed: int, counter: int) -> np.ndarray:
+    """(n, 23) fp32 uniforms exactly as ``mae_augment_params`` generates them for samples 0..n-1."""
+    with np.errstate(over="ignore"):
+        key = splitmix64(splitmix64(np.array([seed + counter], np.uint64)) + np.arange(n, dtype=np.uint64))
+        v = splitmix64(key[:, None] + np.arange(23, dtype=np.uint64)[None, :])
+    return ((v >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)).astype(np.float32)
+
+
 def train_params(n: int, size: int = 96, scale=(0.8, 1.0), ratio=(3.0 / 4.0, 4.0 / 3.0),
                  generator: torch.Generator | None = None) -> np.ndarray:
     """Per-sample ``(i, j, h, w, flip)`` int32 rows in the order the reference's Compose consumes the RNG:

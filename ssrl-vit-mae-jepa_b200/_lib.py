@@ -37,6 +37,7 @@ SIGNATURES = {
     "mae_colsum_rows_f32": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "mae_zero_rows": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "mae_augment_u8": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "mae_augment_params": [_vp, _i, _i, _i, _f, _f, _f, _f, C.c_ulonglong, C.c_ulonglong, _i, _vp],
     "mae_cast_bf16": [_vp, _vp, _ll, _vp],
     "mae_transpose_cast_bf16": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "mae_grad_sumsq": [_vp, _ll, _vp, _i, _vp],

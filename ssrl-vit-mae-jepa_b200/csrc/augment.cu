@@ -187,9 +187,75 @@ __global__ void __launch_bounds__(256) augment_u8_kernel(const uint8_t* __restri
     aug_resample<false>(ax, ay, src_s, Ws, cj, ch, cw, S, tmp_s, lut, flip, dst);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Crop boxes and flips drawn on the device: torchvision RandomResizedCrop.get_params (10 attempts of area ~ U(scale),
+// log-ratio ~ U(log ratio), w = round(sqrt(a r)), h = round(sqrt(a / r)), first fitting one wins, whole-image /
+// centre-crop fallback) followed by RandomHorizontalFlip's coin, one thread per sample.  The uniforms come from a
+// counter-based generator, so a call is a pure function of (seed, counter, sample): no generator state, no host work, no
+// host <-> device traffic in the input pipeline.  u(k) = top 24 bits of splitmix64(splitmix64(splitmix64(seed + counter)
+// + sample) + k) * 2^-24; k = 2a, 2a+1: area / ratio of attempt a; 20, 21: top / left; 22: flip.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(128) augment_params_kernel(int* __restrict__ params, int B, int H, int W, float s0, float s1,
+                                                            float l0, float l1, float rmin, float rmax,
+                                                            unsigned long long seed, unsigned long long counter, int train) {
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int ci = 0, cj = 0, ch = H, cw = W, flip = 0;
+  if (train) {
+    const unsigned long long key = splitmix64(splitmix64(seed + counter) + (unsigned long long)b);
+    auto u = [&](int k) { return float(splitmix64(key + (unsigned long long)k) >> 40) * (1.0f / 16777216.0f); };
+    bool found = false;
+    for (int a = 0; a < 10 && !found; ++a) {
+      // torch: empty(1).uniform_(from, to) = u * (to - from) + from in fp32; .item() -> double
+      const float sf = __fadd_rn(__fmul_rn(u(2 * a), __fsub_rn(s1, s0)), s0);
+      const float lr = __fadd_rn(__fmul_rn(u(2 * a + 1), __fsub_rn(l1, l0)), l0);
+      const double target = double(H * W) * double(sf);
+      const double ar = double(expf(lr));
+      const int w = int(rint(sqrt(target * ar))), h = int(rint(sqrt(target / ar)));  // Python round(): half to even
+      if (w > 0 && w <= W && h > 0 && h <= H) {
+        ci = int(double(u(20)) * double(H - h + 1));
+        cj = int(double(u(21)) * double(W - w + 1));
+        ch = h; cw = w;
+        found = true;
+      }
+    }
+    if (!found) {
+      const float in_ratio = float(W) / float(H);
+      if (in_ratio < rmin) { cw = W; ch = int(rint(double(W) / double(rmin))); }
+      else if (in_ratio > rmax) { ch = H; cw = int(rint(double(H) * double(rmax))); }
+      else { cw = W; ch = H; }
+      ch = ch > H ? H : ch; cw = cw > W ? W : cw;
+      ci = (H - ch) / 2; cj = (W - cw) / 2;
+    }
+    flip = u(22) < 0.5f ? 1 : 0;
+  }
+  int* o = params + size_t(b) * 5;
+  o[0] = ci; o[1] = cj; o[2] = ch; o[3] = cw; o[4] = flip;
+}
+
 }  // namespace mae
 
 using namespace mae;
+
+extern "C" int mae_augment_params(int* params, int B, int H, int W, float scale_lo, float scale_hi, float ratio_lo,
+                                  float ratio_hi, unsigned long long seed, unsigned long long counter, int train,
+                                  cudaStream_t stream) {
+  if (B <= 0) return MAE_OK;
+  if (!params) return MAE_ERR_NULL;
+  if (H <= 0 || W <= 0 || !(scale_lo > 0.f) || scale_hi < scale_lo || !(ratio_lo > 0.f) || ratio_hi < ratio_lo) return MAE_ERR_SHAPE;
+  mae_launch(augment_params_kernel, dim3((B + 127) / 128), dim3(128), 0, stream, params, B, H, W, scale_lo, scale_hi,
+             logf(ratio_lo), logf(ratio_hi), ratio_lo, ratio_hi, seed, counter, train);
+  return MAE_CHECK_LAUNCH();
+}
 
 extern "C" int mae_augment_u8(const uint8_t* images, const int* params, int B, int C, int Hs, int Ws, int S, float* out,
                               cudaStream_t stream) {

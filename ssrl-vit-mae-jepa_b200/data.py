@@ -67,15 +67,31 @@ class GpuAugment:
     """The reference's transforms (``src/data.py:15-34``) applied on the GPU to uint8 batches (B,3,H,W):
     ``train=True``: RandomResizedCrop(size, scale, ratio) -> RandomHorizontalFlip -> ToTensor -> Normalize(.5,.5);
     ``train=False``: Resize/CenterCrop (identity for 96x96 STL-10) -> ToTensor -> Normalize.
-    The pixels come from ``mae_augment_u8`` (bit-exact Pillow bilinear); the random crop boxes / flips are drawn here
-    with torch (on the host by default), all samples at once, following ``RandomResizedCrop.get_params`` (10 attempts of
-    area ~ U(scale), log-ratio ~ U(log ratio), first fitting one wins, centre-crop fallback).  H2D traffic is 4x
-    smaller than shipping float32 images."""
+    The pixels come from ``mae_augment_u8`` (bit-exact Pillow bilinear); the random crop boxes / flips follow
+    ``RandomResizedCrop.get_params`` (10 attempts of area ~ U(scale), log-ratio ~ U(log ratio), first fitting one wins,
+    centre-crop fallback) and are drawn on the device by ``mae_augment_params`` (counter-based generator: nothing of the
+    input pipeline runs on the host per step); passing a ``torch.Generator`` switches to drawing them with torch instead.
+    H2D traffic is 4x smaller than shipping float32 images."""
 
     def __init__(self, size: int = 96, scale=(0.8, 1.0), ratio=(3.0 / 4.0, 4.0 / 3.0), train: bool = True,
-                 generator: Optional[torch.Generator] = None):
+                 generator: Optional[torch.Generator] = None, seed: int = 73):
         self.size, self.scale, self.ratio, self.train, self.generator = size, scale, ratio, train, generator
-        self._next, self._next_key = None, None  # parameters drawn ahead for the next call
+        self._next, self._next_key = None, None  # (torch-generator mode) parameters drawn ahead for the next call
+        # default: boxes / flips drawn on the device by mae_augment_params, a pure function of (seed, call counter, sample)
+        self.seed, self.counter = int(seed), 0
+        self._params: Optional[torch.Tensor] = None
+
+    def device_params(self, B: int, H: int, W: int, device) -> torch.Tensor:
+        """(B,5) int32 rows (i, j, h, w, flip) drawn on ``device`` (no host RNG, no host <-> device copy, no sync)."""
+        from ._lib import calls
+
+        if self._params is None or self._params.shape[0] != B or self._params.device != device:
+            self._params = torch.empty(B, 5, dtype=torch.int32, device=device)
+        calls.mae_augment_params(self._params.data_ptr(), B, H, W, float(self.scale[0]), float(self.scale[1]),
+                                 float(self.ratio[0]), float(self.ratio[1]), self.seed, self.counter, int(self.train),
+                                 torch.cuda.current_stream(device).cuda_stream)
+        self.counter += 1
+        return self._params
 
     def draw_params(self, B: int, H: int, W: int, device) -> torch.Tensor:
         """(B,5) int32 rows (i, j, h, w, flip) on ``device``."""
@@ -103,19 +119,20 @@ class GpuAugment:
         flip = (v[:, 2] < 0.5).long()
         return torch.stack([i, j, h, w, flip], dim=1).to(torch.int32).contiguous()
 
-    def __call__(self, images_u8: torch.Tensor, params: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def __call__(self, images_u8: torch.Tensor, params: Optional[torch.Tensor] = None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
         from ._lib import calls
 
         if not images_u8.is_cuda or images_u8.dtype != torch.uint8 or images_u8.dim() != 4:
             raise RuntimeError("GpuAugment needs a CUDA uint8 (B,C,H,W) batch (there is no CPU fallback)")
         images_u8 = images_u8.contiguous()
         B, C, H, W = images_u8.shape
-        drawn_here = params is None
-        if drawn_here:
-            # Drawn on the host (a few vectorised ops) and shipped as one 40 KB copy from a persistent pinned buffer:
-            # on the device the same ~35 tiny elementwise launches would sit in the compute stream (~0.4 ms per step).
-            # The draw for the NEXT call is made right after this call's kernel launch, so the host work overlaps the
-            # GPU instead of delaying the first launch of a step.
+        drawn_here = params is None and self.generator is not None
+        if params is None and self.generator is None:
+            params = self.device_params(B, H, W, images_u8.device)
+        elif drawn_here:
+            # torch-generator mode (reproducing a torch RNG stream): drawn on the host with a few vectorised ops and shipped
+            # as one small copy from a pinned buffer; the draw for the NEXT call is made right after this call's kernel launch
             key = (B, H, W)
             if self._next_key != key:
                 self._next, self._next_key = self._draw_host(B, H, W), key
@@ -123,7 +140,11 @@ class GpuAugment:
         params = params.to(device=images_u8.device, dtype=torch.int32, non_blocking=True).contiguous()
         if params.shape != (B, 5):
             raise ValueError(f"params must be ({B},5)")
-        out = torch.empty(B, C, self.size, self.size, dtype=torch.float32, device=images_u8.device)
+        if out is None:
+            out = torch.empty(B, C, self.size, self.size, dtype=torch.float32, device=images_u8.device)
+        elif out.shape != (B, C, self.size, self.size) or out.dtype != torch.float32 or not out.is_contiguous() or \
+                out.device != images_u8.device:
+            raise ValueError(f"out must be a contiguous float32 ({B},{C},{self.size},{self.size}) tensor on the input's device")
         calls.mae_augment_u8(images_u8.data_ptr(), params.data_ptr(), B, C, H, W, self.size, out.data_ptr(),
                              torch.cuda.current_stream(images_u8.device).cuda_stream)
         if drawn_here:

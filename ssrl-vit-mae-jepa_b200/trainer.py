@@ -198,7 +198,9 @@ class LiteTrainer:
             elif hasattr(module, "on_train_epoch_start"):
                 module.on_train_epoch_start()
             losses = []
-            batches = DevicePrefetcher(self._images_only(train_loader), self.device) if fused else train_loader
+            # uint8 batches (gpu_augment loaders) are cropped / flipped / normalised on the prefetch stream, behind their copy
+            batches = DevicePrefetcher(self._images_only(train_loader), self.device, transform=self._augmenter(True)) \
+                if fused else train_loader
             for bi, batch in enumerate(batches):
                 if self.limit_batches is not None and bi >= self.limit_batches:
                     break
@@ -282,16 +284,19 @@ class LiteTrainer:
         self._log(out, self.global_step)
         return [out]
 
-    def _prep(self, images: torch.Tensor, train: bool) -> torch.Tensor:
-        """uint8 batches (``gpu_augment`` loaders) get the reference transform on the GPU; float batches pass through."""
-        if images.dtype != torch.uint8:
-            return images
+    def _augmenter(self, train: bool, size: int = 96):
         from .data import GpuAugment
 
         key = "_aug_train" if train else "_aug_eval"
         if getattr(self, key, None) is None:
-            setattr(self, key, GpuAugment(size=images.shape[-1], train=train))
-        return getattr(self, key)(images)
+            setattr(self, key, GpuAugment(size=size, train=train, seed=73 + 1000 * self.rank))  # rank-distinct boxes
+        return getattr(self, key)
+
+    def _prep(self, images: torch.Tensor, train: bool) -> torch.Tensor:
+        """uint8 batches (``gpu_augment`` loaders) get the reference transform on the GPU; float batches pass through."""
+        if images.dtype != torch.uint8:
+            return images
+        return self._augmenter(train, images.shape[-1])(images)
 
     @staticmethod
     def _images_only(loader):

@@ -198,13 +198,19 @@ class DevicePrefetcher:
     computes (two device staging buffers).  Iterating yields device tensors that stay valid until the next
     ``next()``.  This is the piece of Lightning's batch transfer the hot path needs (reference
     ``scripts/training/pretrain_mae.py:128`` -> ``trainer.fit`` moves each batch to the GPU before
-    ``training_step``), made asynchronous."""
+    ``training_step``), made asynchronous.
 
-    def __init__(self, host_batches, device):
+    ``transform`` (a ``GpuAugment``; applied to uint8 batches only) runs on the same side stream right behind the copy, writing
+    into one of two persistent output buffers: the crop / flip / normalize of batch i+1 then overlaps step i as well,
+    instead of sitting at the head of the compute stream."""
+
+    def __init__(self, host_batches, device, transform=None):
         self.it = iter(host_batches)
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(self.device)
+        self.transform = transform
         self.bufs: List[Optional[torch.Tensor]] = [None, None]
+        self.obufs: List[Optional[torch.Tensor]] = [None, None]
         self.k = 0
         self.ready: Optional[torch.cuda.Event] = None
         self.cur: Optional[torch.Tensor] = None
@@ -220,15 +226,22 @@ class DevicePrefetcher:
             host = host[0]
         slot = self.k % 2
         self.k += 1
-        if self.bufs[slot] is None or self.bufs[slot].shape != host.shape:
+        if self.bufs[slot] is None or self.bufs[slot].shape != host.shape or self.bufs[slot].dtype != host.dtype:
             self.bufs[slot] = torch.empty(host.shape, dtype=host.dtype, device=self.device)
         # everything enqueued so far on the compute stream (incl. the step that last read this slot) goes first
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):
             self.bufs[slot].copy_(host, non_blocking=True)
+            result = self.bufs[slot]
+            if self.transform is not None and host.dtype == torch.uint8:  # float batches are already transformed
+                size = getattr(self.transform, "size", host.shape[-1])
+                shape = (host.shape[0], host.shape[1], size, size)
+                if self.obufs[slot] is None or self.obufs[slot].shape != shape:
+                    self.obufs[slot] = torch.empty(shape, dtype=torch.float32, device=self.device)
+                result = self.transform(self.bufs[slot], out=self.obufs[slot])
             self.ready = torch.cuda.Event()
             self.ready.record(self.stream)
-        self.nxt = self.bufs[slot]
+        self.nxt = result
 
     def __iter__(self):
         return self

@@ -90,3 +90,44 @@ def test_rejects_cpu_and_bad_shapes():
         out = torch.empty(1, 1, 8, 8, device=dev)
         big = torch.zeros(1, 1, 96, 96, dtype=torch.uint8, device=dev)
         calls.mae_augment_u8(p(big), p(torch.zeros(1, 5, dtype=torch.int32, device=dev)), 1, 1, 96, 96, 8, p(out), stream())
+
+
+@pytest.mark.parametrize("H,W,scale,ratio", [(96, 96, (0.8, 1.0), (3 / 4, 4 / 3)), (80, 120, (0.08, 1.0), (3 / 4, 4 / 3)),
+                                             (64, 64, (0.9, 1.0), (2.0, 3.0))])
+def test_device_drawn_params_match_the_oracle(H, W, scale, ratio):
+    """mae_augment_params (boxes + flips drawn on the device, counter-based generator) against the numpy restatement of
+    torchvision's RandomResizedCrop.get_params fed with the same uniforms.  Integer outputs: equal, except where CUDA's
+    fp32 exp and numpy's differ in the last bit right at a rounding boundary (bounded: < 0.5 % of the samples, by 1 px)."""
+    B, seed, counter = 4096, 73, 5
+    pr = torch.empty(B, 5, dtype=torch.int32, device=dev)
+    calls.mae_augment_params(p(pr), B, H, W, scale[0], scale[1], ratio[0], ratio[1], seed, counter, 1, stream())
+    got = pr.cpu().numpy()
+    u = A.device_uniforms(B, seed, counter)
+    assert u.min() >= 0.0 and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.01
+    ref = np.array([A.get_params_from_uniforms(H, W, scale, ratio, u[b]) for b in range(B)], np.int32)
+    diff = np.abs(got - ref)
+    assert diff.max() <= 1 and (diff.max(1) > 0).mean() < 0.005, (diff.max(), (diff.max(1) > 0).mean())
+    i, j, h, w, f = [got[:, k] for k in range(5)]
+    assert (h >= 1).all() and (w >= 1).all() and (i >= 0).all() and (j >= 0).all() and (i + h <= H).all() and (j + w <= W).all()
+    assert set(np.unique(f)) <= {0, 1} and 0.45 < f.mean() < 0.55
+    # a pure function of (seed, counter, sample): repeatable, and a new counter gives new boxes
+    pr2 = torch.empty_like(pr)
+    calls.mae_augment_params(p(pr2), B, H, W, scale[0], scale[1], ratio[0], ratio[1], seed, counter, 1, stream())
+    assert torch.equal(pr, pr2)
+    calls.mae_augment_params(p(pr2), B, H, W, scale[0], scale[1], ratio[0], ratio[1], seed, counter + 1, 1, stream())
+    assert (pr2 != pr).any(1).float().mean().item() > (0.9 if ratio[0] < 1 else 0.4)  # (fallback boxes are fixed: only the flips change)
+    calls.mae_augment_params(p(pr2), B, H, W, scale[0], scale[1], ratio[0], ratio[1], seed, counter, 0, stream())
+    assert torch.equal(pr2.cpu(), torch.tensor([[0, 0, H, W, 0]], dtype=torch.int32).expand(B, 5))
+
+
+def test_gpu_augment_default_draws_on_the_device():
+    x = torch.randint(0, 256, (64, 3, 96, 96), dtype=torch.uint8, device=dev)
+    aug = GpuAugment(train=True, seed=9)
+    a = aug(x)
+    pr_a = aug._params.clone()
+    b = aug(x)
+    assert aug.counter == 2 and not torch.equal(a, b) and aug._next is None  # no host-side draw happened
+    ref = A.augment_batch(x[:4].cpu().numpy(), pr_a[:4].cpu().numpy())
+    assert np.array_equal(a[:4].cpu().numpy(), ref)
+    again = GpuAugment(train=True, seed=9)
+    assert torch.equal(again(x), a)  # same seed, same call index -> same augmentation
