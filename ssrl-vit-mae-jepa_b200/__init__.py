@@ -6,5 +6,5 @@ from .mae import MAEEngine, MaskedAutoencoder, num_keep_tokens, sincos_2d  # noq
 from . import training  # noqa: F401
 from .training import DevicePrefetcher, FusedTrainer, MAEPretrainModule  # noqa: F401
 from .classifier import ClassificationHead, ViTClassifier, ViTClassifierTrainModule, ViTEngine, VisionTransformer  # noqa: F401
-from . import data, trainer  # noqa: F401,E402
+from . import data, ops, trainer  # noqa: F401,E402  (ops: registers torch.ops.mae_b200.*)
 from .trainer import LiteTrainer, ModelCheckpoint  # noqa: F401,E402

@@ -368,3 +368,23 @@ def test_reference_scripts_run_unmodified_up_to_fit(monkeypatch, tmp_path):
         assert (out / "config.yaml").exists() and (out / "vit-mae.pt").exists()  # the script's own torch.save ran
     sd = torch.load(tmp_path / "outputs" / "pretrain" / "p" / "vit-mae.pt")
     assert len(sd) == 87
+
+
+def test_torch_library_ops_are_registered_cuda_only():
+    """torch.ops.mae_b200.* exist with inferred schemas, are traceable through their fake implementations, and have no CPU
+    kernel: a CPU tensor is refused by the dispatcher (there is no fallback path to fall into)."""
+    import ssrl_vit_mae_jepa_b200  # noqa: F401
+    ns = torch.ops.mae_b200
+    for name in ("random_token_mask", "gemm_tn", "gemm_wgrad", "patch_embed_tokens", "mlp_fwd", "linear", "layernorm",
+                 "layernorm_bwd", "attention", "attention_bwd", "masked_mse"):
+        assert hasattr(ns, name), name
+    assert "Tensor x, Tensor weight, Tensor bias" in str(ns.linear.default._schema)
+    with pytest.raises(NotImplementedError):
+        ns.linear(torch.zeros(4, 16, dtype=torch.bfloat16), torch.zeros(16, 16, dtype=torch.bfloat16), torch.zeros(16))
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        x = torch.empty(256, 144, dtype=torch.bfloat16, device="cuda")
+        y = ns.linear(x, torch.empty(432, 144, dtype=torch.bfloat16, device="cuda"), torch.empty(432, device="cuda"))
+        assert y.shape == (256, 432) and y.dtype == torch.bfloat16
+        o, lse = ns.attention(y.view(8, 32, 432), 6)
+        assert o.shape == (8, 32, 144) and lse.shape == (8, 6, 32)
