@@ -15,9 +15,10 @@
 //               [64c, 64c+64) as one [D x 64] box) through a 3-stage ring
 //   warp 1      TMEM owner + tcgen05.mma issuer: fc1(c+1) is issued before fc2(c), so the tensor pipe works on the next
 //               chunk while the epilogue warps are busy with the current one
-//   warps 2-17  LayerNorm prologue (8 rows per warp, coalesced fp32 loads, two-pass statistics, bf16 A tile + xn / mean /
-//               rstd for the backward), GELU epilogue (even chunks: warps with grp 0-1, odd chunks: grp 2-3; 32 columns per
-//               warp), output epilogue (bias + residual, fp32)
+//   warps 2-17  LayerNorm prologue (8 rows per warp, 8 lanes per row, coalesced fp32 loads, two-pass statistics, bf16 A tile +
+//               xn / mean / rstd for the backward), GELU epilogue (even chunks: warps with grp 0-1, odd chunks: grp 2-3; 32
+//               columns per warp; four TMEM chunk buffers keep the tensor pipe two chunks ahead of each group), output
+//               epilogue (bias + residual, fp32)
 //   warp 18     TMA bulk stores of the GELU / GELU' tiles
 // Shared memory: [GELU table +][A 48 KB][h 2x16 KB][g 2x16 KB][barriers] ... 128 KB above the + table: [GELU table -][ring].
 #include <stdlib.h>
@@ -40,12 +41,12 @@ static constexpr uint32_t kMlpOffTabN = kGeluNegOff;          // 131072: pinned 
 static constexpr uint32_t kMlpOffRing = kMlpOffTabN + 13 * 1024;
 static constexpr uint32_t kMlpSmem = kMlpOffRing + kMlpStages * kMlpStageBytes;  // 218112
 static constexpr int kMlpStgRow = 80;                         // output staging: 64 data bytes + 16 pad per row
-static constexpr uint32_t kMlpTmemPre = 256;                  // TMEM columns: [0, D) output tile, 256 / 320: fc1 chunks
+static constexpr uint32_t kMlpTmemPre = 256;                  // TMEM columns: [0, D) output tile, 256 + 64 i: four fc1 chunk buffers
 
 struct MlpHdr {
   uint64_t w_full[kMlpStages], w_empty[kMlpStages];
   uint64_t a_ready;
-  uint64_t pre_full[2], pre_free[2];
+  uint64_t pre_full[4], pre_free[4];
   uint64_t h_ready[2], h_free[2];
   uint64_t out_full, out_free;
   uint32_t tmem_base;
@@ -67,11 +68,16 @@ struct MlpFwdParams {
   float *mean, *rstd;
   float* x_out;
   const uint32_t* gelu_tab;
+  long long* dbg;  // optional clock64 timeline of CTA 0 (MAE_MLP_TIMELINE, tools/mlp_timeline.py); nullptr in production
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+// timeline slot layout: [role][event] with 64 events per role; role 0 = epilogue warp 2 (even chunks), 1 = epilogue warp 10
+// (odd chunks), 2 = MMA issuer
+#define MLP_TS(role, ev) do { if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && (ev) < 64) p.dbg[(role) * 64 + (ev)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(kMlpThreads, 1)
 mlp_fwd_kernel(const MlpFwdParams p, const __grid_constant__ CUtensorMap mapW1, const __grid_constant__ CUtensorMap mapW2,
@@ -91,9 +97,11 @@ mlp_fwd_kernel(const MlpFwdParams p, const __grid_constant__ CUtensorMap mapW1, 
     tma_prefetch_desc(&mapG);
     for (int s = 0; s < kMlpStages; ++s) { mbar_init(&hdr->w_full[s], 1); mbar_init(&hdr->w_empty[s], 1); }
     mbar_init(&hdr->a_ready, kMlpEpiWarps);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(&hdr->pre_full[b], 1);
       mbar_init(&hdr->pre_free[b], kMlpEpiWarps / 2);
+    }
+    for (int b = 0; b < 2; ++b) {
       mbar_init(&hdr->h_ready[b], kMlpEpiWarps / 2);
       mbar_init(&hdr->h_free[b], 2);  // fc2 MMAs of the chunk have completed + its TMA stores have read the tiles
     }
@@ -121,20 +129,20 @@ mlp_fwd_kernel(const MlpFwdParams p, const __grid_constant__ CUtensorMap mapW1, 
       int stage = 0; uint32_t phase = 0;
       const uint32_t w1_bytes = uint32_t(p.nkb) * 8192u, w2_bytes = uint32_t(D) * 128u;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        // same order as the MMA issuer consumes them: W1_0, W1_1, then per chunk c: W1_{c+2}, W2_c
-        for (int c = -2; c < NC; ++c) {
-          if (c + 2 < NC) {  // W1 rows [64(c+2), +64): nkb boxes of [64 rows x 64 k]; k >= D is zero-filled
-            mbar_wait(&hdr->w_empty[stage], phase ^ 1);
-            uint8_t* dst = smem + kMlpOffRing + stage * kMlpStageBytes;
-            mbar_expect_tx(&hdr->w_full[stage], w1_bytes);
-            for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(dst + kb * 8192, &mapW1, &hdr->w_full[stage], kb * BK, (c + 2) * kMlpHC);
-            if (++stage == kMlpStages) { stage = 0; phase ^= 1; }
-          }
+        // same order as the MMA issuer consumes them: W1_0..W1_3, then per chunk c: W2_c, W1_{c+4}
+        for (int c = -4; c < NC; ++c) {
           if (c >= 0) {  // W2 columns [64c, +64): one box of [D rows x 64 k]
             mbar_wait(&hdr->w_empty[stage], phase ^ 1);
             uint8_t* dst = smem + kMlpOffRing + stage * kMlpStageBytes;
             mbar_expect_tx(&hdr->w_full[stage], w2_bytes);
             tma_load_2d(dst, &mapW2, &hdr->w_full[stage], c * kMlpHC, 0);
+            if (++stage == kMlpStages) { stage = 0; phase ^= 1; }
+          }
+          if (c + 4 < NC) {  // W1 rows [64(c+4), +64): nkb boxes of [64 rows x 64 k]; k >= D is zero-filled
+            mbar_wait(&hdr->w_empty[stage], phase ^ 1);
+            uint8_t* dst = smem + kMlpOffRing + stage * kMlpStageBytes;
+            mbar_expect_tx(&hdr->w_full[stage], w1_bytes);
+            for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(dst + kb * 8192, &mapW1, &hdr->w_full[stage], kb * BK, (c + 4) * kMlpHC);
             if (++stage == kMlpStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -147,19 +155,39 @@ mlp_fwd_kernel(const MlpFwdParams p, const __grid_constant__ CUtensorMap mapW1, 
       int stage = 0; uint32_t phase = 0;
       uint32_t g0 = 0, t = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
+        if (t == 1) MLP_TS(2, 0);
         mbar_wait(&hdr->a_ready, t & 1);
         tc_fence_after();
-        // fc1(0), fc1(1), then per chunk c: fc1(c+2) as soon as the epilogue warps have pulled chunk c out of its TMEM
-        // buffer, fc2(c) as soon as they have written its GELU tile: the tensor pipe fills one buffer while the other
-        // chunk is in the epilogue
-        for (int c = -2; c < NC; ++c) {
-          if (c + 2 < NC) {  // fc1 chunk c+2: pre[b] = A[128 x D] * W1[64 x D]^T
-            const uint32_t g = g0 + uint32_t(c + 2), b = g & 1u;
-            mbar_wait(&hdr->pre_free[b], ((g >> 1) & 1u) ^ 1u);
+        if (t == 1) MLP_TS(2, 1);
+        // fc1(0..3) up front (four 64-column TMEM buffers), then per chunk c: fc2(c) as soon as the epilogue warps have
+        // written its GELU tile, and fc1(c+4) into the buffer chunk c came from: the tensor pipe stays two chunks ahead of
+        // each of the two epilogue groups, which therefore never wait for it
+        for (int c = -4; c < NC; ++c) {
+          if (c >= 0) {  // fc2 chunk c: out += h[hb][128 x 64] * W2[D x 64]^T
+            const uint32_t g = g0 + uint32_t(c), hb = g & 1u;
+            if (c == 0) mbar_wait(&hdr->out_free, (t & 1u) ^ 1u);  // previous tile's output has been read out of TMEM
+            mbar_wait(&hdr->h_ready[hb], (g >> 1) & 1u);
+            if (t == 1) MLP_TS(2, 2 + 2 * c);
             mbar_wait(&hdr->w_full[stage], phase);
             tc_fence_after();
             const uint32_t sb = ring_s + stage * kMlpStageBytes;
-            const uint32_t d_tmem = tmem_base + kMlpTmemPre + b * kMlpHC;
+#pragma unroll
+            for (int k = 0; k < kMlpHC / 16; ++k) {
+              const uint64_t adesc = umma_sdesc_sw128(h_s + hb * 16384 + k * 32, 16, 1024);
+              const uint64_t bdesc = umma_sdesc_sw128(sb + k * 32, 16, 1024);
+              umma_bf16(tmem_base, adesc, bdesc, idesc2, (c > 0 || k != 0) ? 1u : 0u);
+            }
+            umma_commit(&hdr->w_empty[stage]);
+            umma_commit(&hdr->h_free[hb]);
+            if (++stage == kMlpStages) { stage = 0; phase ^= 1; }
+          }
+          if (c + 4 < NC) {  // fc1 chunk c+4: pre[pb] = A[128 x D] * W1[64 x D]^T
+            const uint32_t g = g0 + uint32_t(c + 4), pb = g & 3u;
+            mbar_wait(&hdr->pre_free[pb], ((g >> 2) & 1u) ^ 1u);
+            mbar_wait(&hdr->w_full[stage], phase);
+            tc_fence_after();
+            const uint32_t sb = ring_s + stage * kMlpStageBytes;
+            const uint32_t d_tmem = tmem_base + kMlpTmemPre + pb * kMlpHC;
             for (int ks = 0; ks < ks1; ++ks) {
               const int kb = ks >> 2, k = ks & 3;
               const uint64_t adesc = umma_sdesc_sw128(a_s + kb * 16384 + k * 32, 16, 1024);
@@ -167,28 +195,13 @@ mlp_fwd_kernel(const MlpFwdParams p, const __grid_constant__ CUtensorMap mapW1, 
               umma_bf16(d_tmem, adesc, bdesc, idesc1, ks != 0);
             }
             umma_commit(&hdr->w_empty[stage]);
-            umma_commit(&hdr->pre_full[b]);
+            umma_commit(&hdr->pre_full[pb]);
             if (++stage == kMlpStages) { stage = 0; phase ^= 1; }
-          }
-          if (c >= 0) {  // fc2 chunk c: out += h[b][128 x 64] * W2[D x 64]^T
-            const uint32_t g = g0 + uint32_t(c), b = g & 1u;
-            if (c == 0) mbar_wait(&hdr->out_free, (t & 1u) ^ 1u);  // previous tile's output has been read out of TMEM
-            mbar_wait(&hdr->h_ready[b], (g >> 1) & 1u);
-            mbar_wait(&hdr->w_full[stage], phase);
-            tc_fence_after();
-            const uint32_t sb = ring_s + stage * kMlpStageBytes;
-#pragma unroll
-            for (int k = 0; k < kMlpHC / 16; ++k) {
-              const uint64_t adesc = umma_sdesc_sw128(h_s + b * 16384 + k * 32, 16, 1024);
-              const uint64_t bdesc = umma_sdesc_sw128(sb + k * 32, 16, 1024);
-              umma_bf16(tmem_base, adesc, bdesc, idesc2, (c > 0 || k != 0) ? 1u : 0u);
-            }
-            umma_commit(&hdr->w_empty[stage]);
-            umma_commit(&hdr->h_free[b]);
-            if (++stage == kMlpStages) { stage = 0; phase ^= 1; }
+            if (t == 1 && c >= 0) MLP_TS(2, 3 + 2 * c);
           }
         }
         umma_commit(&hdr->out_full);
+        if (t == 1) MLP_TS(2, 40);
         g0 += uint32_t(NC);
       }
     }
@@ -213,28 +226,28 @@ mlp_fwd_kernel(const MlpFwdParams p, const __grid_constant__ CUtensorMap mapW1, 
     const int grp = ew >> 2;        // which of the quarter's four warps
     const uint32_t half = uint32_t(grp >> 1), sub = uint32_t(grp & 1);  // GELU epilogue: chunk parity / 32-column half
     const uint32_t tab_s = smem_u32(smem + kMlpOffTabP) - kGeluLo * 4;
-    // LayerNorm affine parameters of this lane's columns: 64 j + 2 lane, j = 0..2
-    float2 gm[3], bt[3];
-    bool has[3];
+    // LayerNorm prologue mapping: 8 lanes per row (4 rows per warp instruction); lane `sub` owns the float4 column groups
+    // 4 sub + 32 j, j = 0..5 (D <= 192), i.e. 16 B of every 128-byte line of the row: coalesced loads, 3 shuffle steps
+    const int lsub = lane & 7, lrow = lane >> 3;
+    bool has[6];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int c = 64 * j + 2 * lane;
-      has[j] = c < D;
-      gm[j] = bt[j] = make_float2(0.f, 0.f);
-      if (has[j]) { gm[j] = *reinterpret_cast<const float2*>(p.gamma + c); bt[j] = *reinterpret_cast<const float2*>(p.beta + c); }
-    }
+    for (int j = 0; j < 6; ++j) has[j] = 4 * lsub + 32 * j < D;
     const float invD = 1.0f / float(D);
     uint8_t* stg = smem + kMlpOffA + ew * (32 * kMlpStgRow);
     uint32_t g0 = 0, t = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++t) {
       const int row0 = tile * BM;
+      const int role = ew == 0 ? 0 : (ew == 8 ? 1 : 3);  // timeline only
+      int kth = 0;
+      if (t == 1 && role < 3) MLP_TS(role, 0);
       // ---------------- LayerNorm prologue: rows [8 ew, 8 ew + 8) of the tile ----------------
       {
-        float2 v[8][3];
-        long long srow[8];
+        float4 v[2][6];
+        long long srow[2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int gr = row0 + ew * 8 + i;
+        for (int i = 0; i < 2; ++i) {
+          const int lr = ew * 8 + i * 4 + lrow;
+          const int gr = row0 + lr;
           long long sr = -1;
           if (gr < p.rows) {
             sr = gr;
@@ -242,45 +255,59 @@ mlp_fwd_kernel(const MlpFwdParams p, const __grid_constant__ CUtensorMap mapW1, 
               sr = (long long)(uint32_t(gr) / uint32_t(p.n_sel)) * p.L_src + __ldg(p.gather_idx + gr);
           }
           srow[i] = sr;
-          if (lane == 0) hdr->rowmap[ew * 8 + i] = int(sr);
+          if (lsub == 0) hdr->rowmap[lr] = int(sr);
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            v[i][j] = make_float2(0.f, 0.f);
-            if (has[j] && sr >= 0) v[i][j] = *reinterpret_cast<const float2*>(p.x + sr * D + 64 * j + 2 * lane);
+          for (int j = 0; j < 6; ++j) {
+            v[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has[j] && sr >= 0) v[i][j] = *reinterpret_cast<const float4*>(p.x + sr * D + 4 * lsub + 32 * j);
           }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int lr = ew * 8 + i;
+        for (int i = 0; i < 2; ++i) {
+          const int lr = ew * 8 + i * 4 + lrow;
           float s = 0.f;
 #pragma unroll
-          for (int j = 0; j < 3; ++j) s += v[i][j].x + v[i][j].y;
-          const float mu = warp_sum(s) * invD;
+          for (int j = 0; j < 6; ++j) s += (v[i][j].x + v[i][j].y) + (v[i][j].z + v[i][j].w);
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          s += __shfl_xor_sync(0xffffffffu, s, 4);
+          const float mu = s * invD;
           float sq = 0.f;
 #pragma unroll
-          for (int j = 0; j < 3; ++j)
+          for (int j = 0; j < 6; ++j)
             if (has[j]) {
-              const float a = v[i][j].x - mu, b = v[i][j].y - mu;
-              sq += a * a + b * b;
+              const float a = v[i][j].x - mu, b = v[i][j].y - mu, c = v[i][j].z - mu, d = v[i][j].w - mu;
+              sq += (a * a + b * b) + (c * c + d * d);
             }
-          const float rs = rsqrtf(warp_sum(sq) * invD + p.eps);
+          sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+          sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+          sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+          const float rs = rsqrtf(sq * invD + p.eps);
           const bool ok = srow[i] >= 0;
           const long long gr = row0 + lr;
+          // row lr of K panel j/2: 16-byte chunk 4 (j & 1) + sub / 2 (swizzled by the row), 8 bytes at (sub & 1) * 8
+          const uint32_t srow_s = a_s + uint32_t(lr) * 128u + uint32_t(lsub & 1) * 8u;
 #pragma unroll
-          for (int j = 0; j < 3; ++j)
+          for (int j = 0; j < 6; ++j)
             if (has[j]) {
-              uint32_t o = 0u;
-              if (ok) o = pack_bf16x2((v[i][j].x - mu) * rs * gm[j].x + bt[j].x, (v[i][j].y - mu) * rs * gm[j].y + bt[j].y);
-              // K panel j, row lr, 16-byte chunk lane/4 (swizzled by the row), 4 bytes at (lane % 4)
-              const uint32_t sa = a_s + j * 16384 + lr * 128 + ((uint32_t(lane >> 2) ^ uint32_t(lr & 7)) << 4) + (lane & 3) * 4;
-              asm volatile("st.shared.u32 [%0], %1;" ::"r"(sa), "r"(o) : "memory");
-              if (ok) *reinterpret_cast<uint32_t*>(p.xn + gr * D + 64 * j + 2 * lane) = o;
+              uint32_t lo = 0u, hi = 0u;
+              if (ok) {  // (the affine parameters come from L1: keeping 12 float4 of them in registers spills)
+                const float4 gm = __ldg(reinterpret_cast<const float4*>(p.gamma + 4 * lsub + 32 * j));
+                const float4 bt = __ldg(reinterpret_cast<const float4*>(p.beta + 4 * lsub + 32 * j));
+                lo = pack_bf16x2((v[i][j].x - mu) * rs * gm.x + bt.x, (v[i][j].y - mu) * rs * gm.y + bt.y);
+                hi = pack_bf16x2((v[i][j].z - mu) * rs * gm.z + bt.z, (v[i][j].w - mu) * rs * gm.w + bt.w);
+              }
+              const uint32_t chunk = uint32_t(4 * (j & 1) + (lsub >> 1));
+              const uint32_t sa = srow_s + uint32_t(j >> 1) * 16384u + ((chunk ^ uint32_t(lr & 7)) << 4);
+              asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sa), "r"(lo), "r"(hi) : "memory");
+              if (ok) *reinterpret_cast<uint2*>(p.xn + gr * D + 4 * lsub + 32 * j) = make_uint2(lo, hi);
             }
-          if (ok && lane == 0) { p.mean[gr] = mu; p.rstd[gr] = rs; }
+          if (ok && lsub == 0) { p.mean[gr] = mu; p.rstd[gr] = rs; }
         }
         fence_proxy_async_smem();  // generic-proxy writes of the A tile -> visible to tcgen05.mma (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&hdr->a_ready);
+        if (t == 1 && role < 3) MLP_TS(role, 1);
       }
       {  // pull this warp's 8 rows of the CTA's next tile into L2 while the current tile is computed
         const int ntile = tile + gridDim.x;
@@ -304,17 +331,19 @@ mlp_fwd_kernel(const MlpFwdParams p, const __grid_constant__ CUtensorMap mapW1, 
       for (int c = 0; c < NC; ++c) {
         const uint32_t g = g0 + uint32_t(c);
         if ((g & 1u) != half) continue;
-        const uint32_t b = half;
-        mbar_wait(&hdr->pre_full[b], (g >> 1) & 1u);
+        const uint32_t b = half, pb = g & 3u;  // GELU tile buffer / fc1 TMEM buffer of this chunk
+        if (t == 1 && role < 3) MLP_TS(role, 2 + 4 * kth);
+        mbar_wait(&hdr->pre_full[pb], (g >> 2) & 1u);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + kMlpTmemPre + b * kMlpHC + sub * 32;
+        if (t == 1 && role < 3) MLP_TS(role, 3 + 4 * kth);
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + kMlpTmemPre + pb * kMlpHC + sub * 32;
         uint32_t raw[2][16];
         tmem_ld16_issue(taddr, raw[0]);
         tmem_ld16_issue(taddr + 16, raw[1]);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&hdr->pre_free[b]);  // the accumulator is in registers: fc1 of chunk c+2 may overwrite it
+        if (lane == 0) mbar_arrive(&hdr->pre_free[pb]);  // the accumulator is in registers: fc1 of chunk c+4 may overwrite it
         const int row = q * 32 + lane;
         const uint32_t hb = h_s + b * 16384, gb = g_s + b * 16384;
 #pragma unroll
@@ -331,8 +360,9 @@ mlp_fwd_kernel(const MlpFwdParams p, const __grid_constant__ CUtensorMap mapW1, 
           for (int i = 0; i < 8; ++i)  // autocast semantics: the linear's output is rounded to bf16 and GELU reads that value
             pre[i] = pack_bf16x2(__uint_as_float(raw[u][2 * i]) + bia[2 * i], __uint_as_float(raw[u][2 * i + 1]) + bia[2 * i + 1]);
           gelu_table8(pre, tab_s, hh, dd);
-          // (the look-ups above overlap chunk c-2's fc2 MMAs and TMA stores, which must be done with the tiles now)
-          if (u == 0) mbar_wait(&hdr->h_free[b], ((g >> 1) & 1u) ^ 1u);
+          // the first group's look-ups overlap chunk c-2's fc2 MMAs and TMA stores, which must be done with the tiles now
+          // (measured: waiting before the loop instead, so that both groups' look-ups can interleave, is 10 % slower)
+          if (u == 0) { mbar_wait(&hdr->h_free[b], ((g >> 1) & 1u) ^ 1u); if (t == 1 && role < 3) MLP_TS(role, 4 + 4 * kth); }
           const int ch = int(sub) * 4 + u * 2;  // 16-byte chunks of the 128-byte row
           sts128(swz128(hb, row, ch), hh[0], hh[1], hh[2], hh[3]);
           sts128(swz128(hb, row, ch + 1), hh[4], hh[5], hh[6], hh[7]);
@@ -342,6 +372,8 @@ mlp_fwd_kernel(const MlpFwdParams p, const __grid_constant__ CUtensorMap mapW1, 
         fence_proxy_async_smem();  // -> visible to tcgen05.mma (A operand) and to the TMA stores
         __syncwarp();
         if (lane == 0) mbar_arrive(&hdr->h_ready[b]);
+        if (t == 1 && role < 3) MLP_TS(role, 5 + 4 * kth);
+        ++kth;
       }
       // ---------------- output epilogue: y = acc + b2 + x, fp32 ----------------
       {
@@ -362,8 +394,10 @@ mlp_fwd_kernel(const MlpFwdParams p, const __grid_constant__ CUtensorMap mapW1, 
             if (sc_begin + u < sc_end && orow[i] >= 0)
               xr[u][i] = *reinterpret_cast<const float4*>(p.x + (long long)orow[i] * D + (sc_begin + u) * 16 + chk * 4);
           }
+        if (t == 1 && role < 3) MLP_TS(role, 30);
         mbar_wait(&hdr->out_full, t & 1u);  // all fc2 MMAs of the tile have completed
         tc_fence_after();
+        if (t == 1 && role < 3) MLP_TS(role, 31);
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
           const int sc = sc_begin + u;
@@ -402,7 +436,9 @@ mlp_fwd_kernel(const MlpFwdParams p, const __grid_constant__ CUtensorMap mapW1, 
       __syncwarp();
       if (lane == 0) mbar_arrive(&hdr->out_free);
       // the staging tiles alias the A panels and rowmap is rewritten by the next prologue: all epilogue warps first
+      if (t == 1 && role < 3) MLP_TS(role, 32);
       named_bar_sync(1, kMlpEpiWarps * 32);
+      if (t == 1 && role < 3) MLP_TS(role, 33);
       g0 += uint32_t(NC);
     }
   }
@@ -431,6 +467,10 @@ extern "C" int mae_mlp_fwd(const float* x, const int64_t* gather_idx, int n_sel,
   p.x = x; p.gather_idx = gather_idx; p.n_sel = n_sel; p.L_src = L_src;
   p.gamma = gamma; p.beta = beta; p.eps = eps; p.b1 = b1; p.b2 = b2;
   p.xn = reinterpret_cast<__nv_bfloat16*>(xn_bf16); p.mean = mean; p.rstd = rstd; p.x_out = x_out;
+  {
+    const char* e = getenv("MAE_MLP_TIMELINE");  // device address of >= 3 x 64 int64 slots (tools/mlp_timeline.py)
+    p.dbg = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+  }
   p.gelu_tab = gelu_table_device_ptr();
   if (!p.gelu_tab) return MAE_ERR_DRIVER;
   CUtensorMap m1, m2, mh, mg;

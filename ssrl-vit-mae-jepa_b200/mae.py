@@ -199,11 +199,12 @@ class MAEEngine:
         # decoder-input assembly fused with the first decoder block's norm1: correct, but measured slower than the two
         # launches it replaces (8.27 vs 8.16 ms/step: 80 registers, dependent index -> pos loads), so opt-in only
         self.scatter_ln = os.environ.get("MAE_SCATTER_LN", "0") == "1"
-        # norm2 + fc1 + GELU + fc2 + residual as one tcgen05 kernel for D <= 192 (csrc/mlp_fused.cu).  Correct (GPU tests run
-        # it against the three launches and torch), moves 35 % fewer HBM bytes, but measured slower: the GELU table look-up
-        # epilogue is instruction-issue bound (~13 instructions per element at 16 epilogue warps), and LayerNorm / output
-        # epilogue run as serial phases of the same warps (profiles/r02_mlp_fused.md).  Opt-in: MAE_FUSED_MLP=1
-        self.fused_mlp = os.environ.get("MAE_FUSED_MLP", "0") == "1"
+        # norm2 + fc1 + GELU + fc2 + residual as one tcgen05 kernel for D <= 192 (csrc/mlp_fused.cu): 35 % fewer HBM bytes,
+        # but its epilogues are instruction-issue / latency bound (profiles/r02_mlp_fused.md).  Measured at B = 2000: faster
+        # than the three launches when the stream is L2-resident (encoder, 72 k x 144: 103 vs 117 us), slower on the
+        # HBM-sized decoder streams (554 vs 466 us).  Default "auto": fused where rows * D * 4 B fits in ~half of L2.
+        # MAE_FUSED_MLP=1 / 0 forces it on / off everywhere.
+        self.fused_mlp = {"1": "on", "0": "off"}.get(os.environ.get("MAE_FUSED_MLP", "auto"), "auto")
         # patch gather + patch-embed GEMM + bias / pos / class-token assembly in one launch (MAE_FUSED_PATCH_EMBED=0: three)
         self.fused_patch_embed = os.environ.get("MAE_FUSED_PATCH_EMBED", "1") != "0"
         self._side_skip = False
@@ -394,8 +395,10 @@ class MAEEngine:
     def _use_masked_tail(self) -> bool:
         return self.masked_tail and len(self.dec_blocks) > 0 and self.dims["Dd"] <= 256
 
-    def _use_fused_mlp(self, D: int) -> bool:
-        return self.fused_mlp and 64 <= D <= 192 and D % 16 == 0
+    def _use_fused_mlp(self, D: int, rows: int = 0) -> bool:
+        if self.fused_mlp == "off" or not (64 <= D <= 192 and D % 16 == 0):
+            return False
+        return self.fused_mlp == "on" or rows * D * 4 <= 64 * 1024 * 1024
 
     def _block_fwd(self, w: _BlockW, s: Dict[str, torch.Tensor], x_out: Optional[torch.Tensor], M: int, B: int, L: int,
                    st: int, tail: bool = False, skip_norm1: bool = False):
@@ -411,7 +414,7 @@ class MAEEngine:
         calls.mae_attention_fwd(_ptr(s["qkv"]), B, L, H, hd, _ptr(s["att"]), _ptr(s["lse"]), st)
         calls.mae_gemm_tn(_ptr(s["att"]), self.pw(w.projw), M, D, D, EPI_RESID_F32, self.pf(w.projb),
                           _ptr(s["x_mid"]), None, _ptr(s["x_in"]), st)
-        if self._use_fused_mlp(D):
+        if self._use_fused_mlp(D, self.dims["Mm"] if tail else M):
             # norm2 -> fc1 -> GELU -> fc2 -> + residual in one launch (csrc/mlp_fused.cu); the tail variant gathers the
             # idx_mask rows on the way in and leaves the compact fp32 sums  x_mid[idx_mask] + mlp(...)  in x_dec
             ws, d = self.ws, self.dims
@@ -573,7 +576,7 @@ class MAEEngine:
             x_out = ws["dec"][i + 1]["x_in"] if i + 1 < n_dec else ws["x_dec"]
             self._block_fwd(w, ws["dec"][i], x_out, d["Md"], B, L, st, tail=tail and i == n_dec - 1,
                             skip_norm1=fused_ln and i == 0)
-        if tail and self._use_fused_mlp(Dd):
+        if tail and self._use_fused_mlp(Dd, d["Mm"]):
             # the fused MLP kernel already left the compact sums in x_dec: plain LayerNorm over Mm rows
             calls.mae_layernorm_fwd(_ptr(ws["x_dec"]), self.pf(o("decoder.decoder_norm.weight")),
                                     self.pf(o("decoder.decoder_norm.bias")), None, 0, 0, d["Mm"], Dd, LN_EPS,

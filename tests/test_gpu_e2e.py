@@ -136,9 +136,16 @@ def test_full_size_batch_properties():
     assert (allidx.sort(1).values == torch.arange(145, device="cuda")).all()
     t_ref = O.get_at_index(O.patchify(images, 8), ws["idx_mask"] - 1)
     assert torch.equal(target, t_ref) and pred.shape == (B, 109, 192) and torch.isfinite(pred.float()).all()
-    # batch-split consistency: the first 100 samples alone give the same predictions
+    # batch-split consistency: the first 100 samples alone give the same predictions.  The default schedule depends on the
+    # batch (the fused MLP kernel runs where the stream is L2-resident, i.e. in every block at B = 100 but only in the
+    # encoder at B = 2000), so the bit-level comparison pins one schedule; across schedules: bf16 rounding noise only
+    p100_auto, _ = mod.model(images[:100].contiguous(), noise=noise[:100].contiguous())
+    assert rel_err(p100_auto, pred[:100]) < 1e-2
+    mod.model.engine.fused_mlp = "off"
+    pred_off, _ = mod.model(images, noise=noise)
     p100, _ = mod.model(images[:100].contiguous(), noise=noise[:100].contiguous())
-    assert max_err(p100, pred[:100]) < 1e-6
+    assert max_err(p100, pred_off[:100]) < 1e-6
+    mod.model.engine.fused_mlp = "auto"
     l0 = tr.train_step(images, noise)
     for _ in range(3):
         l = tr.train_step(images, noise)
@@ -268,3 +275,28 @@ def test_masked_tail_matches_all_rows_schedule():
     report("masked_tail", loss_all_rows=l0, loss_tail=l1, pred_rel=rel_err(p1, p0))
     assert abs(l1 - l0) / abs(l0) < 1e-3 and rel_err(p1, p0) < 1e-2
     check_grads("masked_tail_grad", g1, g0)
+
+
+def test_fused_mlp_matches_three_launch_schedule():
+    """norm2 -> fc1 -> GELU -> fc2 -> + residual as one launch (mae_mlp_fwd; default where the stream is L2-resident, forced on
+    here for every block incl. the masked tail) against the three-launch schedule: same loss, predictions and gradients up
+    to the summation order of the LayerNorm statistics (1 bf16 ulp on a few xn values) and, for the tail, the bf16 rounding
+    of mlp.fc2's output that only the three-launch masked tail performs."""
+    _, m = make_pair()
+    eng = m.engine
+    torch.manual_seed(10)
+    images = torch.randn(48, 3, 96, 96, device="cuda")
+    noise = torch.rand(48, 145, device="cuda")
+    got = {}
+    for mode in ("off", "on"):
+        eng.fused_mlp = mode
+        loss, pred, _ = m.forward_loss(images, noise=noise)
+        eng.backward()
+        torch.cuda.synchronize()
+        got[mode] = (loss.item(), pred.detach().float().cpu().clone(),
+                     {n: g.detach().float().cpu().clone() for n, g in eng.named_grads().items()})
+    eng.fused_mlp = "auto"
+    (l0, p0, g0), (l1, p1, g1) = got["off"], got["on"]
+    report("fused_mlp", loss_three=l0, loss_fused=l1, pred_rel=rel_err(p1, p0))
+    assert abs(l1 - l0) / abs(l0) < 1e-3 and rel_err(p1, p0) < 1e-2
+    check_grads("fused_mlp_grad", g1, g0)
