@@ -220,6 +220,8 @@ def algorithmic_cost(name, a):
         return a[2] * a[3] * a[6] * 4.0, 0.0, f"rows={a[2] * a[3]} D={a[6]}"
     if name == "mae_cast_bf16":
         return a[2] * 6.0, 0.0, f"n={a[2]}"
+    if name == "mae_allreduce_avg_sumsq":
+        return a[1] * a[3] * 4.0 + a[3] * 4.0, 0.0, f"world={a[1]} n={a[3]}"  # (world - 1) of the reads cross NVLink
     if name == "mae_grad_sumsq":
         return a[1] * 4.0, 0.0, f"n={a[1]}"
     if name == "mae_clip_adamw":
@@ -372,7 +374,11 @@ def run_ours(args):
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev)
+    rank_ms = [ms / args.steps]
     if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        rank_ms = [x.item() / args.steps for x in allt]  # per-rank device time per step: the skew the MAX is made of
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item()
     value = world * B * args.steps / (ms * 1e-3)
@@ -426,6 +432,9 @@ def run_ours(args):
     if rank == 0:
         pk = peaks()
         share, roof, extra = kernel_breakdown(tr, pool[0], None, pk)
+        extra["rank_ms_per_step"] = [round(x, 4) for x in rank_ms]
+        extra["grad_exchange"] = ("p2p: own kernel over NVLink peer memory (mae_allreduce_avg_sumsq)" if getattr(tr, "_peer", None)
+                                  is not None else ("nccl buckets" if world > 1 else None))
         extra["replica_param_maxdiff"] = replica_maxdiff  # N > 1: max |param(rank i) - param(rank j)| after all steps; must be 0.0
         extra["e2e_uint8_gpu_augment"] = {"value": e2e_u8_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * IMG * IMG,
                                           "note": "uint8 host batches; crop boxes / flips drawn on the device, RandomResizedCrop/flip/normalize on the prefetch stream, all inside the timed loop"}

@@ -194,6 +194,16 @@ int mae_clip_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, l
                    float beta2, float eps, float weight_decay, float max_norm, int step, const float* partials,
                    int n_partials, float* grad_norm_out, mae_stream_t stream);
 
+/* Data-parallel gradient exchange over NVLink peer memory, fused with the first pass of the global-norm clip:
+ *   out[offset + i] = (1/world) * sum_r peers[r][offset + i],  i < n;   partials[b] = sum of out^2 over block b's elements.
+ * peer_ptrs_dev: DEVICE array of `world` pointers to the ranks' flat fp32 gradient buffers (symmetric memory: peer-mapped
+ * over NVLink; entry `rank` is the local buffer).  Fixed summation order r = 0..world-1: bit-identical on every rank.
+ * The caller orders it behind a cross-rank barrier (every rank's bucket is complete) and must not reuse the gradient
+ * buffers before a second barrier.  n, offset % 4 == 0; world <= 16; writes `nblocks` partials (feed mae_clip_adamw).
+ * Replaces ncclAllReduce(avg) + mae_grad_sumsq (reference: devices=1, scripts/training/pretrain_mae.py:116-118). */
+int mae_allreduce_avg_sumsq(const void* peer_ptrs_dev, int world, long long offset, long long n, float* out,
+                            float* partials, int nblocks, mae_stream_t stream);
+
 /* The input transform that precedes the hot path (reference src/data.py:15-34), on the GPU: for sample b, crop
  * rows [i, i+h) x cols [j, j+w) of the uint8 image (B,C,Hs,Ws; torchvision STL10.data layout), resize to S x S exactly
  * like Pillow's 8-bit bilinear ImagingResample (what RandomResizedCrop does to a PIL image: two separable fixed-point

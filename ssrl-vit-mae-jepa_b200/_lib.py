@@ -40,6 +40,7 @@ SIGNATURES = {
     "mae_augment_params": [_vp, _i, _i, _i, _f, _f, _f, _f, C.c_ulonglong, C.c_ulonglong, _i, _vp],
     "mae_cast_bf16": [_vp, _vp, _ll, _vp],
     "mae_transpose_cast_bf16": [_vp, _vp, _vp, _i, _i, _i, _vp],
+    "mae_allreduce_avg_sumsq": [_vp, _i, _ll, _ll, _vp, _vp, _i, _vp],
     "mae_grad_sumsq": [_vp, _ll, _vp, _i, _vp],
     "mae_clip_adamw": [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _f, _i, _vp, _i, _vp, _vp],
 }

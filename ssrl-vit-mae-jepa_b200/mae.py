@@ -758,15 +758,19 @@ class MAEEngine:
 
     # ---------------- optimizer ----------------
     def clip_adamw(self, lr: float, weight_decay: float = 0.05, betas=(0.9, 0.999), eps: float = 1e-8,
-                   max_norm: float = 1.0) -> torch.Tensor:
+                   max_norm: float = 1.0, grads: Optional[torch.Tensor] = None, n_partials: int = 0) -> torch.Tensor:
         """Lightning clip-by-norm + AdamW over the flat buffers; refreshes the bf16 shadows.  Returns the
-        (device) pre-clip gradient norm."""
+        (device) pre-clip gradient norm.  ``grads`` / ``n_partials``: an already reduced gradient buffer whose sum-of-
+        squares partials are in ``self.partials[:n_partials]`` (the peer-memory all-reduce produces both)."""
         st = torch.cuda.current_stream(self.flat.device).cuda_stream
         self._wg_join()  # (a no-op after backward(); orders a pending W^T refresh before the weights change again)
         self.step_count += 1
-        nparts = 1024
-        calls.mae_grad_sumsq(self.grads.data_ptr(), self.n_opt, self.partials.data_ptr(), nparts, st)
-        calls.mae_clip_adamw(self.flat.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(),
+        if grads is None:
+            grads, nparts = self.grads, 1024
+            calls.mae_grad_sumsq(grads.data_ptr(), self.n_opt, self.partials.data_ptr(), nparts, st)
+        else:
+            nparts = n_partials
+        calls.mae_clip_adamw(self.flat.data_ptr(), grads.data_ptr(), self.exp_avg.data_ptr(),
                              self.exp_avg_sq.data_ptr(), self.flat_bf16.data_ptr(), self.n_opt, float(lr), betas[0],
                              betas[1], eps, weight_decay, max_norm, self.step_count, self.partials.data_ptr(), nparts,
                              self.grad_norm.data_ptr(), st)

@@ -13,12 +13,14 @@ autograd graph and no host synchronisation.
 from __future__ import annotations
 
 import math
+import os
 from typing import Any, Dict, List, Optional, Tuple
 
 import torch
 from torch.optim import AdamW
 from torch.optim.lr_scheduler import LambdaLR
 
+from ._lib import calls
 from .mae import MaskedAutoencoder
 
 from .shims import install as _install_shims
@@ -126,6 +128,55 @@ class GradBuckets:
             self.flat.div_(dist.get_world_size(self.group))
 
 
+class PeerGradReducer:
+    """Gradient exchange through NVLink peer memory instead of NCCL (``csrc/collective.cu``): the engine's flat gradient
+    buffer is re-homed in symmetric memory (``torch.distributed._symmetric_memory``: one allocation per rank, all of them
+    mapped into every process of the node), and per bucket ``mae_allreduce_avg_sumsq`` reads all ranks' slices over
+    NVLink, averages them in a fixed order (bit-identical on every rank) into a local buffer and emits the
+    sum-of-squares partials of the clip in the same pass.  Cross-rank ordering: a symmetric-memory barrier before each
+    bucket (every rank's backward has produced it) and one after the last (nobody still reads what the next backward
+    zeroes); everything runs on a side stream, so the compute stream never waits for a peer during backward."""
+
+    NBLK = 128  # CTAs (and sum-of-squares partials) per bucket
+
+    def __init__(self, engine, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self.engine = engine
+        dev = engine.flat.device
+        group = group if group is not None else dist.group.WORLD
+        if hasattr(symm, "is_symm_mem_enabled_for_group") and not symm.is_symm_mem_enabled_for_group(group.group_name):
+            symm.enable_symm_mem_for_group(group.group_name)
+        self.sym = symm.empty(engine.n_opt, dtype=torch.float32, device=dev)
+        self.hdl = symm.rendezvous(self.sym, group)
+        self.sym.zero_()
+        engine.grads = self.sym  # backward now accumulates straight into the peer-visible buffer
+        self.out = torch.zeros(engine.n_opt, dtype=torch.float32, device=dev)
+        self.world = self.hdl.world_size
+        self.bounds = engine.grad_bucket_boundaries()
+        self.n_partials = self.NBLK * (len(self.bounds) - 1)
+        self.stream = torch.cuda.Stream(dev)
+
+    def launch(self, i: int) -> None:
+        eng, dev = self.engine, self.engine.flat.device
+        lo, hi = self.bounds[i], self.bounds[i + 1]
+        cs = self.stream
+        cs.wait_stream(torch.cuda.current_stream(dev))
+        if eng._side is not None:
+            cs.wait_stream(eng._side)
+        with torch.cuda.stream(cs):
+            self.hdl.barrier(channel=0)  # every rank has produced this bucket
+            calls.mae_allreduce_avg_sumsq(self.hdl.buffer_ptrs_dev, self.world, lo, hi - lo, self.out.data_ptr(),
+                                          eng.partials.data_ptr() + 4 * self.NBLK * i, self.NBLK, cs.cuda_stream)
+
+    def finish(self) -> None:
+        dev = self.engine.flat.device
+        with torch.cuda.stream(self.stream):
+            self.hdl.barrier(channel=0)  # every rank has read every bucket: the gradient buffers may be reused
+        torch.cuda.current_stream(dev).wait_stream(self.stream)
+
+
 class FusedTrainer:
     """fwd + masked-MSE + bwd + grad all-reduce + clip + AdamW on one stream through the C ABI.
 
@@ -145,6 +196,9 @@ class FusedTrainer:
             if distributed is None else distributed
         self._buckets: Optional[GradBuckets] = None
         self._comm_trigger = None
+        # gradient exchange: "p2p" = our own kernel over NVLink peer memory (default on CUDA), "nccl" = bucketed ncclAllReduce
+        self.exchange = os.environ.get("MAE_GRAD_EXCHANGE", "p2p")
+        self._peer: Optional[PeerGradReducer] = None
 
     def set_epoch(self, epoch: int) -> None:
         self.epoch = epoch
@@ -161,6 +215,24 @@ class FusedTrainer:
             # stem + first encoder block bucket (1.1 MB) is still in flight when backward ends
             self._buckets = GradBuckets(eng.grads, eng.grad_bucket_boundaries())
         return self._buckets
+
+    def _ensure_peer(self) -> Optional[PeerGradReducer]:
+        """The peer-memory reducer, or None when NCCL is to be used (``MAE_GRAD_EXCHANGE=nccl``, CPU tensors, or symmetric
+        memory cannot be set up on this system: the reason is printed once)."""
+        eng = self.engine
+        if self.exchange != "p2p" or eng.flat.device.type != "cuda":
+            return None
+        if self._peer is not None and self._peer.sym.data_ptr() == eng.grads.data_ptr():
+            return self._peer
+        try:
+            self._peer = PeerGradReducer(eng)
+        except Exception as e:  # noqa: BLE001 - no P2P / symmetric-memory support here
+            import torch.distributed as dist
+
+            if dist.get_rank() == 0:
+                print(f"[FusedTrainer] peer-memory gradient exchange unavailable ({e!r}); using NCCL buckets")
+            self.exchange, self._peer = "nccl", None
+        return self._peer
 
     def _launch_bucket(self, i: int) -> None:
         """Starts bucket ``i``'s all-reduce behind everything enqueued so far on the compute stream AND on the engine's
@@ -182,14 +254,22 @@ class FusedTrainer:
         """One optimisation step; returns the 0-dim device loss tensor (no host sync)."""
         eng = self.engine
         _, _, loss = eng.forward(images, noise, self.model.mask_ratio)
+        reduced, n_partials = None, 0
         if self.distributed:
             eng._ensure_flat(images.device)
-            self._ensure_buckets()
-            eng.backward(bucket_cb=self._launch_bucket)
-            self._buckets.finish()  # the compute stream waits for every bucket's collective
+            peer = self._ensure_peer()
+            if peer is not None:
+                eng.backward(bucket_cb=peer.launch)
+                peer.finish()
+                reduced, n_partials = peer.out, peer.n_partials
+            else:
+                self._ensure_buckets()
+                eng.backward(bucket_cb=self._launch_bucket)
+                self._buckets.finish()  # the compute stream waits for every bucket's collective
         else:
             eng.backward()
-        eng.clip_adamw(self.current_lr(), weight_decay=self.module.weight_decay, max_norm=self.max_norm)
+        eng.clip_adamw(self.current_lr(), weight_decay=self.module.weight_decay, max_norm=self.max_norm, grads=reduced,
+                       n_partials=n_partials)
         return loss[0].clone()  # the workspace scalar is overwritten by the next step
 
 

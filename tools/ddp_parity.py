@@ -6,7 +6,7 @@ ranks' noise concatenated in rank order.  Because the loss is a mean over equall
 equals the single-process gradient (reference `src/training/mae.py:45-50`, `configs/mae.yaml:27`), so after S steps:
   * all ranks hold bit-identical parameters (max |diff| must be exactly 0.0),
   * they equal the single-process parameters up to the summation order of the fp32 gradient reductions
-    (rel-L2 per tensor: <= 1e-5 for every weight / token / LayerNorm-scale tensor; <= 1e-3 for the zero-initialised biases,
+    (rel-L2 per tensor: <= 1e-5 for every weight / token / LayerNorm-scale tensor; <= 5e-3 for the zero-initialised biases,
     which after a few steps consist of nothing but the accumulated update; the zero-gradient K third of attn.qkv.bias excluded),
   * the mean of the per-rank losses equals the single-process loss (rel <= 1e-5).
 Prints one JSON line on rank 0 and exits non-zero on failure."""
@@ -85,12 +85,12 @@ def main() -> int:
             elif d > worst:
                 worst, worst_name = d, n
         loss_rel = max(abs(x - y) / abs(y) for x, y in zip(losses, losses1))
-        ok = replica_maxdiff == 0.0 and worst <= 1e-5 and worst_b <= 1e-3 and loss_rel <= 1e-5
+        ok = replica_maxdiff == 0.0 and worst <= 1e-5 and worst_b <= 5e-3 and loss_rel <= 1e-5
         print(json.dumps({"tool": "ddp_parity", "world": world, "per_rank_batch": a.batch, "steps": a.steps,
                           "replica_param_maxdiff": replica_maxdiff, "weights_worst_rel_vs_single": worst,
                           "worst_tensor": worst_name, "zero_init_biases_worst_rel_vs_single": worst_b,
                           "worst_bias": worst_b_name, "loss_ddp": losses, "loss_single": losses1,
-                          "loss_worst_rel": loss_rel, "ok": ok}))
+                          "loss_worst_rel": loss_rel, "grad_exchange": "p2p" if tr._peer is not None else "nccl", "ok": ok}))
     dist.barrier()
     dist.destroy_process_group()
     return 0 if ok else 1
