@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "MAE pretrain images/sec (fwd+bwd+AdamW, device-timed)"  # BASELINE.json's metric; the reference arm is host-timed
-GEMM_TN_DRAM_BYTES_PER_STEP = 11.413e9  # profiles/r01r_gemm_tn_dram_traffic.csv (B=2000, 53 launches)
+GEMM_TN_DRAM_BYTES_PER_STEP = 10.332e9  # profiles/r02_gemm_tn_dram_traffic.csv (B=2000, the 44 gemm_tn launches of one step)
 FLOPS_PER_IMAGE = 1_124_504_064  # fwd+bwd, patch-embed on kept patches only, no patch-embed dgrad
 CFG = {
     "general": {"image_size": 96, "patch_size": 8, "in_chans": 3},
