@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmae_b200.so")
-SOURCES = ["gemm.cu", "mlp_fused.cu", "patch_embed.cu", "attention.cu", "attention_tc.cu", "elementwise.cu", "augment.cu", "collective.cu"]
+SOURCES = ["gemm.cu", "mlp_fused.cu", "patch_embed.cu", "attention.cu", "attention_tc.cu", "attention_enc.cu", "elementwise.cu", "augment.cu", "collective.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",

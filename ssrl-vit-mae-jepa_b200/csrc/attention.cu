@@ -464,6 +464,7 @@ extern "C" int mae_attention_fwd(const void* qkv, int B, int L, int H, int hd, v
   {
     static const bool no_tc = getenv("MAE_ATTN_NO_TC") != nullptr;  // A/B switch: keep everything on the mma.sync kernels
     if (!no_tc && hd == 32 && L > 128 && L <= 160 && (H % 2) == 0) return attn_fwd_tc(qkv, B, L, H, out, lse, stream);
+    if (!no_tc && attn_enc_covers(L, hd)) return attn_fwd_enc(qkv, B, L, H, hd, out, lse, stream);
   }
   MAE_ATTN_DISPATCH(launch_fwd, qkv, B, L, H, out, lse, stream)
 }
@@ -477,6 +478,7 @@ extern "C" int mae_attention_bwd(const void* qkv, const void* out, const void* d
   {
     static const bool no_tc = getenv("MAE_ATTN_NO_TC") != nullptr || getenv("MAE_ATTN_NO_TC_BWD") != nullptr;
     if (!no_tc && hd == 32 && L > 128 && L <= 160 && (H % 2) == 0) return attn_bwd_tc(qkv, out, dout, lse, B, L, H, dqkv, stream);
+    if (!no_tc && attn_enc_covers(L, hd)) return attn_bwd_enc(qkv, out, dout, lse, B, L, H, hd, dqkv, stream);
   }
   MAE_ATTN_DISPATCH(launch_bwd, qkv, out, dout, lse, B, L, H, dqkv, stream)
 }

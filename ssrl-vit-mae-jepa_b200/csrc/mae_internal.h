@@ -14,6 +14,11 @@ int make_tmap_bf16(CUtensorMap* map, const void* ptr, int rows, int cols, int ld
 int attn_fwd_tc(const void* qkv, int B, int L, int H, void* out, float* lse, cudaStream_t st);
 int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, int B, int L, int H, void* dqkv,
                 cudaStream_t st);
+// attention_enc.cu: tcgen05 attention for short rows (L <= 64, head_dim 8..32): several samples per 128-row tile
+bool attn_enc_covers(int L, int hd);
+int attn_fwd_enc(const void* qkv, int B, int L, int H, int hd, void* out, float* lse, cudaStream_t st);
+int attn_bwd_enc(const void* qkv, const void* out, const void* dout, const float* lse, int B, int L, int H, int hd,
+                 void* dqkv, cudaStream_t st);
 }
 
 // Launch with the programmatic-dependent-launch attribute (see ptx.cuh: pdl_trigger / pdl_wait).

@@ -374,7 +374,11 @@ def test_gemm_wgrad(M, Pc, Qc):
                                       (1, 160, 1, 32), (1, 1, 1, 24), (2, 49, 12, 64), (2, 197, 16, 32), (1, 197, 12, 64),
                                       (1, 208, 2, 64), (2, 99, 3, 64),
                                       # the tcgen05 forward (128 < L <= 160, hd 32, even H): ragged L, one / many items per CTA
-                                      (1, 129, 2, 32), (3, 160, 4, 32), (2, 131, 6, 32), (250, 145, 6, 32)])
+                                      (1, 129, 2, 32), (3, 160, 4, 32), (2, 131, 6, 32), (250, 145, 6, 32),
+                                      # the short-row tcgen05 kernels (L <= 64, hd <= 32): every row pitch (16 / 32 / 40 / 48 / 64),
+                                      # batches that are not a multiple of the samples per tile, head dims 8 .. 32
+                                      (7, 36, 6, 24), (500, 36, 6, 24), (9, 16, 3, 8), (5, 33, 2, 16), (4, 40, 1, 32), (5, 48, 2, 24),
+                                      (3, 64, 4, 32), (3, 57, 2, 24), (17, 9, 5, 32)])
 def test_attention_fwd_bwd(B, L, H, hd):
     D = H * hd
     g = torch.Generator().manual_seed(L * 7 + hd)
@@ -432,6 +436,39 @@ def test_attention_tc_repeatable_and_item_distribution(B, L, H):
         ref.backward(dout[b:b + 1].float())
         assert max_err(out[b:b + 1], ref) < 2e-2
         assert rel_err(dqkv[b:b + 1], qf.grad) < 3e-2
+
+
+@pytest.mark.parametrize("B,L,H,hd", [(1, 36, 1, 24), (2, 36, 6, 24), (148 * 3 + 1, 36, 2, 24), (1000, 36, 6, 24), (301, 17, 2, 32)])
+def test_attention_enc_repeatable_and_item_distribution(B, L, H, hd):
+    """The short-row tcgen05 attention (encoder shape: several samples per 128-row tile, two softmax groups alternating over a
+    persistent CTA's items): bit-identical from run to run, correct for one item, fewer / more items than CTAs, odd item counts
+    per CTA (the two groups get different numbers of items) and a last tile with missing samples; outputs outside the tensors'
+    live rows must not be touched (canary rows of NaN stay NaN-free inside, and a guard region after the buffers stays intact)."""
+    D = H * hd
+    g = torch.Generator().manual_seed(B + L)
+    qkv = bf(torch.randn(B, L, 3, H, hd, generator=g)).to(dev)
+    dout = bf(torch.randn(B, L, D, generator=g)).to(dev)
+    outs = []
+    for _ in range(3):
+        out = torch.full((B + 1, L, D), float("nan"), dtype=torch.bfloat16, device=dev)
+        lse = torch.full((B + 1, H, L), float("nan"), device=dev)
+        dqkv = torch.full((B + 1, L, 3, H, hd), float("nan"), dtype=torch.bfloat16, device=dev)
+        calls.mae_attention_fwd(p(qkv), B, L, H, hd, p(out), p(lse), stream())
+        calls.mae_attention_bwd(p(qkv), p(out), p(dout), p(lse), B, L, H, hd, p(dqkv), stream())
+        assert torch.isnan(out[B].float()).all() and torch.isnan(lse[B]).all() and torch.isnan(dqkv[B].float()).all()  # guard
+        outs.append((out[:B], lse[:B], dqkv[:B]))
+    for o in outs[1:]:
+        assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2])
+    out, lse, dqkv = outs[0]
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all() and torch.isfinite(dqkv.float()).all()
+    qf = qkv.float().requires_grad_(True)
+    q, k, v = qf.permute(2, 0, 3, 1, 4).unbind(0)
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, L, D)
+    ref.backward(dout.float())
+    assert max_err(out, ref) < 2e-2
+    for b in sorted({0, B // 2, B - 1}):  # per-sample bound as well: a swapped sample slot would hide in a global norm
+        assert rel_err(dqkv[b], qf.grad[b]) < 3e-2
+    assert rel_err(dqkv, qf.grad) < 3e-2
 
 
 def test_scatter_decoder_and_row_ops():
