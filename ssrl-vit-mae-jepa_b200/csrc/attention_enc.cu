@@ -15,9 +15,9 @@
 // [128 rows x 64 bytes], 64-byte swizzle; rows G*LP..127 are zeroed once.  The same tile serves as K-major operand
 // (S = Q K^T, dP = dO V^T) and as MN-major operand (O = P V, dQ = dS K, dK = dS^T Q, dV = P^T dO): no transposes.
 //
-// Persistent, one CTA per SM, 10 warps: two softmax groups of 4 warps (one TMEM lane quarter each) take the CTA's items
-// alternately, so one group's softmax runs under the other group's MMAs; warp 8 = TMA producer, warp 9 = tcgen05.mma
-// issuer.  MMAs complete in issue order, which the schedule uses: the accumulators of a group's previous item are
+// Persistent, one CTA per SM: softmax groups of 4 warps (one TMEM lane quarter each; three groups in the forward, two in
+// the backward) take the CTA's items in turn, so one group's softmax runs under the other groups' MMAs; one TMA producer
+// warp, one tcgen05.mma issuer warp.  MMAs complete in issue order, which the schedule uses: the accumulators of a group's previous item are
 // complete whenever the S of its next item is, so each group drains them right after pulling S (no extra waits).
 #include "mae_internal.h"
 #include "attn_tc_common.cuh"
@@ -97,9 +97,17 @@ __device__ __forceinline__ uint4 lds16(uint32_t saddr) {
   return v;
 }
 
-static constexpr int kEncThreads = 10 * 32;
 static constexpr uint32_t kEncTile = 128 * 64;   // one [128 x 32] bf16 operand tile
 static constexpr uint32_t kEncPTile = 2 * 16384;  // [128 queries x 128 keys] bf16, two 128-byte-swizzled boxes of 64 keys
+
+// packed fp32 pairs (FFMA2 / FADD2 / FMUL2): the softmax threads are issue-latency bound, every instruction counts
+__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ uint64_t pk2u(uint32_t a, uint32_t b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // geometry of a pitch
 template <int LP>
@@ -109,55 +117,72 @@ struct EncGeo {
   static constexpr int KS = (ROWS + 15) / 16;              // K = 16 steps over keys / query rows
   static constexpr int NS = KS * 16;                       // MMA N of S / dP
   static constexpr uint32_t kBox = uint32_t(ROWS) * 64u;   // bytes one TMA box writes
+  // a kernel instance serves MS < L <= LP (MS = the next smaller pitch): only columns >= MS need the `< L` predicate
+  static constexpr int MS = LP == 16 ? 0 : LP == 32 ? 16 : LP == 40 ? 32 : LP == 48 ? 40 : 48;
+  static constexpr int NG = LP <= 48 ? 3 : 2;              // forward: softmax groups (registers: 144 per thread at 14 warps)
+};
+
+// (group of samples, head) of the k-th item of a softmax group, advanced without divisions
+struct ItemIter {
+  int grp, h, dq, dr, H;
+  __device__ __forceinline__ ItemIter(int first, int step, int H_) : grp(first / H_), h(first % H_), dq(step / H_), dr(step % H_), H(H_) {}
+  __device__ __forceinline__ void next() {
+    grp += dq; h += dr;
+    if (h >= H) { h -= H; ++grp; }
+  }
 };
 
 // =============================================================================================
 // forward
 // =============================================================================================
+template <int NG>
+struct EfCfg {
+  static constexpr int kStages = NG == 3 ? 5 : 6;
+  static constexpr int kThreads = (4 * NG + 2) * 32;
+  static constexpr uint32_t qkv = 0;                              // [stages][Q, K, V]
+  static constexpr uint32_t p = kStages * 3 * kEncTile;           // [NG groups] P tiles
+  static constexpr uint32_t bars = p + NG * kEncPTile;
+  static constexpr uint32_t total = bars + 1024;
+  static constexpr uint32_t colS = 0, colO = NG * 128;            // TMEM: S NG x 128 columns, O NG x 32
+};
 struct EfBars {
-  uint64_t kv_full[4], kv_empty[4];  // Q / K / V of an item landed / its MMAs have completed
-  uint64_t s_full[2], s_free[2];     // [group]: S complete in TMEM / pulled into registers
-  uint64_t p_ready[2], p_free[2];    // [group]: P tile written / P V has read it
-  uint64_t o_full[2];                // [group]: O complete in TMEM
+  uint64_t kv_full[6], kv_empty[6];  // Q / K / V of an item landed / its MMAs have completed
+  uint64_t s_full[3], s_free[3];     // [group]: S complete in TMEM / pulled into registers
+  uint64_t p_ready[3], p_free[3];    // [group]: P tile written / P V has read it
+  uint64_t o_full[3];                // [group]: O complete in TMEM
   uint32_t tmem_base;
 };
-struct EfSmem {
-  static constexpr int kStages = 4;
-  static constexpr uint32_t qkv = 0;                              // [4 stages][Q, K, V]
-  static constexpr uint32_t p = kStages * 3 * kEncTile;           // [2 groups] P tiles
-  static constexpr uint32_t bars = p + 2 * kEncPTile;
-  static constexpr uint32_t total = bars + 1024;
-};
-static constexpr uint32_t kEfColS = 0, kEfColO = 256;  // S: 2 x 128 columns, O: 2 x 32
 
-template <int LP>
-__global__ void __launch_bounds__(kEncThreads, 1)
+template <int LP, int HDC>  // HDC = head_dim / 8 at compile time (0: runtime)
+__global__ void __launch_bounds__(EfCfg<EncGeo<LP>::NG>::kThreads, 1)
 attn_fwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
                     int B, int L, int H, int hd, float scale) {
   using Geo = EncGeo<LP>;
-  constexpr int G = Geo::G;
+  constexpr int G = Geo::G, NG = Geo::NG, MS = Geo::MS;
+  using Cfg = EfCfg<NG>;
+  constexpr int kProd = 4 * NG, kMma = 4 * NG + 1;
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  EfBars* bars = reinterpret_cast<EfBars*>(smem + EfSmem::bars);
+  EfBars* bars = reinterpret_cast<EfBars*>(smem + Cfg::bars);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ngroups = (B + G - 1) / G;
   const int nitems = ngroups * H;
   const int my_items = nitems > int(blockIdx.x) ? (nitems - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
 
   // zero the operand and P tiles once: rows past G * LP, and the off-diagonal blocks of P, are never written afterwards
-  for (uint32_t i = threadIdx.x; i < EfSmem::bars / 16; i += kEncThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  if (warp == 8 && lane == 0) {
+  for (uint32_t i = threadIdx.x; i < Cfg::bars / 16; i += Cfg::kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == kProd && lane == 0) {
     tma_prefetch_desc(&mapQKV);
-    for (int i = 0; i < EfSmem::kStages; ++i) { mbar_init(&bars->kv_full[i], 1); mbar_init(&bars->kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&bars->kv_full[i], 1); mbar_init(&bars->kv_empty[i], 1); }
+    for (int i = 0; i < NG; ++i) {
       mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_free[i], 4);
       mbar_init(&bars->p_ready[i], 4); mbar_init(&bars->p_free[i], 1);
       mbar_init(&bars->o_full[i], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc(&bars->tmem_base, 512);
+  if (warp == kMma) tmem_alloc(&bars->tmem_base, 512);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -165,58 +190,63 @@ attn_fwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, __nv_bfloat16* _
   const uint32_t tmem_base = bars->tmem_base;
   pdl_wait();
 
-  if (warp == 8) {
+  if (warp == kProd) {
     if (lane == 0) {
-      for (int n = 0; n < my_items; ++n) {
-        const int item = int(blockIdx.x) + n * int(gridDim.x);
-        const int grp = item / H, h = item % H, s = n % EfSmem::kStages;
-        mbar_wait(&bars->kv_empty[s], ((n / EfSmem::kStages) & 1) ^ 1);
-        const uint32_t dst = smem_u32(smem + EfSmem::qkv + s * 3 * kEncTile);
+      ItemIter it(int(blockIdx.x), int(gridDim.x), H);
+      for (int n = 0, s = 0, ph = 1; n < my_items; ++n, it.next()) {
+        mbar_wait(&bars->kv_empty[s], ph);
+        const uint32_t dst = smem_u32(smem + Cfg::qkv + s * 3 * kEncTile);
         mbar_expect_tx(&bars->kv_full[s], 3 * Geo::kBox);
-        tma_load_4d(dst, &mapQKV, &bars->kv_full[s], 0, h, 0, grp * G);
-        tma_load_4d(dst + kEncTile, &mapQKV, &bars->kv_full[s], 0, H + h, 0, grp * G);
-        tma_load_4d(dst + 2 * kEncTile, &mapQKV, &bars->kv_full[s], 0, 2 * H + h, 0, grp * G);
+        tma_load_4d(dst, &mapQKV, &bars->kv_full[s], 0, it.h, 0, it.grp * G);
+        tma_load_4d(dst + kEncTile, &mapQKV, &bars->kv_full[s], 0, H + it.h, 0, it.grp * G);
+        tma_load_4d(dst + 2 * kEncTile, &mapQKV, &bars->kv_full[s], 0, 2 * H + it.h, 0, it.grp * G);
+        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMma) {
     if (lane == 0) {
       const uint32_t id_s = umma_idesc_bf16(128, Geo::NS, 0, 0);  // S: both operands K-major
       const uint32_t id_o = umma_idesc_bf16(128, 32, 0, 1);       // O: A = P K-major, B = V MN-major
       const uint64_t t64 = umma_sdesc_sw64(0, 16, 512);
       const uint64_t t128 = umma_sdesc_sw128(0, 16, 1024);
       auto d_at = [](uint64_t templ, uint32_t addr) { return templ + uint64_t((addr & 0x3ffffu) >> 4); };
-      const uint32_t tiles0 = smem_u32(smem + EfSmem::qkv), p0 = smem_u32(smem + EfSmem::p);
-      for (int n = 0; n <= my_items; ++n) {
-        if (n < my_items) {  // S of item n
-          const int gi = n & 1, k = n >> 1, s = n % EfSmem::kStages;
-          mbar_wait(&bars->kv_full[s], (n / EfSmem::kStages) & 1);
-          if (k >= 1) mbar_wait(&bars->s_free[gi], (k - 1) & 1);
+      const uint32_t tiles0 = smem_u32(smem + Cfg::qkv), p0 = smem_u32(smem + Cfg::p);
+      // step n issues S of item n, then O = P V of item n - (NG - 1): NG softmaxes are in flight
+      int s_st = 0, s_ph = 0, s_g = 0, s_k = 0;   // S side: stage / phase of kv_full, group, the group's item index
+      int o_st = 0, o_g = 0, o_k = 0;             // P V side
+      for (int n = 0; n < my_items + NG - 1; ++n) {
+        if (n < my_items) {
+          mbar_wait(&bars->kv_full[s_st], s_ph);
+          if (s_k >= 1) mbar_wait(&bars->s_free[s_g], (s_k - 1) & 1);
           tc_fence_after();
-          const uint32_t tb = tiles0 + uint32_t(s) * 3u * kEncTile;
+          const uint32_t tb = tiles0 + uint32_t(s_st) * 3u * kEncTile;
           const uint64_t dq = d_at(t64, tb), dk = d_at(t64, tb + kEncTile);
-          const uint32_t d = tmem_base + kEfColS + uint32_t(gi) * 128u;
+          const uint32_t d = tmem_base + Cfg::colS + uint32_t(s_g) * 128u;
           umma_bf16(d, dq, dk, id_s, 0);
           umma_bf16(d, dq + 2, dk + 2, id_s, 1);  // +32 B per K = 16
-          umma_commit(&bars->s_full[gi]);
+          umma_commit(&bars->s_full[s_g]);
+          if (++s_st == Cfg::kStages) { s_st = 0; s_ph ^= 1; }
+          if (++s_g == NG) { s_g = 0; ++s_k; }
         }
-        if (n >= 1) {  // O = P V of item n - 1 (its softmax ran under the S above)
-          const int m = n - 1, gi = m & 1, k = m >> 1, s = m % EfSmem::kStages;
-          mbar_wait(&bars->p_ready[gi], k & 1);  // also: the group has drained O of its previous item (program order)
+        if (n >= NG - 1) {  // its softmax ran under the S MMAs above
+          mbar_wait(&bars->p_ready[o_g], o_k & 1);  // also: the group has drained O of its previous item (program order)
           tc_fence_after();
-          const uint64_t a0 = d_at(t128, p0 + uint32_t(gi) * kEncPTile);
-          uint64_t b = d_at(t64, tiles0 + uint32_t(s) * 3u * kEncTile + 2 * kEncTile);
-          const uint32_t d = tmem_base + kEfColO + uint32_t(gi) * 32u;
+          const uint64_t a0 = d_at(t128, p0 + uint32_t(o_g) * kEncPTile);
+          uint64_t b = d_at(t64, tiles0 + uint32_t(o_st) * 3u * kEncTile + 2 * kEncTile);
+          const uint32_t d = tmem_base + Cfg::colO + uint32_t(o_g) * 32u;
 #pragma unroll
           for (int j = 0; j < Geo::KS; ++j, b += 64)  // V as MN-major B: +1024 B per 16 keys
             umma_bf16(d, a0 + uint64_t((uint32_t(j >> 2) * 16384u + uint32_t(j & 3) * 32u) >> 4), b, id_o, j != 0);
-          umma_commit(&bars->o_full[gi]);
-          umma_commit(&bars->p_free[gi]);
-          umma_commit(&bars->kv_empty[s]);
+          umma_commit(&bars->o_full[o_g]);
+          umma_commit(&bars->p_free[o_g]);
+          umma_commit(&bars->kv_empty[o_st]);
+          if (++o_st == Cfg::kStages) o_st = 0;
+          if (++o_g == NG) { o_g = 0; ++o_k; }
         }
       }
     }
   } else {
-    // softmax groups: warps 0..3 = group 0, 4..7 = group 1; row = TMEM lane
+    // softmax groups: warps 4 gi .. 4 gi + 3 = group gi, one TMEM lane quarter each; row = TMEM lane
     const int gi = warp >> 2, quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const int g = r / LP, l = r - g * LP;               // sample slot and token of this row
@@ -225,13 +255,18 @@ attn_fwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, __nv_bfloat16* _
     const bool second = g > g_lo;
     const bool row_ok = g < G && l < L;
     const float sl2 = scale * 1.4426950408889634f;
+    const uint64_t sl2_2 = pk2(sl2, sl2);
     const uint32_t lane_off = uint32_t(quarter * 32) << 16;
-    const uint32_t s_addr = tmem_base + lane_off + kEfColS + uint32_t(gi) * 128u;
-    const uint32_t o_addr = tmem_base + lane_off + kEfColO + uint32_t(gi) * 32u;
-    const uint32_t p_base = smem_u32(smem + EfSmem::p) + uint32_t(gi) * kEncPTile;
-    const int cnt = my_items > gi ? (my_items - gi + 1) / 2 : 0;
-    const int D = H * hd;
+    const uint32_t s_addr = tmem_base + lane_off + Cfg::colS + uint32_t(gi) * 128u;
+    const uint32_t o_addr = tmem_base + lane_off + Cfg::colO + uint32_t(gi) * 32u;
+    const int c0 = (g * LP) >> 3;  // first 16-byte chunk of this sample's keys inside the P row
+    const uint32_t p_row = smem_u32(smem + Cfg::p) + uint32_t(gi) * kEncPTile + uint32_t(r) * 128u;
+    const int cnt = my_items > gi ? (my_items - gi + NG - 1) / NG : 0;
+    const int D = HDC ? H * HDC * 8 : H * hd;
+    const int hdv = HDC ? HDC * 8 : hd;
+    ItemIter it(int(blockIdx.x) + gi * int(gridDim.x), NG * int(gridDim.x), H);
     float inv_prev = 0.f;
+    __nv_bfloat16* dst_prev = nullptr;  // output row of the previous item (nullptr: nothing to store)
 #pragma unroll 1
     for (int k = 0; k <= cnt; ++k) {
       uint32_t sr[LP];
@@ -244,101 +279,110 @@ attn_fwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, __nv_bfloat16* _
         if (lane == 0) mbar_arrive(&bars->s_free[gi]);
       }
       if (k >= 1) {  // O rows of the group's previous item: complete, because its P V was issued before this item's S
-        const int item = int(blockIdx.x) + (2 * (k - 1) + gi) * int(gridDim.x);
-        const int b = (item / H) * G + g, h = item % H;
         mbar_wait(&bars->o_full[gi], (k - 1) & 1);
         tc_fence_after();
         uint32_t o[32];
         tmem_ld32_nowait(o_addr, o);
         tmem_wait_ld();
         tc_fence_before();
-        if (row_ok && b < B) {
-          __nv_bfloat16* dst = out + (size_t(b) * L + l) * D + h * hd;
+        if (dst_prev) {
+          const uint64_t inv2 = pk2(inv_prev, inv_prev);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            if (c * 8 >= hd) break;
-            uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(o[8 * c]) * inv_prev, __uint_as_float(o[8 * c + 1]) * inv_prev);
-            w.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv_prev, __uint_as_float(o[8 * c + 3]) * inv_prev);
-            w.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv_prev, __uint_as_float(o[8 * c + 5]) * inv_prev);
-            w.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv_prev, __uint_as_float(o[8 * c + 7]) * inv_prev);
-            *reinterpret_cast<uint4*>(dst + 8 * c) = w;
+            if (HDC ? c >= HDC : c * 8 >= hd) break;
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a, b;
+              upk2(mul2(pk2u(o[8 * c + 2 * j], o[8 * c + 2 * j + 1]), inv2), a, b);
+              w[j] = pack_bf16x2(a, b);
+            }
+            *reinterpret_cast<uint4*>(dst_prev + 8 * c) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
       }
       if (k < cnt) {
-        const int item = int(blockIdx.x) + (2 * k + gi) * int(gridDim.x);
-        const int b = (item / H) * G + g, h = item % H;
+        const int b = it.grp * G + g, h = it.h;
+        it.next();
+        const bool ok = row_ok && b < B;
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int i = 0; i < LP; ++i)
-          if (i < L) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sr[i]));
+          if (i < MS || i < L) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sr[i]));
         const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         const float msl2 = mx * sl2;
-        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint64_t nm2 = pk2(-msl2, -msl2);
+        uint64_t acc[2] = {pk2(0.f, 0.f), pk2(0.f, 0.f)};
         uint32_t pk[LP / 2];
 #pragma unroll
         for (int i = 0; i < LP / 2; ++i) {
-          float p0 = ex2_approx(__uint_as_float(sr[2 * i]) * sl2 - msl2);
-          float p1 = ex2_approx(__uint_as_float(sr[2 * i + 1]) * sl2 - msl2);
-          if (2 * i >= L) p0 = 0.f;
-          if (2 * i + 1 >= L) p1 = 0.f;
-          l4[i & 3] += p0 + p1;
+          float a, b2;
+          upk2(fma2(pk2u(sr[2 * i], sr[2 * i + 1]), sl2_2, nm2), a, b2);
+          float p0 = ex2_approx(a), p1 = ex2_approx(b2);
+          if (2 * i + 1 >= MS) {
+            if (2 * i >= L) p0 = 0.f;
+            if (2 * i + 1 >= L) p1 = 0.f;
+          }
+          acc[i & 1] = add2(acc[i & 1], pk2(p0, p1));
           pk[i] = pack_bf16x2(p0, p1);
         }
-        const float sum = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        float s0, s1;
+        upk2(add2(acc[0], acc[1]), s0, s1);
+        const float sum = s0 + s1;
         if (k >= 1) mbar_wait(&bars->p_free[gi], (k - 1) & 1);  // the previous item's P V has read the tile
         if (g < G) {
-          const int c0 = (g * LP) >> 3;  // first 16-byte chunk of this sample's keys
 #pragma unroll
           for (int j = 0; j < LP / 8; ++j) {
             const int c = c0 + j;
-            sts16(swz(p_base + uint32_t(c >> 3) * 16384u, r, c & 7), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            sts16(p_row + uint32_t(c >> 3) * 16384u + (uint32_t((c ^ r) & 7) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
           }
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->p_ready[gi]);
-        if (row_ok && b < B) lse[(size_t(b) * H + h) * L + l] = mx * scale + logf(sum);
-        inv_prev = 1.0f / sum;
+        if (ok) lse[(size_t(b) * H + h) * L + l] = (msl2 + lg2_approx(sum)) * 0.6931471805599453f;
+        inv_prev = rcp_approx(sum);
+        dst_prev = ok ? out + (size_t(b) * L + l) * D + h * hdv : nullptr;
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, 512);
+  if (warp == kMma) tmem_dealloc(tmem_base, 512);
 }
 
 // =============================================================================================
 // backward.  Per (group, head), with the forward's log-sum-exp:
-//   S = Q K^T,  P = exp(S / sqrt(hd) - lse),  dP = dO V^T,  delta = rowsum(dO o O),  dS = P o (dP - delta)
-//   dQ = dS K / sqrt(hd),  dK = dS^T Q / sqrt(hd),  dV = P^T dO
-// Q, K, V, dO and O tiles by TMA (delta comes from the dO / O tiles in shared memory: no strided global row reads);
-// S and dP share one TMEM region (a group pulls its rows into registers at once, which frees it for the next item);
-// the bf16 P and dS tiles (block diagonal, one pair per group) feed dQ = dS K as K-major A and dK / dV as MN-major A.
+//   S = Q K^T,  P = exp(S / sqrt(hd) - lse),  dP = dO V^T,  delta = rowsum(P o dP)  (= rowsum(dO o O) with O = P V),
+//   dS = P o (dP - delta),  dQ = dS K / sqrt(hd),  dK = dS^T Q / sqrt(hd),  dV = P^T dO
+// A softmax thread holds the whole S and dP rows of its sample, so delta comes from registers: O is never read.
+// 1 / sqrt(hd) is folded into dS.  Q, K, V, dO tiles by TMA, three stages; S and dP share one TMEM region (a group
+// pulls its rows into registers at once, which frees it for the next item); the bf16 P and dS tiles (block diagonal,
+// one pair per group) feed dQ = dS K as K-major A and dK / dV as MN-major A.
 // =============================================================================================
+static constexpr int kEbThreads = 10 * 32;
+static constexpr int kEbStages = 3;
 struct EbBars {
-  uint64_t ld_full[2], ld_empty[2];    // [stage = group]
+  uint64_t ld_full[kEbStages], ld_empty[kEbStages];
   uint64_t sd_full[2], sd_free[2];     // [group]: S and dP complete / pulled out of TMEM
   uint64_t pds_ready[2], pds_free[2];  // [group]: P and dS tiles written / the MMAs reading them are done
   uint64_t g_full[2];                  // [group]: dQ, dK, dV complete
   uint32_t tmem_base;
 };
 struct EbSmem {
-  static constexpr uint32_t tiles = 0;                           // [2 stages][Q, K, V, dO, O]
-  static constexpr uint32_t pds = 2 * 5 * kEncTile;              // [2 groups][P, dS]
+  static constexpr uint32_t tiles = 0;                           // [3 stages][Q, K, V, dO]
+  static constexpr uint32_t pds = kEbStages * 4 * kEncTile;      // [2 groups][P, dS]
   static constexpr uint32_t bars = pds + 2 * 2 * kEncPTile;
   static constexpr uint32_t total = bars + 1024;
 };
 static constexpr uint32_t kEbColS = 0, kEbColDP = 128, kEbColG = 256;  // per group at kEbColG + 96 g: dQ, dK, dV (32 each)
 
-template <int LP>
-__global__ void __launch_bounds__(kEncThreads, 1)
+template <int LP, int HDC>
+__global__ void __launch_bounds__(kEbThreads, 1)
 attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ CUtensorMap mapDO,
-                    const __grid_constant__ CUtensorMap mapO, const float* __restrict__ lse,
-                    __nv_bfloat16* __restrict__ dqkv, int B, int L, int H, int hd, float scale) {
+                    const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, int B, int L, int H, int hd, float scale) {
   using Geo = EncGeo<LP>;
-  constexpr int G = Geo::G;
+  constexpr int G = Geo::G, MS = Geo::MS;
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -348,13 +392,12 @@ attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
   const int nitems = ngroups * H;
   const int my_items = nitems > int(blockIdx.x) ? (nitems - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
 
-  for (uint32_t i = threadIdx.x; i < EbSmem::bars / 16; i += kEncThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (uint32_t i = threadIdx.x; i < EbSmem::bars / 16; i += kEbThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&mapQKV);
     tma_prefetch_desc(&mapDO);
-    tma_prefetch_desc(&mapO);
+    for (int i = 0; i < kEbStages; ++i) { mbar_init(&bars->ld_full[i], 1); mbar_init(&bars->ld_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->ld_full[i], 1); mbar_init(&bars->ld_empty[i], 5);  // the MMAs (commit) + the group's 4 warps (delta)
       mbar_init(&bars->sd_full[i], 1); mbar_init(&bars->sd_free[i], 4);
       mbar_init(&bars->pds_ready[i], 4); mbar_init(&bars->pds_free[i], 1);
       mbar_init(&bars->g_full[i], 1);
@@ -371,17 +414,16 @@ attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
 
   if (warp == 8) {
     if (lane == 0) {
-      for (int n = 0; n < my_items; ++n) {
-        const int item = int(blockIdx.x) + n * int(gridDim.x);
-        const int grp = item / H, h = item % H, s = n & 1;
-        mbar_wait(&bars->ld_empty[s], ((n >> 1) & 1) ^ 1);
-        const uint32_t dst = smem_u32(smem + EbSmem::tiles + s * 5 * kEncTile);
-        mbar_expect_tx(&bars->ld_full[s], 5 * Geo::kBox);
-        tma_load_4d(dst, &mapQKV, &bars->ld_full[s], 0, h, 0, grp * G);
-        tma_load_4d(dst + kEncTile, &mapQKV, &bars->ld_full[s], 0, H + h, 0, grp * G);
-        tma_load_4d(dst + 2 * kEncTile, &mapQKV, &bars->ld_full[s], 0, 2 * H + h, 0, grp * G);
-        tma_load_4d(dst + 3 * kEncTile, &mapDO, &bars->ld_full[s], 0, h, 0, grp * G);
-        tma_load_4d(dst + 4 * kEncTile, &mapO, &bars->ld_full[s], 0, h, 0, grp * G);
+      ItemIter it(int(blockIdx.x), int(gridDim.x), H);
+      for (int n = 0, s = 0, ph = 1; n < my_items; ++n, it.next()) {
+        mbar_wait(&bars->ld_empty[s], ph);
+        const uint32_t dst = smem_u32(smem + EbSmem::tiles + s * 4 * kEncTile);
+        mbar_expect_tx(&bars->ld_full[s], 4 * Geo::kBox);
+        tma_load_4d(dst, &mapQKV, &bars->ld_full[s], 0, it.h, 0, it.grp * G);
+        tma_load_4d(dst + kEncTile, &mapQKV, &bars->ld_full[s], 0, H + it.h, 0, it.grp * G);
+        tma_load_4d(dst + 2 * kEncTile, &mapQKV, &bars->ld_full[s], 0, 2 * H + it.h, 0, it.grp * G);
+        tma_load_4d(dst + 3 * kEncTile, &mapDO, &bars->ld_full[s], 0, it.h, 0, it.grp * G);
+        if (++s == kEbStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 9) {
@@ -394,19 +436,18 @@ attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
       const uint64_t t128mn = umma_sdesc_sw128(0, 16384, 1024);    // ... as MN-major A (LBO = stride between the 64-key boxes)
       auto d_at = [](uint64_t templ, uint32_t addr) { return templ + uint64_t((addr & 0x3ffffu) >> 4); };
       const uint32_t tiles0 = smem_u32(smem + EbSmem::tiles), pds0 = smem_u32(smem + EbSmem::pds);
-      auto issue_sdp = [&](int n) {
-        const uint32_t tb = tiles0 + uint32_t(n & 1) * 5u * kEncTile;
+      auto issue_sdp = [&](int st, int gi) {
+        const uint32_t tb = tiles0 + uint32_t(st) * 4u * kEncTile;
         const uint64_t dq = d_at(t64, tb), dk = d_at(t64, tb + kEncTile), dv = d_at(t64, tb + 2 * kEncTile),
                        ddo = d_at(t64, tb + 3 * kEncTile);
         umma_bf16(tmem_base + kEbColS, dq, dk, id_s, 0);
         umma_bf16(tmem_base + kEbColS, dq + 2, dk + 2, id_s, 1);
         umma_bf16(tmem_base + kEbColDP, ddo, dv, id_s, 0);
         umma_bf16(tmem_base + kEbColDP, ddo + 2, dv + 2, id_s, 1);
-        umma_commit(&bars->sd_full[n & 1]);
+        umma_commit(&bars->sd_full[gi]);
       };
-      auto issue_grads = [&](int n) {
-        const int gi = n & 1;
-        const uint32_t tb = tiles0 + uint32_t(gi) * 5u * kEncTile;
+      auto issue_grads = [&](int st, int gi) {
+        const uint32_t tb = tiles0 + uint32_t(st) * 4u * kEncTile;
         const uint32_t sp = pds0 + uint32_t(gi) * 2u * kEncPTile, sds = sp + kEncPTile;
         const uint32_t dcol = tmem_base + kEbColG + uint32_t(gi) * 96u;
         {  // dQ = dS . K   (B = K tile as MN-major: +1024 B per 16 keys)
@@ -426,23 +467,28 @@ attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
         }
         umma_commit(&bars->g_full[gi]);
         umma_commit(&bars->pds_free[gi]);
-        umma_commit(&bars->ld_empty[gi]);
+        umma_commit(&bars->ld_empty[st]);
       };
+      int st_next = 0, ph_next = 0;  // stage / kv phase of the next item whose S / dP will be issued
       if (my_items > 0) {
         mbar_wait(&bars->ld_full[0], 0);
         tc_fence_after();
-        issue_sdp(0);
+        issue_sdp(0, 0);
+        st_next = 1;
       }
+      int st = 0;
       for (int n = 0; n < my_items; ++n) {
         if (n + 1 < my_items) {  // the next item's S / dP as soon as this item's rows are in registers
-          mbar_wait(&bars->ld_full[(n + 1) & 1], ((n + 1) >> 1) & 1);
+          mbar_wait(&bars->ld_full[st_next], ph_next);
           mbar_wait(&bars->sd_free[n & 1], (n >> 1) & 1);
           tc_fence_after();
-          issue_sdp(n + 1);
+          issue_sdp(st_next, (n + 1) & 1);
+          if (++st_next == kEbStages) { st_next = 0; ph_next ^= 1; }
         }
         mbar_wait(&bars->pds_ready[n & 1], (n >> 1) & 1);  // also: the group has drained dQ / dK / dV of its previous item
         tc_fence_after();
-        issue_grads(n);
+        issue_grads(st, n & 1);
+        if (++st == kEbStages) st = 0;
       }
     }
   } else {
@@ -454,31 +500,25 @@ attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
     const bool second = g > g_lo;
     const bool row_ok = g < G && l < L;
     const float l2e = 1.4426950408889634f, sl2 = scale * l2e;
+    const uint64_t sl2_2 = pk2(sl2, sl2), sc2 = pk2(scale, scale);
     const uint32_t lane_off = uint32_t(quarter * 32) << 16;
     const uint32_t g_addr = tmem_base + lane_off + kEbColG + uint32_t(gi) * 96u;
-    const uint32_t p_base = smem_u32(smem + EbSmem::pds) + uint32_t(gi) * 2u * kEncPTile, ds_base = p_base + kEncPTile;
-    const uint32_t tile_do = smem_u32(smem + EbSmem::tiles) + uint32_t(gi) * 5u * kEncTile + 3 * kEncTile, tile_o = tile_do + kEncTile;
+    const int c0 = (g * LP) >> 3;
+    const uint32_t p_row = smem_u32(smem + EbSmem::pds) + uint32_t(gi) * 2u * kEncPTile + uint32_t(r) * 128u;
     const int cnt = my_items > gi ? (my_items - gi + 1) / 2 : 0;
-    const int D = H * hd;
+    const int D = HDC ? H * HDC * 8 : H * hd;
+    const int hdv = HDC ? HDC * 8 : hd;
+    ItemIter it(int(blockIdx.x) + gi * int(gridDim.x), 2 * int(gridDim.x), H);
+    __nv_bfloat16* dst_prev = nullptr;
+    float lse2 = INFINITY;
+    {
+      const int b = it.grp * G + g;
+      if (cnt > 0 && row_ok && b < B) lse2 = __ldg(lse + (size_t(b) * H + it.h) * L + l) * l2e;
+    }
 #pragma unroll 1
     for (int k = 0; k <= cnt; ++k) {
       uint32_t sr[LP], dr[LP];
-      float lse2 = INFINITY, delta = 0.f;
       if (k < cnt) {
-        const int item = int(blockIdx.x) + (2 * k + gi) * int(gridDim.x);
-        const int b = (item / H) * G + g, h = item % H;
-        const bool ok = row_ok && b < B;
-        if (ok) lse2 = __ldg(lse + (size_t(b) * H + h) * L + l) * l2e;  // rows that do not exist: +inf makes P and dS vanish
-        mbar_wait(&bars->ld_full[gi], k & 1);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {  // delta = rowsum(dO o O) from the staged tiles (padding columns are zero)
-          if (c * 8 >= hd) break;
-          const uint4 o4 = lds16(swz64(tile_o, r, c)), d4 = lds16(swz64(tile_do, r, c));
-          delta += bf16_lo(o4.x) * bf16_lo(d4.x) + bf16_hi(o4.x) * bf16_hi(d4.x) + bf16_lo(o4.y) * bf16_lo(d4.y) + bf16_hi(o4.y) * bf16_hi(d4.y) +
-                   bf16_lo(o4.z) * bf16_lo(d4.z) + bf16_hi(o4.z) * bf16_hi(d4.z) + bf16_lo(o4.w) * bf16_lo(d4.w) + bf16_hi(o4.w) * bf16_hi(d4.w);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->ld_empty[gi]);
         mbar_wait(&bars->sd_full[gi], k & 1);
         tc_fence_after();
         tmem_ld_own<LP>(tmem_base + lane_off + kEbColS, g_lo, two, second, sr);
@@ -488,58 +528,81 @@ attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
         if (lane == 0) mbar_arrive(&bars->sd_free[gi]);
       }
       if (k >= 1) {  // gradients of the group's previous item: complete (issued before this item's S / dP)
-        const int item = int(blockIdx.x) + (2 * (k - 1) + gi) * int(gridDim.x);
-        const int b = (item / H) * G + g, h = item % H;
         mbar_wait(&bars->g_full[gi], (k - 1) & 1);
         tc_fence_after();
-        __nv_bfloat16* dst = dqkv + (size_t(b) * L + l) * 3 * D + h * hd;
-        const bool ok = row_ok && b < B;
 #pragma unroll 1
         for (int w = 0; w < 3; ++w) {  // dQ, dK, dV one after the other: 32 live registers next to the S / dP rows
           uint32_t o[32];
           tmem_ld32_nowait(g_addr + uint32_t(w) * 32u, o);
           tmem_wait_ld();
-          const float mul = w == 2 ? 1.0f : scale;
-          if (ok) {
+          if (dst_prev) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              if (c * 8 >= hd) break;
+              if (HDC ? c >= HDC : c * 8 >= hd) break;
               uint4 v;
-              v.x = pack_bf16x2(__uint_as_float(o[8 * c]) * mul, __uint_as_float(o[8 * c + 1]) * mul);
-              v.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * mul, __uint_as_float(o[8 * c + 3]) * mul);
-              v.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * mul, __uint_as_float(o[8 * c + 5]) * mul);
-              v.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * mul, __uint_as_float(o[8 * c + 7]) * mul);
-              *reinterpret_cast<uint4*>(dst + w * D + 8 * c) = v;
+              v.x = pack_bf16x2(__uint_as_float(o[8 * c]), __uint_as_float(o[8 * c + 1]));
+              v.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]), __uint_as_float(o[8 * c + 3]));
+              v.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]), __uint_as_float(o[8 * c + 5]));
+              v.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]), __uint_as_float(o[8 * c + 7]));
+              *reinterpret_cast<uint4*>(dst_prev + w * D + 8 * c) = v;
             }
           }
         }
         tc_fence_before();
       }
       if (k < cnt) {
-        uint32_t pk[LP / 2], dk[LP / 2];
-#pragma unroll
-        for (int i = 0; i < LP / 2; ++i) {
-          float p0 = ex2_approx(__uint_as_float(sr[2 * i]) * sl2 - lse2);
-          float p1 = ex2_approx(__uint_as_float(sr[2 * i + 1]) * sl2 - lse2);
-          if (2 * i >= L) p0 = 0.f;
-          if (2 * i + 1 >= L) p1 = 0.f;
-          pk[i] = pack_bf16x2(p0, p1);
-          dk[i] = pack_bf16x2(p0 * (__uint_as_float(dr[2 * i]) - delta), p1 * (__uint_as_float(dr[2 * i + 1]) - delta));
+        const int b = it.grp * G + g, h = it.h;
+        it.next();
+        const bool ok = row_ok && b < B;
+        const uint64_t nl2 = pk2(-lse2, -lse2);
+        // the next item's log-sum-exp: in flight during the arithmetic below
+        float lse_next = INFINITY;
+        {
+          const int bn = it.grp * G + g;
+          if (k + 1 < cnt && row_ok && bn < B) lse_next = __ldg(lse + (size_t(bn) * H + it.h) * L + l);
         }
+        uint64_t dacc[2] = {pk2(0.f, 0.f), pk2(0.f, 0.f)};
+#pragma unroll
+        for (int i = 0; i < LP / 2; ++i) {  // S -> P in place (fp32), delta accumulated on the way
+          float a, b2;
+          upk2(fma2(pk2u(sr[2 * i], sr[2 * i + 1]), sl2_2, nl2), a, b2);
+          float p0 = ex2_approx(a), p1 = ex2_approx(b2);
+          if (2 * i + 1 >= MS) {
+            if (2 * i >= L) p0 = 0.f;
+            if (2 * i + 1 >= L) p1 = 0.f;
+          }
+          sr[2 * i] = __float_as_uint(p0);
+          sr[2 * i + 1] = __float_as_uint(p1);
+          dacc[i & 1] = fma2(pk2(p0, p1), pk2u(dr[2 * i], dr[2 * i + 1]), dacc[i & 1]);
+        }
+        float d0, d1;
+        upk2(add2(dacc[0], dacc[1]), d0, d1);
+        const float nds = -(d0 + d1) * scale;  // - delta / sqrt(hd)
+        const uint64_t nds2 = pk2(nds, nds);
         if (k >= 1) mbar_wait(&bars->pds_free[gi], (k - 1) & 1);  // the previous item's MMAs have read the tiles
         if (g < G) {
-          const int c0 = (g * LP) >> 3;
 #pragma unroll
           for (int j = 0; j < LP / 8; ++j) {
             const int c = c0 + j;
-            const uint32_t off = uint32_t(c >> 3) * 16384u;
-            sts16(swz(p_base + off, r, c & 7), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-            sts16(swz(ds_base + off, r, c & 7), dk[4 * j], dk[4 * j + 1], dk[4 * j + 2], dk[4 * j + 3]);
+            const uint32_t a = p_row + uint32_t(c >> 3) * 16384u + (uint32_t((c ^ r) & 7) << 4);
+            uint32_t pw[4], dk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {  // dS / sqrt(hd) = P o (dP / sqrt(hd) - delta / sqrt(hd))
+              const int i = 4 * j + q;
+              pw[q] = pack_bf16x2(__uint_as_float(sr[2 * i]), __uint_as_float(sr[2 * i + 1]));
+              float x, y;
+              upk2(mul2(pk2u(sr[2 * i], sr[2 * i + 1]), fma2(pk2u(dr[2 * i], dr[2 * i + 1]), sc2, nds2)), x, y);
+              dk[q] = pack_bf16x2(x, y);
+            }
+            sts16(a, pw[0], pw[1], pw[2], pw[3]);
+            sts16(a + kEncPTile, dk[0], dk[1], dk[2], dk[3]);
           }
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->pds_ready[gi]);
+        dst_prev = ok ? dqkv + (size_t(b) * L + l) * 3 * D + h * hdv : nullptr;
+        lse2 = lse_next * l2e;
       }
     }
   }
@@ -548,39 +611,38 @@ attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
   if (warp == 9) tmem_dealloc(tmem_base, 512);
 }
 
-template <int LP>
+template <int LP, int HDC>
 static int launch_fwd_enc(const void* qkv, int B, int L, int H, int hd, void* out, float* lse, cudaStream_t st) {
   using Geo = EncGeo<LP>;
+  using Cfg = EfCfg<Geo::NG>;
   CUtensorMap mq;
   int rc = make_tmap_enc(&mq, qkv, hd, 3 * H, L, B, LP, Geo::G);
   if (rc) return rc;
   static bool done[kMaxDevices] = {};
-  if (!ensure_dyn_smem(attn_fwd_enc_kernel<LP>, EfSmem::total + 1024, done)) return MAE_ERR_LAUNCH;
+  if (!ensure_dyn_smem(attn_fwd_enc_kernel<LP, HDC>, Cfg::total + 1024, done)) return MAE_ERR_LAUNCH;
   const int sms = num_sms();
   const int nitems = ((B + Geo::G - 1) / Geo::G) * H;
   const int grid = nitems < sms ? nitems : sms;
-  mae_launch(attn_fwd_enc_kernel<LP>, dim3(grid), dim3(kEncThreads), size_t(EfSmem::total) + 1024, st, mq,
+  mae_launch(attn_fwd_enc_kernel<LP, HDC>, dim3(grid), dim3(Cfg::kThreads), size_t(Cfg::total) + 1024, st, mq,
              reinterpret_cast<__nv_bfloat16*>(out), lse, B, L, H, hd, 1.0f / sqrtf(float(hd)));
   return MAE_CHECK_LAUNCH();
 }
 
-template <int LP>
-static int launch_bwd_enc(const void* qkv, const void* out, const void* dout, const float* lse, int B, int L, int H, int hd,
-                          void* dqkv, cudaStream_t st) {
+template <int LP, int HDC>
+static int launch_bwd_enc(const void* qkv, const void* dout, const float* lse, int B, int L, int H, int hd, void* dqkv,
+                          cudaStream_t st) {
   using Geo = EncGeo<LP>;
-  CUtensorMap mq, md, mo;
+  CUtensorMap mq, md;
   int rc = make_tmap_enc(&mq, qkv, hd, 3 * H, L, B, LP, Geo::G);
   if (rc) return rc;
   rc = make_tmap_enc(&md, dout, hd, H, L, B, LP, Geo::G);
   if (rc) return rc;
-  rc = make_tmap_enc(&mo, out, hd, H, L, B, LP, Geo::G);
-  if (rc) return rc;
   static bool done[kMaxDevices] = {};
-  if (!ensure_dyn_smem(attn_bwd_enc_kernel<LP>, EbSmem::total + 1024, done)) return MAE_ERR_LAUNCH;
+  if (!ensure_dyn_smem(attn_bwd_enc_kernel<LP, HDC>, EbSmem::total + 1024, done)) return MAE_ERR_LAUNCH;
   const int sms = num_sms();
   const int nitems = ((B + Geo::G - 1) / Geo::G) * H;
   const int grid = nitems < sms ? nitems : sms;
-  mae_launch(attn_bwd_enc_kernel<LP>, dim3(grid), dim3(kEncThreads), size_t(EbSmem::total) + 1024, st, mq, md, mo, lse,
+  mae_launch(attn_bwd_enc_kernel<LP, HDC>, dim3(grid), dim3(kEbThreads), size_t(EbSmem::total) + 1024, st, mq, md, lse,
              reinterpret_cast<__nv_bfloat16*>(dqkv), B, L, H, hd, 1.0f / sqrtf(float(hd)));
   return MAE_CHECK_LAUNCH();
 }
@@ -595,25 +657,30 @@ static int enc_pitch(int L) {
 
 bool attn_enc_covers(int L, int hd) { return L >= 1 && enc_pitch(L) != 0 && hd >= 8 && hd <= 32 && (hd & 7) == 0; }
 
+// head_dim 24 (configs/mae.yaml) gets compile-time chunk counts, every other head_dim the runtime loop bounds
+#define MAE_ENC_CASE(FN, LPV, ...) \
+  case LPV: return hd == 24 ? FN<LPV, 3>(__VA_ARGS__) : FN<LPV, 0>(__VA_ARGS__);
+
 int attn_fwd_enc(const void* qkv, int B, int L, int H, int hd, void* out, float* lse, cudaStream_t st) {
   switch (enc_pitch(L)) {
-    case 16: return launch_fwd_enc<16>(qkv, B, L, H, hd, out, lse, st);
-    case 32: return launch_fwd_enc<32>(qkv, B, L, H, hd, out, lse, st);
-    case 40: return launch_fwd_enc<40>(qkv, B, L, H, hd, out, lse, st);
-    case 48: return launch_fwd_enc<48>(qkv, B, L, H, hd, out, lse, st);
-    case 64: return launch_fwd_enc<64>(qkv, B, L, H, hd, out, lse, st);
+    MAE_ENC_CASE(launch_fwd_enc, 16, qkv, B, L, H, hd, out, lse, st)
+    MAE_ENC_CASE(launch_fwd_enc, 32, qkv, B, L, H, hd, out, lse, st)
+    MAE_ENC_CASE(launch_fwd_enc, 40, qkv, B, L, H, hd, out, lse, st)
+    MAE_ENC_CASE(launch_fwd_enc, 48, qkv, B, L, H, hd, out, lse, st)
+    MAE_ENC_CASE(launch_fwd_enc, 64, qkv, B, L, H, hd, out, lse, st)
     default: return MAE_ERR_SHAPE;
   }
 }
 
 int attn_bwd_enc(const void* qkv, const void* out, const void* dout, const float* lse, int B, int L, int H, int hd,
                  void* dqkv, cudaStream_t st) {
+  (void)out;  // delta = rowsum(P o dP) comes from registers: the forward output is not read
   switch (enc_pitch(L)) {
-    case 16: return launch_bwd_enc<16>(qkv, out, dout, lse, B, L, H, hd, dqkv, st);
-    case 32: return launch_bwd_enc<32>(qkv, out, dout, lse, B, L, H, hd, dqkv, st);
-    case 40: return launch_bwd_enc<40>(qkv, out, dout, lse, B, L, H, hd, dqkv, st);
-    case 48: return launch_bwd_enc<48>(qkv, out, dout, lse, B, L, H, hd, dqkv, st);
-    case 64: return launch_bwd_enc<64>(qkv, out, dout, lse, B, L, H, hd, dqkv, st);
+    MAE_ENC_CASE(launch_bwd_enc, 16, qkv, dout, lse, B, L, H, hd, dqkv, st)
+    MAE_ENC_CASE(launch_bwd_enc, 32, qkv, dout, lse, B, L, H, hd, dqkv, st)
+    MAE_ENC_CASE(launch_bwd_enc, 40, qkv, dout, lse, B, L, H, hd, dqkv, st)
+    MAE_ENC_CASE(launch_bwd_enc, 48, qkv, dout, lse, B, L, H, hd, dqkv, st)
+    MAE_ENC_CASE(launch_bwd_enc, 64, qkv, dout, lse, B, L, H, hd, dqkv, st)
     default: return MAE_ERR_SHAPE;
   }
 }
