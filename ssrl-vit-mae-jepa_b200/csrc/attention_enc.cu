@@ -19,6 +19,8 @@
 // the backward) take the CTA's items in turn, so one group's softmax runs under the other groups' MMAs; one TMA producer
 // warp, one tcgen05.mma issuer warp.  MMAs complete in issue order, which the schedule uses: the accumulators of a group's previous item are
 // complete whenever the S of its next item is, so each group drains them right after pulling S (no extra waits).
+#include <stdlib.h>
+
 #include "mae_internal.h"
 #include "attn_tc_common.cuh"
 
@@ -132,13 +134,16 @@ struct ItemIter {
   }
 };
 
+// optional clock64 timeline of CTA 0 (MAE_ENC_TIMELINE = device address of 4 x 128 int64 slots, tools/enc_timeline.py)
+#define ENC_TS(role, ev) do { if (tl != nullptr && blockIdx.x == 0 && (ev) < 128) tl[(role) * 128 + (ev)] = clock64(); } while (0)
+
 // =============================================================================================
 // forward
 // =============================================================================================
 template <int NG>
 struct EfCfg {
   static constexpr int kStages = NG == 3 ? 5 : 6;
-  static constexpr int kThreads = (4 * NG + 2) * 32;
+  static constexpr int kThreads = (4 * NG + 4) * 32;  // softmax groups + TMA producer + S issuer + two P V issuers
   static constexpr uint32_t qkv = 0;                              // [stages][Q, K, V]
   static constexpr uint32_t p = kStages * 3 * kEncTile;           // [NG groups] P tiles
   static constexpr uint32_t bars = p + NG * kEncPTile;
@@ -148,19 +153,19 @@ struct EfCfg {
 struct EfBars {
   uint64_t kv_full[6], kv_empty[6];  // Q / K / V of an item landed / its MMAs have completed
   uint64_t s_full[3], s_free[3];     // [group]: S complete in TMEM / pulled into registers
-  uint64_t p_ready[3], p_free[3];    // [group]: P tile written / P V has read it
-  uint64_t o_full[3];                // [group]: O complete in TMEM
+  uint64_t p_ready[3];               // [group]: P tile written (and O of the previous item drained)
+  uint64_t o_full[3];                // [group]: O complete in TMEM = P V has read the P tile
   uint32_t tmem_base;
 };
 
 template <int LP, int HDC>  // HDC = head_dim / 8 at compile time (0: runtime)
 __global__ void __launch_bounds__(EfCfg<EncGeo<LP>::NG>::kThreads, 1)
 attn_fwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
-                    int B, int L, int H, int hd, float scale) {
+                    int B, int L, int H, int hd, float scale, int dbg, long long* tl) {
   using Geo = EncGeo<LP>;
   constexpr int G = Geo::G, NG = Geo::NG, MS = Geo::MS;
   using Cfg = EfCfg<NG>;
-  constexpr int kProd = 4 * NG, kMma = 4 * NG + 1;
+  constexpr int kProd = 4 * NG, kMma = 4 * NG + 1, kPv = 4 * NG + 2;  // warps kPv, kPv + 1: P V of the even / odd items
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -177,7 +182,7 @@ attn_fwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, __nv_bfloat16* _
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&bars->kv_full[i], 1); mbar_init(&bars->kv_empty[i], 1); }
     for (int i = 0; i < NG; ++i) {
       mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_free[i], 4);
-      mbar_init(&bars->p_ready[i], 4); mbar_init(&bars->p_free[i], 1);
+      mbar_init(&bars->p_ready[i], 4);
       mbar_init(&bars->o_full[i], 1);
     }
     fence_mbar_init();
@@ -196,6 +201,7 @@ attn_fwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, __nv_bfloat16* _
       for (int n = 0, s = 0, ph = 1; n < my_items; ++n, it.next()) {
         mbar_wait(&bars->kv_empty[s], ph);
         const uint32_t dst = smem_u32(smem + Cfg::qkv + s * 3 * kEncTile);
+        if ((dbg & 2) && n >= Cfg::kStages) { mbar_arrive(&bars->kv_full[s]); if (++s == Cfg::kStages) { s = 0; ph ^= 1; } continue; }
         mbar_expect_tx(&bars->kv_full[s], 3 * Geo::kBox);
         tma_load_4d(dst, &mapQKV, &bars->kv_full[s], 0, it.h, 0, it.grp * G);
         tma_load_4d(dst + kEncTile, &mapQKV, &bars->kv_full[s], 0, H + it.h, 0, it.grp * G);
@@ -204,45 +210,53 @@ attn_fwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, __nv_bfloat16* _
       }
     }
   } else if (warp == kMma) {
+    // One thread can issue a tcgen05.mma only every ~70 cycles (tools/probes/umma_issue_probe.cu), the tensor pipe takes a
+    // small one every 40: the S MMAs and the P V MMAs of alternate items come from three different warps.
     if (lane == 0) {
       const uint32_t id_s = umma_idesc_bf16(128, Geo::NS, 0, 0);  // S: both operands K-major
+      const uint64_t t64 = umma_sdesc_sw64(0, 16, 512);
+      auto d_at = [](uint64_t templ, uint32_t addr) { return templ + uint64_t((addr & 0x3ffffu) >> 4); };
+      const uint32_t tiles0 = smem_u32(smem + Cfg::qkv);
+      for (int n = 0, st = 0, ph = 0, g = 0, k = 0; n < my_items; ++n) {
+        mbar_wait(&bars->kv_full[st], ph);
+        ENC_TS(0, 5 * n);
+        if (k >= 1) mbar_wait(&bars->s_free[g], (k - 1) & 1);
+        tc_fence_after();
+        ENC_TS(0, 5 * n + 1);
+        const uint32_t tb = tiles0 + uint32_t(st) * 3u * kEncTile;
+        const uint64_t dq = d_at(t64, tb), dk = d_at(t64, tb + kEncTile);
+        const uint32_t d = tmem_base + Cfg::colS + uint32_t(g) * 128u;
+        umma_bf16(d, dq, dk, id_s, 0);
+        umma_bf16(d, dq + 2, dk + 2, id_s, 1);  // +32 B per K = 16
+        umma_commit(&bars->s_full[g]);
+        ENC_TS(0, 5 * n + 2);
+        if (++st == Cfg::kStages) { st = 0; ph ^= 1; }
+        if (++g == NG) { g = 0; ++k; }
+      }
+    }
+  } else if (warp >= kPv) {
+    if (lane == 0) {
+      const int par = warp - kPv;  // this issuer's items: n = par, par + 2, ...
       const uint32_t id_o = umma_idesc_bf16(128, 32, 0, 1);       // O: A = P K-major, B = V MN-major
       const uint64_t t64 = umma_sdesc_sw64(0, 16, 512);
       const uint64_t t128 = umma_sdesc_sw128(0, 16, 1024);
       auto d_at = [](uint64_t templ, uint32_t addr) { return templ + uint64_t((addr & 0x3ffffu) >> 4); };
       const uint32_t tiles0 = smem_u32(smem + Cfg::qkv), p0 = smem_u32(smem + Cfg::p);
-      // step n issues S of item n, then O = P V of item n - (NG - 1): NG softmaxes are in flight
-      int s_st = 0, s_ph = 0, s_g = 0, s_k = 0;   // S side: stage / phase of kv_full, group, the group's item index
-      int o_st = 0, o_g = 0, o_k = 0;             // P V side
-      for (int n = 0; n < my_items + NG - 1; ++n) {
-        if (n < my_items) {
-          mbar_wait(&bars->kv_full[s_st], s_ph);
-          if (s_k >= 1) mbar_wait(&bars->s_free[s_g], (s_k - 1) & 1);
-          tc_fence_after();
-          const uint32_t tb = tiles0 + uint32_t(s_st) * 3u * kEncTile;
-          const uint64_t dq = d_at(t64, tb), dk = d_at(t64, tb + kEncTile);
-          const uint32_t d = tmem_base + Cfg::colS + uint32_t(s_g) * 128u;
-          umma_bf16(d, dq, dk, id_s, 0);
-          umma_bf16(d, dq + 2, dk + 2, id_s, 1);  // +32 B per K = 16
-          umma_commit(&bars->s_full[s_g]);
-          if (++s_st == Cfg::kStages) { s_st = 0; s_ph ^= 1; }
-          if (++s_g == NG) { s_g = 0; ++s_k; }
-        }
-        if (n >= NG - 1) {  // its softmax ran under the S MMAs above
-          mbar_wait(&bars->p_ready[o_g], o_k & 1);  // also: the group has drained O of its previous item (program order)
-          tc_fence_after();
-          const uint64_t a0 = d_at(t128, p0 + uint32_t(o_g) * kEncPTile);
-          uint64_t b = d_at(t64, tiles0 + uint32_t(o_st) * 3u * kEncTile + 2 * kEncTile);
-          const uint32_t d = tmem_base + Cfg::colO + uint32_t(o_g) * 32u;
+      for (int n = par; n < my_items; n += 2) {
+        const int st = n % Cfg::kStages, g = n % NG, k = n / NG;
+        mbar_wait(&bars->kv_full[st], (n / Cfg::kStages) & 1);  // (complete long ago: makes the TMA writes visible to this thread's MMAs)
+        mbar_wait(&bars->p_ready[g], k & 1);  // also: the group has drained O of its previous item (program order)
+        tc_fence_after();
+        if (par == 0) ENC_TS(0, 5 * n + 3);
+        const uint64_t a0 = d_at(t128, p0 + uint32_t(g) * kEncPTile);
+        uint64_t b = d_at(t64, tiles0 + uint32_t(st) * 3u * kEncTile + 2 * kEncTile);
+        const uint32_t d = tmem_base + Cfg::colO + uint32_t(g) * 32u;
 #pragma unroll
-          for (int j = 0; j < Geo::KS; ++j, b += 64)  // V as MN-major B: +1024 B per 16 keys
-            umma_bf16(d, a0 + uint64_t((uint32_t(j >> 2) * 16384u + uint32_t(j & 3) * 32u) >> 4), b, id_o, j != 0);
-          umma_commit(&bars->o_full[o_g]);
-          umma_commit(&bars->p_free[o_g]);
-          umma_commit(&bars->kv_empty[o_st]);
-          if (++o_st == Cfg::kStages) o_st = 0;
-          if (++o_g == NG) { o_g = 0; ++o_k; }
-        }
+        for (int j = 0; j < Geo::KS; ++j, b += 64)  // V as MN-major B: +1024 B per 16 keys
+          umma_bf16(d, a0 + uint64_t((uint32_t(j >> 2) * 16384u + uint32_t(j & 3) * 32u) >> 4), b, id_o, j != 0);
+        umma_commit(&bars->o_full[g]);
+        umma_commit(&bars->kv_empty[st]);
+        if (par == 0) ENC_TS(0, 5 * n + 4);
       }
     }
   } else {
@@ -273,10 +287,12 @@ attn_fwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, __nv_bfloat16* _
       if (k < cnt) {
         mbar_wait(&bars->s_full[gi], k & 1);
         tc_fence_after();
+        if (threadIdx.x == gi * 128) ENC_TS(1 + gi, 6 * k);
         tmem_ld_own<LP>(s_addr, g_lo, two, second, sr);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->s_free[gi]);
+        if (threadIdx.x == gi * 128) ENC_TS(1 + gi, 6 * k + 1);
       }
       if (k >= 1) {  // O rows of the group's previous item: complete, because its P V was issued before this item's S
         mbar_wait(&bars->o_full[gi], (k - 1) & 1);
@@ -302,9 +318,18 @@ attn_fwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, __nv_bfloat16* _
         }
       }
       if (k < cnt) {
+        if (threadIdx.x == gi * 128) ENC_TS(1 + gi, 6 * k + 2);
         const int b = it.grp * G + g, h = it.h;
         it.next();
         const bool ok = row_ok && b < B;
+        if (dbg & 1) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->p_ready[gi]);
+          inv_prev = __uint_as_float(sr[0]);
+          dst_prev = ok ? out + (size_t(b) * L + l) * D + h * hdv : nullptr;
+          continue;
+        }
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int i = 0; i < LP; ++i)
@@ -329,7 +354,9 @@ attn_fwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, __nv_bfloat16* _
         float s0, s1;
         upk2(add2(acc[0], acc[1]), s0, s1);
         const float sum = s0 + s1;
-        if (k >= 1) mbar_wait(&bars->p_free[gi], (k - 1) & 1);  // the previous item's P V has read the tile
+        if (threadIdx.x == gi * 128) ENC_TS(1 + gi, 6 * k + 3);
+        // (the P tile is free: o_full of the previous item, waited for above, is the completion of its P V)
+        if (threadIdx.x == gi * 128) ENC_TS(1 + gi, 6 * k + 4);
         if (g < G) {
 #pragma unroll
           for (int j = 0; j < LP / 8; ++j) {
@@ -340,6 +367,7 @@ attn_fwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, __nv_bfloat16* _
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->p_ready[gi]);
+        if (threadIdx.x == gi * 128) ENC_TS(1 + gi, 6 * k + 5);
         if (ok) lse[(size_t(b) * H + h) * L + l] = (msl2 + lg2_approx(sum)) * 0.6931471805599453f;
         inv_prev = rcp_approx(sum);
         dst_prev = ok ? out + (size_t(b) * L + l) * D + h * hdv : nullptr;
@@ -360,13 +388,13 @@ attn_fwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, __nv_bfloat16* _
 // pulls its rows into registers at once, which frees it for the next item); the bf16 P and dS tiles (block diagonal,
 // one pair per group) feed dQ = dS K as K-major A and dK / dV as MN-major A.
 // =============================================================================================
-static constexpr int kEbThreads = 10 * 32;
+static constexpr int kEbThreads = 12 * 32;  // 2 softmax groups, TMA producer, three MMA issuers (S / dP + dQ, dK, dV)
 static constexpr int kEbStages = 3;
 struct EbBars {
   uint64_t ld_full[kEbStages], ld_empty[kEbStages];
   uint64_t sd_full[2], sd_free[2];     // [group]: S and dP complete / pulled out of TMEM
-  uint64_t pds_ready[2], pds_free[2];  // [group]: P and dS tiles written / the MMAs reading them are done
-  uint64_t g_full[2];                  // [group]: dQ, dK, dV complete
+  uint64_t pds_ready[2];               // [group]: P and dS tiles written (and the previous item's gradients drained)
+  uint64_t g_full[2];                  // [group]: dQ, dK, dV complete (three issuers) = the P / dS tiles have been read
   uint32_t tmem_base;
 };
 struct EbSmem {
@@ -380,7 +408,7 @@ static constexpr uint32_t kEbColS = 0, kEbColDP = 128, kEbColG = 256;  // per gr
 template <int LP, int HDC>
 __global__ void __launch_bounds__(kEbThreads, 1)
 attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ CUtensorMap mapDO,
-                    const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, int B, int L, int H, int hd, float scale) {
+                    const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, int B, int L, int H, int hd, float scale, int dbg) {
   using Geo = EncGeo<LP>;
   constexpr int G = Geo::G, MS = Geo::MS;
   pdl_trigger();
@@ -396,11 +424,11 @@ attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&mapQKV);
     tma_prefetch_desc(&mapDO);
-    for (int i = 0; i < kEbStages; ++i) { mbar_init(&bars->ld_full[i], 1); mbar_init(&bars->ld_empty[i], 1); }
+    for (int i = 0; i < kEbStages; ++i) { mbar_init(&bars->ld_full[i], 1); mbar_init(&bars->ld_empty[i], 3); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->sd_full[i], 1); mbar_init(&bars->sd_free[i], 4);
-      mbar_init(&bars->pds_ready[i], 4); mbar_init(&bars->pds_free[i], 1);
-      mbar_init(&bars->g_full[i], 1);
+      mbar_init(&bars->pds_ready[i], 4);
+      mbar_init(&bars->g_full[i], 3);
     }
     fence_mbar_init();
   }
@@ -418,6 +446,7 @@ attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
       for (int n = 0, s = 0, ph = 1; n < my_items; ++n, it.next()) {
         mbar_wait(&bars->ld_empty[s], ph);
         const uint32_t dst = smem_u32(smem + EbSmem::tiles + s * 4 * kEncTile);
+        if ((dbg & 2) && n >= kEbStages) { mbar_arrive(&bars->ld_full[s]); if (++s == kEbStages) { s = 0; ph ^= 1; } continue; }
         mbar_expect_tx(&bars->ld_full[s], 4 * Geo::kBox);
         tma_load_4d(dst, &mapQKV, &bars->ld_full[s], 0, it.h, 0, it.grp * G);
         tma_load_4d(dst + kEncTile, &mapQKV, &bars->ld_full[s], 0, H + it.h, 0, it.grp * G);
@@ -426,8 +455,11 @@ attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
         if (++s == kEbStages) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp >= 9) {
+    // Three issuers (one thread issues a tcgen05.mma only every ~70 cycles, the tensor pipe takes a small one every 40):
+    // warp 9: S / dP of the next item, then dQ;  warp 10: dK;  warp 11: dV.  Each commits to g_full and ld_empty.
     if (lane == 0) {
+      const int role = warp - 9;
       const uint32_t id_s = umma_idesc_bf16(128, Geo::NS, 0, 0);  // S, dP: both operands K-major
       const uint32_t id_q = umma_idesc_bf16(128, 32, 0, 1);       // dQ: A K-major, B MN-major
       const uint32_t id_kv = umma_idesc_bf16(128, 32, 1, 1);      // dK, dV: both MN-major
@@ -436,59 +468,65 @@ attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
       const uint64_t t128mn = umma_sdesc_sw128(0, 16384, 1024);    // ... as MN-major A (LBO = stride between the 64-key boxes)
       auto d_at = [](uint64_t templ, uint32_t addr) { return templ + uint64_t((addr & 0x3ffffu) >> 4); };
       const uint32_t tiles0 = smem_u32(smem + EbSmem::tiles), pds0 = smem_u32(smem + EbSmem::pds);
-      auto issue_sdp = [&](int st, int gi) {
-        const uint32_t tb = tiles0 + uint32_t(st) * 4u * kEncTile;
-        const uint64_t dq = d_at(t64, tb), dk = d_at(t64, tb + kEncTile), dv = d_at(t64, tb + 2 * kEncTile),
-                       ddo = d_at(t64, tb + 3 * kEncTile);
-        umma_bf16(tmem_base + kEbColS, dq, dk, id_s, 0);
-        umma_bf16(tmem_base + kEbColS, dq + 2, dk + 2, id_s, 1);
-        umma_bf16(tmem_base + kEbColDP, ddo, dv, id_s, 0);
-        umma_bf16(tmem_base + kEbColDP, ddo + 2, dv + 2, id_s, 1);
-        umma_commit(&bars->sd_full[gi]);
-      };
-      auto issue_grads = [&](int st, int gi) {
-        const uint32_t tb = tiles0 + uint32_t(st) * 4u * kEncTile;
-        const uint32_t sp = pds0 + uint32_t(gi) * 2u * kEncPTile, sds = sp + kEncPTile;
-        const uint32_t dcol = tmem_base + kEbColG + uint32_t(gi) * 96u;
-        {  // dQ = dS . K   (B = K tile as MN-major: +1024 B per 16 keys)
-          const uint64_t a0 = d_at(t128k, sds);
-          uint64_t b = d_at(t64, tb + kEncTile);
-#pragma unroll
-          for (int j = 0; j < Geo::KS; ++j, b += 64)
-            umma_bf16(dcol, a0 + uint64_t((uint32_t(j >> 2) * 16384u + uint32_t(j & 3) * 32u) >> 4), b, id_q, j != 0);
-        }
-        {  // dK = dS^T . Q,  dV = P^T . dO   (M = keys; K = query rows: A +2048 B, B +1024 B per 16 rows)
-          uint64_t a = d_at(t128mn, sds), b = d_at(t64, tb);
-#pragma unroll
-          for (int s = 0; s < Geo::KS; ++s, a += 128, b += 64) umma_bf16(dcol + 32, a, b, id_kv, s != 0);
-          a = d_at(t128mn, sp); b = d_at(t64, tb + 3 * kEncTile);
-#pragma unroll
-          for (int s = 0; s < Geo::KS; ++s, a += 128, b += 64) umma_bf16(dcol + 64, a, b, id_kv, s != 0);
-        }
-        umma_commit(&bars->g_full[gi]);
-        umma_commit(&bars->pds_free[gi]);
-        umma_commit(&bars->ld_empty[st]);
-      };
-      int st_next = 0, ph_next = 0;  // stage / kv phase of the next item whose S / dP will be issued
-      if (my_items > 0) {
-        mbar_wait(&bars->ld_full[0], 0);
-        tc_fence_after();
-        issue_sdp(0, 0);
-        st_next = 1;
-      }
-      int st = 0;
-      for (int n = 0; n < my_items; ++n) {
-        if (n + 1 < my_items) {  // the next item's S / dP as soon as this item's rows are in registers
-          mbar_wait(&bars->ld_full[st_next], ph_next);
-          mbar_wait(&bars->sd_free[n & 1], (n >> 1) & 1);
+      if (role == 0) {
+        auto issue_sdp = [&](int st, int gi) {
+          const uint32_t tb = tiles0 + uint32_t(st) * 4u * kEncTile;
+          const uint64_t dq = d_at(t64, tb), dk = d_at(t64, tb + kEncTile), dv = d_at(t64, tb + 2 * kEncTile),
+                         ddo = d_at(t64, tb + 3 * kEncTile);
+          umma_bf16(tmem_base + kEbColS, dq, dk, id_s, 0);
+          umma_bf16(tmem_base + kEbColS, dq + 2, dk + 2, id_s, 1);
+          umma_bf16(tmem_base + kEbColDP, ddo, dv, id_s, 0);
+          umma_bf16(tmem_base + kEbColDP, ddo + 2, dv + 2, id_s, 1);
+          umma_commit(&bars->sd_full[gi]);
+        };
+        int st_next = 0, ph_next = 0;  // stage / phase of the next item whose S / dP will be issued
+        if (my_items > 0) {
+          mbar_wait(&bars->ld_full[0], 0);
           tc_fence_after();
-          issue_sdp(st_next, (n + 1) & 1);
-          if (++st_next == kEbStages) { st_next = 0; ph_next ^= 1; }
+          issue_sdp(0, 0);
+          st_next = 1;
         }
-        mbar_wait(&bars->pds_ready[n & 1], (n >> 1) & 1);  // also: the group has drained dQ / dK / dV of its previous item
-        tc_fence_after();
-        issue_grads(st, n & 1);
-        if (++st == kEbStages) st = 0;
+        int st = 0;
+        for (int n = 0; n < my_items; ++n) {
+          const int gi = n & 1;
+          if (n + 1 < my_items) {  // the next item's S / dP as soon as this item's rows are in registers
+            mbar_wait(&bars->ld_full[st_next], ph_next);
+            mbar_wait(&bars->sd_free[gi], (n >> 1) & 1);
+            tc_fence_after();
+            issue_sdp(st_next, gi ^ 1);
+            if (++st_next == kEbStages) { st_next = 0; ph_next ^= 1; }
+          }
+          mbar_wait(&bars->pds_ready[gi], (n >> 1) & 1);  // also: the group has drained dQ / dK / dV of its previous item
+          tc_fence_after();
+          {  // dQ = dS . K   (B = K tile as MN-major: +1024 B per 16 keys)
+            const uint64_t a0 = d_at(t128k, pds0 + uint32_t(gi) * 2u * kEncPTile + kEncPTile);
+            uint64_t b = d_at(t64, tiles0 + uint32_t(st) * 4u * kEncTile + kEncTile);
+            const uint32_t dcol = tmem_base + kEbColG + uint32_t(gi) * 96u;
+#pragma unroll
+            for (int j = 0; j < Geo::KS; ++j, b += 64)
+              umma_bf16(dcol, a0 + uint64_t((uint32_t(j >> 2) * 16384u + uint32_t(j & 3) * 32u) >> 4), b, id_q, j != 0);
+          }
+          umma_commit(&bars->g_full[gi]);
+          umma_commit(&bars->ld_empty[st]);
+          if (++st == kEbStages) st = 0;
+        }
+      } else {
+        // dK = dS^T . Q  (role 1),  dV = P^T . dO  (role 2):  M = keys; K = query rows: A +2048 B, B +1024 B per 16 rows
+        for (int n = 0, st = 0, ph = 0; n < my_items; ++n) {
+          const int gi = n & 1;
+          mbar_wait(&bars->ld_full[st], ph);  // (complete long ago: makes the TMA writes visible to this thread's MMAs)
+          mbar_wait(&bars->pds_ready[gi], (n >> 1) & 1);
+          tc_fence_after();
+          const uint32_t tb = tiles0 + uint32_t(st) * 4u * kEncTile;
+          const uint32_t sp = pds0 + uint32_t(gi) * 2u * kEncPTile;
+          uint64_t a = d_at(t128mn, role == 1 ? sp + kEncPTile : sp), b = d_at(t64, role == 1 ? tb : tb + 3 * kEncTile);
+          const uint32_t dcol = tmem_base + kEbColG + uint32_t(gi) * 96u + (role == 1 ? 32u : 64u);
+#pragma unroll
+          for (int s = 0; s < Geo::KS; ++s, a += 128, b += 64) umma_bf16(dcol, a, b, id_kv, s != 0);
+          umma_commit(&bars->g_full[gi]);
+          umma_commit(&bars->ld_empty[st]);
+          if (++st == kEbStages) { st = 0; ph ^= 1; }
+        }
       }
     }
   } else {
@@ -561,6 +599,14 @@ attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
           const int bn = it.grp * G + g;
           if (k + 1 < cnt && row_ok && bn < B) lse_next = __ldg(lse + (size_t(bn) * H + it.h) * L + l);
         }
+        if (dbg & 1) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->pds_ready[gi]);
+          dst_prev = ok ? dqkv + (size_t(b) * L + l) * 3 * D + h * hdv + (sr[0] == 0x12345u) + (dr[0] == 0x12345u) : nullptr;
+          lse2 = lse_next * l2e + __uint_as_float(nl2 >> 40) * 0.f;
+          continue;
+        }
         uint64_t dacc[2] = {pk2(0.f, 0.f), pk2(0.f, 0.f)};
 #pragma unroll
         for (int i = 0; i < LP / 2; ++i) {  // S -> P in place (fp32), delta accumulated on the way
@@ -579,7 +625,7 @@ attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
         upk2(add2(dacc[0], dacc[1]), d0, d1);
         const float nds = -(d0 + d1) * scale;  // - delta / sqrt(hd)
         const uint64_t nds2 = pk2(nds, nds);
-        if (k >= 1) mbar_wait(&bars->pds_free[gi], (k - 1) & 1);  // the previous item's MMAs have read the tiles
+        // (the P / dS tiles are free: g_full of the previous item, waited for above, is the completion of the MMAs reading them)
         if (g < G) {
 #pragma unroll
           for (int j = 0; j < LP / 8; ++j) {
@@ -611,6 +657,17 @@ attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
   if (warp == 9) tmem_dealloc(tmem_base, 512);
 }
 
+// MAE_ENC_DBG (measurement only, results are wrong): 1 = softmax threads skip the arithmetic, 2 = no TMA after the first stages
+static int enc_dbg() {
+  static const int v = getenv("MAE_ENC_DBG") ? atoi(getenv("MAE_ENC_DBG")) : 0;
+  return v;
+}
+
+static long long* enc_timeline() {
+  static long long* v = getenv("MAE_ENC_TIMELINE") ? reinterpret_cast<long long*>(strtoull(getenv("MAE_ENC_TIMELINE"), nullptr, 0)) : nullptr;
+  return v;
+}
+
 template <int LP, int HDC>
 static int launch_fwd_enc(const void* qkv, int B, int L, int H, int hd, void* out, float* lse, cudaStream_t st) {
   using Geo = EncGeo<LP>;
@@ -624,7 +681,7 @@ static int launch_fwd_enc(const void* qkv, int B, int L, int H, int hd, void* ou
   const int nitems = ((B + Geo::G - 1) / Geo::G) * H;
   const int grid = nitems < sms ? nitems : sms;
   mae_launch(attn_fwd_enc_kernel<LP, HDC>, dim3(grid), dim3(Cfg::kThreads), size_t(Cfg::total) + 1024, st, mq,
-             reinterpret_cast<__nv_bfloat16*>(out), lse, B, L, H, hd, 1.0f / sqrtf(float(hd)));
+             reinterpret_cast<__nv_bfloat16*>(out), lse, B, L, H, hd, 1.0f / sqrtf(float(hd)), enc_dbg(), enc_timeline());
   return MAE_CHECK_LAUNCH();
 }
 
@@ -643,7 +700,7 @@ static int launch_bwd_enc(const void* qkv, const void* dout, const float* lse, i
   const int nitems = ((B + Geo::G - 1) / Geo::G) * H;
   const int grid = nitems < sms ? nitems : sms;
   mae_launch(attn_bwd_enc_kernel<LP, HDC>, dim3(grid), dim3(kEbThreads), size_t(EbSmem::total) + 1024, st, mq, md, lse,
-             reinterpret_cast<__nv_bfloat16*>(dqkv), B, L, H, hd, 1.0f / sqrtf(float(hd)));
+             reinterpret_cast<__nv_bfloat16*>(dqkv), B, L, H, hd, 1.0f / sqrtf(float(hd)), enc_dbg());
   return MAE_CHECK_LAUNCH();
 }
 
