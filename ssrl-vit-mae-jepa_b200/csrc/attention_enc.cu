@@ -99,6 +99,48 @@ __device__ __forceinline__ uint4 lds16(uint32_t saddr) {
   return v;
 }
 
+// Ampere-style 16-byte async copies (LDGSTS): TMA serves these tiles at ~3.3 cycles per 48-byte row (one request per
+// (token, head) row: 1.2 k cycles per forward item, measured), loader warps with one 16-byte chunk per lane are faster
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {  // src_bytes 0: zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Chunk table of one loader thread: the 16-byte chunks (tensor slice t, live row, chunk j) it copies for every item, as
+// offsets from the item's base address (global) and from the stage base (shared, 64-byte-swizzled tile t).  Rows >= L of a
+// sample slot and the chunks past the head dim are never written: they stay zero from the kernel prologue.
+template <int LP, int MAXC>
+struct ChunkTable {
+  uint32_t goff[MAXC], soff[MAXC];  // soff: bits 0..15 smem offset, bits 16.. sample slot (0xffffffff: no chunk)
+  __device__ __forceinline__ void init(int lt, int nthreads, int nt, int L, int ch, uint32_t row_bytes, uint32_t slice_bytes, int dbg = 0) {
+    constexpr int G = 128 / LP;
+    const int per_t = G * L * ch, total = nt * per_t;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      const int idx = lt + nthreads * c;
+      goff[c] = 0; soff[c] = 0xffffffffu;
+      if (idx < total) {
+        const int t = idx / per_t, rem = idx - t * per_t, rl = rem / ch, j = rem - rl * ch, g = rl / L, l = rl - g * L;
+        const int row = g * LP + l;
+        goff[c] = uint32_t(rl) * row_bytes + uint32_t(t) * slice_bytes + uint32_t(j) * 16u;
+        soff[c] = (uint32_t(t) * (128u * 64u) + uint32_t(row) * 64u + (uint32_t(j ^ ((row >> 1) & 3)) << 4)) | (uint32_t(g) << 16);
+        if ((dbg & 4) && j != 0) soff[c] = 0xffffffffu;  // timing experiment: one chunk per row (same requests, a third of the bytes)
+        if (dbg & 8) goff[c] = uint32_t(idx) * 16u;      // timing experiment: the same bytes from contiguous addresses
+      }
+    }
+  }
+  __device__ __forceinline__ void issue(uint32_t stage, const char* base, int nvalid) const {
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (soff[c] != 0xffffffffu) {
+        const bool ok = int(soff[c] >> 16) < nvalid;  // sample slots past the batch end are zero-filled
+        cp_async16(stage + (soff[c] & 0xffffu), ok ? base + goff[c] : base, ok ? 16u : 0u);
+      }
+  }
+};
+
 static constexpr uint32_t kEncTile = 128 * 64;   // one [128 x 32] bf16 operand tile
 static constexpr uint32_t kEncPTile = 2 * 16384;  // [128 queries x 128 keys] bf16, two 128-byte-swizzled boxes of 64 keys
 
@@ -121,7 +163,7 @@ struct EncGeo {
   static constexpr uint32_t kBox = uint32_t(ROWS) * 64u;   // bytes one TMA box writes
   // a kernel instance serves MS < L <= LP (MS = the next smaller pitch): only columns >= MS need the `< L` predicate
   static constexpr int MS = LP == 16 ? 0 : LP == 32 ? 16 : LP == 40 ? 32 : LP == 48 ? 40 : 48;
-  static constexpr int NG = LP <= 48 ? 3 : 2;              // forward: softmax groups (registers: 144 per thread at 14 warps)
+  static constexpr int NG = 2;                              // forward: softmax groups
 };
 
 // (group of samples, head) of the k-th item of a softmax group, advanced without divisions
@@ -143,7 +185,8 @@ struct ItemIter {
 template <int NG>
 struct EfCfg {
   static constexpr int kStages = NG == 3 ? 5 : 6;
-  static constexpr int kThreads = (4 * NG + 4) * 32;  // softmax groups + TMA producer + S issuer + two P V issuers
+  static constexpr int kLoadAhead = 4;                            // cp.async groups in flight per loader thread (<= 4)
+  static constexpr int kThreads = (4 * NG + 7) * 32;  // softmax groups + 4 loader warps + S issuer + two P V issuers
   static constexpr uint32_t qkv = 0;                              // [stages][Q, K, V]
   static constexpr uint32_t p = kStages * 3 * kEncTile;           // [NG groups] P tiles
   static constexpr uint32_t bars = p + NG * kEncPTile;
@@ -160,12 +203,13 @@ struct EfBars {
 
 template <int LP, int HDC>  // HDC = head_dim / 8 at compile time (0: runtime)
 __global__ void __launch_bounds__(EfCfg<EncGeo<LP>::NG>::kThreads, 1)
-attn_fwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
+attn_fwd_enc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
                     int B, int L, int H, int hd, float scale, int dbg, long long* tl) {
   using Geo = EncGeo<LP>;
   constexpr int G = Geo::G, NG = Geo::NG, MS = Geo::MS;
   using Cfg = EfCfg<NG>;
-  constexpr int kProd = 4 * NG, kMma = 4 * NG + 1, kPv = 4 * NG + 2;  // warps kPv, kPv + 1: P V of the even / odd items
+  constexpr int kProd = 4 * NG, kMma = 4 * NG + 4, kPv = 4 * NG + 5;  // warps kProd..+3: loaders; kPv, kPv + 1: P V of the even / odd items
+  if (threadIdx.x == 0) ENC_TS(3, 0);
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -178,8 +222,7 @@ attn_fwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, __nv_bfloat16* _
   // zero the operand and P tiles once: rows past G * LP, and the off-diagonal blocks of P, are never written afterwards
   for (uint32_t i = threadIdx.x; i < Cfg::bars / 16; i += Cfg::kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (warp == kProd && lane == 0) {
-    tma_prefetch_desc(&mapQKV);
-    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&bars->kv_full[i], 1); mbar_init(&bars->kv_empty[i], 1); }
+    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&bars->kv_full[i], 128); mbar_init(&bars->kv_empty[i], 1); }
     for (int i = 0; i < NG; ++i) {
       mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_free[i], 4);
       mbar_init(&bars->p_ready[i], 4);
@@ -192,21 +235,52 @@ attn_fwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, __nv_bfloat16* _
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (threadIdx.x == 0) ENC_TS(3, 1);
   const uint32_t tmem_base = bars->tmem_base;
+  ChunkTable<LP, 12> tab;  // loader warps: built before the grid dependency resolves (divisions; no global memory access)
+  if (warp >= kProd && warp < kMma) {
+    const int hdl = HDC ? HDC * 8 : hd;
+    tab.init(int(threadIdx.x) - kProd * 32, 128, 3, L, hdl >> 3, uint32_t(3 * H * hdl) * 2u, uint32_t(H * hdl) * 2u, dbg);
+  }
   pdl_wait();
+  if (threadIdx.x == 0) ENC_TS(3, 2);
 
-  if (warp == kProd) {
-    if (lane == 0) {
-      ItemIter it(int(blockIdx.x), int(gridDim.x), H);
-      for (int n = 0, s = 0, ph = 1; n < my_items; ++n, it.next()) {
-        mbar_wait(&bars->kv_empty[s], ph);
-        const uint32_t dst = smem_u32(smem + Cfg::qkv + s * 3 * kEncTile);
-        if ((dbg & 2) && n >= Cfg::kStages) { mbar_arrive(&bars->kv_full[s]); if (++s == Cfg::kStages) { s = 0; ph ^= 1; } continue; }
-        mbar_expect_tx(&bars->kv_full[s], 3 * Geo::kBox);
-        tma_load_4d(dst, &mapQKV, &bars->kv_full[s], 0, it.h, 0, it.grp * G);
-        tma_load_4d(dst + kEncTile, &mapQKV, &bars->kv_full[s], 0, H + it.h, 0, it.grp * G);
-        tma_load_4d(dst + 2 * kEncTile, &mapQKV, &bars->kv_full[s], 0, 2 * H + it.h, 0, it.grp * G);
+  if (warp >= kProd && warp < kMma) {
+    // loader warps: Q / K / V chunks of the item by 16-byte async copies, kLoadAhead items in flight per thread; the
+    // writer makes its completed copies visible to the async proxy (fence) before it arrives on the stage's barrier
+    const int hdl = HDC ? HDC * 8 : hd;
+    const uint32_t stage0 = smem_u32(smem + Cfg::qkv);
+    const size_t grp_bytes = size_t(G) * L * 3 * H * hdl * 2;
+    ItemIter it(int(blockIdx.x), int(gridDim.x), H);
+    // event driven: issue up to kLoadAhead items ahead while stages are free, otherwise retire the oldest outstanding
+    // group (its arrival must not wait for a stage that only frees once older items have been consumed)
+    int issued = 0, retired = 0, s = 0, ph = 1, sd = 0;
+    while (retired < my_items) {
+      const int outstanding = issued - retired;
+      bool go = issued < my_items && outstanding < Cfg::kLoadAhead;
+      if (go) {
+        if (outstanding == 0) mbar_wait(&bars->kv_empty[s], ph);
+        else go = mbar_test_wait(&bars->kv_empty[s], ph);
+      }
+      if (go) {
+        if (!((dbg & 2) && issued >= Cfg::kStages))
+          tab.issue(stage0 + uint32_t(s) * 3u * kEncTile, reinterpret_cast<const char*>(qkv) + size_t(it.grp) * grp_bytes + size_t(it.h) * hdl * 2,
+                    B - it.grp * G);
+        cp_async_commit();
+        it.next();
+        ++issued;
         if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+      } else {
+        switch (outstanding) {
+          case 1: cp_async_wait<0>(); break;
+          case 2: cp_async_wait<1>(); break;
+          case 3: cp_async_wait<2>(); break;
+          default: cp_async_wait<3>(); break;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&bars->kv_full[sd]);
+        ++retired;
+        if (++sd == Cfg::kStages) sd = 0;
       }
     }
   } else if (warp == kMma) {
@@ -374,8 +448,10 @@ attn_fwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, __nv_bfloat16* _
       }
     }
   }
+  if (threadIdx.x == 0) ENC_TS(3, 3);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) ENC_TS(3, 4);
   if (warp == kMma) tmem_dealloc(tmem_base, 512);
 }
 
@@ -672,16 +748,14 @@ template <int LP, int HDC>
 static int launch_fwd_enc(const void* qkv, int B, int L, int H, int hd, void* out, float* lse, cudaStream_t st) {
   using Geo = EncGeo<LP>;
   using Cfg = EfCfg<Geo::NG>;
-  CUtensorMap mq;
-  int rc = make_tmap_enc(&mq, qkv, hd, 3 * H, L, B, LP, Geo::G);
-  if (rc) return rc;
+  if (reinterpret_cast<uintptr_t>(qkv) & 15) return MAE_ERR_ALIGN;
   static bool done[kMaxDevices] = {};
   if (!ensure_dyn_smem(attn_fwd_enc_kernel<LP, HDC>, Cfg::total + 1024, done)) return MAE_ERR_LAUNCH;
   const int sms = num_sms();
   const int nitems = ((B + Geo::G - 1) / Geo::G) * H;
   const int grid = nitems < sms ? nitems : sms;
-  mae_launch(attn_fwd_enc_kernel<LP, HDC>, dim3(grid), dim3(Cfg::kThreads), size_t(Cfg::total) + 1024, st, mq,
-             reinterpret_cast<__nv_bfloat16*>(out), lse, B, L, H, hd, 1.0f / sqrtf(float(hd)), enc_dbg(), enc_timeline());
+  mae_launch(attn_fwd_enc_kernel<LP, HDC>, dim3(grid), dim3(Cfg::kThreads), size_t(Cfg::total) + 1024, st,
+             reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), lse, B, L, H, hd, 1.0f / sqrtf(float(hd)), enc_dbg(), enc_timeline());
   return MAE_CHECK_LAUNCH();
 }
 

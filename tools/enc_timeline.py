@@ -15,6 +15,9 @@ for _ in range(3):
 torch.cuda.synchronize()
 t = tl.cpu().view(4, 128)
 t0 = int(t[t > 0].min())
+print("kernel: [entry, setup done, pdl_wait done, thread 0 loop done, all warps done]", [int(x) - t0 if x > 0 else None for x in t[3, 0:5]], "items per CTA ~", 4002 / 148)
+last = [int(x) - t0 for x in t[0] if x > 0]
+print("last MMA stamp", max(last))
 print("MMA issuer, per step: [kv_full ok, s_free ok, S committed, p_ready ok, PV committed]")
 for n in range(14):
     print(n, [int(x) - t0 if x > 0 else None for x in t[0, 5 * n:5 * n + 5]])
