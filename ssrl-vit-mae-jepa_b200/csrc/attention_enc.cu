@@ -214,7 +214,7 @@ attn_fwd_enc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   EfBars* bars = reinterpret_cast<EfBars*>(smem + Cfg::bars);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const int ngroups = (B + G - 1) / G;
   const int nitems = ngroups * H;
   const int my_items = nitems > int(blockIdx.x) ? (nitems - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
@@ -286,30 +286,33 @@ attn_fwd_enc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
   } else if (warp == kMma) {
     // One thread can issue a tcgen05.mma only every ~70 cycles (tools/probes/umma_issue_probe.cu), the tensor pipe takes a
     // small one every 40: the S MMAs and the P V MMAs of alternate items come from three different warps.
-    if (lane == 0) {
+    {  // the whole warp runs the loop (uniform control flow, descriptors in uniform registers); one elected lane issues
       const uint32_t id_s = umma_idesc_bf16(128, Geo::NS, 0, 0);  // S: both operands K-major
       const uint64_t t64 = umma_sdesc_sw64(0, 16, 512);
       auto d_at = [](uint64_t templ, uint32_t addr) { return templ + uint64_t((addr & 0x3ffffu) >> 4); };
       const uint32_t tiles0 = smem_u32(smem + Cfg::qkv);
       for (int n = 0, st = 0, ph = 0, g = 0, k = 0; n < my_items; ++n) {
         mbar_wait(&bars->kv_full[st], ph);
-        ENC_TS(0, 5 * n);
+        if (lane == 0) ENC_TS(0, 5 * n);
         if (k >= 1) mbar_wait(&bars->s_free[g], (k - 1) & 1);
         tc_fence_after();
-        ENC_TS(0, 5 * n + 1);
+        if (lane == 0) ENC_TS(0, 5 * n + 1);
         const uint32_t tb = tiles0 + uint32_t(st) * 3u * kEncTile;
         const uint64_t dq = d_at(t64, tb), dk = d_at(t64, tb + kEncTile);
         const uint32_t d = tmem_base + Cfg::colS + uint32_t(g) * 128u;
-        umma_bf16(d, dq, dk, id_s, 0);
-        umma_bf16(d, dq + 2, dk + 2, id_s, 1);  // +32 B per K = 16
-        umma_commit(&bars->s_full[g]);
-        ENC_TS(0, 5 * n + 2);
+        if (elect_one_sync()) {
+          umma_bf16(d, dq, dk, id_s, 0);
+          umma_bf16(d, dq + 2, dk + 2, id_s, 1);  // +32 B per K = 16
+          umma_commit(&bars->s_full[g]);
+        }
+        __syncwarp();
+        if (lane == 0) ENC_TS(0, 5 * n + 2);
         if (++st == Cfg::kStages) { st = 0; ph ^= 1; }
         if (++g == NG) { g = 0; ++k; }
       }
     }
   } else if (warp >= kPv) {
-    if (lane == 0) {
+    {
       const int par = warp - kPv;  // this issuer's items: n = par, par + 2, ...
       const uint32_t id_o = umma_idesc_bf16(128, 32, 0, 1);       // O: A = P K-major, B = V MN-major
       const uint64_t t64 = umma_sdesc_sw64(0, 16, 512);
@@ -321,16 +324,19 @@ attn_fwd_enc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __rest
         mbar_wait(&bars->kv_full[st], (n / Cfg::kStages) & 1);  // (complete long ago: makes the TMA writes visible to this thread's MMAs)
         mbar_wait(&bars->p_ready[g], k & 1);  // also: the group has drained O of its previous item (program order)
         tc_fence_after();
-        if (par == 0) ENC_TS(0, 5 * n + 3);
+        if (par == 0 && lane == 0) ENC_TS(0, 5 * n + 3);
         const uint64_t a0 = d_at(t128, p0 + uint32_t(g) * kEncPTile);
-        uint64_t b = d_at(t64, tiles0 + uint32_t(st) * 3u * kEncTile + 2 * kEncTile);
+        const uint64_t b0 = d_at(t64, tiles0 + uint32_t(st) * 3u * kEncTile + 2 * kEncTile);
         const uint32_t d = tmem_base + Cfg::colO + uint32_t(g) * 32u;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int j = 0; j < Geo::KS; ++j, b += 64)  // V as MN-major B: +1024 B per 16 keys
-          umma_bf16(d, a0 + uint64_t((uint32_t(j >> 2) * 16384u + uint32_t(j & 3) * 32u) >> 4), b, id_o, j != 0);
-        umma_commit(&bars->o_full[g]);
-        umma_commit(&bars->kv_empty[st]);
-        if (par == 0) ENC_TS(0, 5 * n + 4);
+          for (int j = 0; j < Geo::KS; ++j)  // V as MN-major B: +1024 B per 16 keys
+            umma_bf16(d, a0 + uint64_t((uint32_t(j >> 2) * 16384u + uint32_t(j & 3) * 32u) >> 4), b0 + uint64_t(64 * j), id_o, j != 0);
+          umma_commit(&bars->o_full[g]);
+          umma_commit(&bars->kv_empty[st]);
+        }
+        __syncwarp();
+        if (par == 0 && lane == 0) ENC_TS(0, 5 * n + 4);
       }
     }
   } else {
@@ -491,7 +497,7 @@ attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   EbBars* bars = reinterpret_cast<EbBars*>(smem + EbSmem::bars);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const int ngroups = (B + G - 1) / G;
   const int nitems = ngroups * H;
   const int my_items = nitems > int(blockIdx.x) ? (nitems - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
@@ -517,24 +523,30 @@ attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
   pdl_wait();
 
   if (warp == 8) {
-    if (lane == 0) {
+    {  // whole warp, uniform control flow; one elected lane issues the TMA loads
       ItemIter it(int(blockIdx.x), int(gridDim.x), H);
       for (int n = 0, s = 0, ph = 1; n < my_items; ++n, it.next()) {
         mbar_wait(&bars->ld_empty[s], ph);
         const uint32_t dst = smem_u32(smem + EbSmem::tiles + s * 4 * kEncTile);
-        if ((dbg & 2) && n >= kEbStages) { mbar_arrive(&bars->ld_full[s]); if (++s == kEbStages) { s = 0; ph ^= 1; } continue; }
-        mbar_expect_tx(&bars->ld_full[s], 4 * Geo::kBox);
-        tma_load_4d(dst, &mapQKV, &bars->ld_full[s], 0, it.h, 0, it.grp * G);
-        tma_load_4d(dst + kEncTile, &mapQKV, &bars->ld_full[s], 0, H + it.h, 0, it.grp * G);
-        tma_load_4d(dst + 2 * kEncTile, &mapQKV, &bars->ld_full[s], 0, 2 * H + it.h, 0, it.grp * G);
-        tma_load_4d(dst + 3 * kEncTile, &mapDO, &bars->ld_full[s], 0, it.h, 0, it.grp * G);
+        if (elect_one_sync()) {
+          if ((dbg & 2) && n >= kEbStages) {
+            mbar_arrive(&bars->ld_full[s]);
+          } else {
+            mbar_expect_tx(&bars->ld_full[s], 4 * Geo::kBox);
+            tma_load_4d(dst, &mapQKV, &bars->ld_full[s], 0, it.h, 0, it.grp * G);
+            tma_load_4d(dst + kEncTile, &mapQKV, &bars->ld_full[s], 0, H + it.h, 0, it.grp * G);
+            tma_load_4d(dst + 2 * kEncTile, &mapQKV, &bars->ld_full[s], 0, 2 * H + it.h, 0, it.grp * G);
+            tma_load_4d(dst + 3 * kEncTile, &mapDO, &bars->ld_full[s], 0, it.h, 0, it.grp * G);
+          }
+        }
+        __syncwarp();
         if (++s == kEbStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp >= 9) {
     // Three issuers (one thread issues a tcgen05.mma only every ~70 cycles, the tensor pipe takes a small one every 40):
     // warp 9: S / dP of the next item, then dQ;  warp 10: dK;  warp 11: dV.  Each commits to g_full and ld_empty.
-    if (lane == 0) {
+    {  // whole warp, uniform control flow; one elected lane issues
       const int role = warp - 9;
       const uint32_t id_s = umma_idesc_bf16(128, Geo::NS, 0, 0);  // S, dP: both operands K-major
       const uint32_t id_q = umma_idesc_bf16(128, 32, 0, 1);       // dQ: A K-major, B MN-major
@@ -549,11 +561,14 @@ attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
           const uint32_t tb = tiles0 + uint32_t(st) * 4u * kEncTile;
           const uint64_t dq = d_at(t64, tb), dk = d_at(t64, tb + kEncTile), dv = d_at(t64, tb + 2 * kEncTile),
                          ddo = d_at(t64, tb + 3 * kEncTile);
-          umma_bf16(tmem_base + kEbColS, dq, dk, id_s, 0);
-          umma_bf16(tmem_base + kEbColS, dq + 2, dk + 2, id_s, 1);
-          umma_bf16(tmem_base + kEbColDP, ddo, dv, id_s, 0);
-          umma_bf16(tmem_base + kEbColDP, ddo + 2, dv + 2, id_s, 1);
-          umma_commit(&bars->sd_full[gi]);
+          if (elect_one_sync()) {
+            umma_bf16(tmem_base + kEbColS, dq, dk, id_s, 0);
+            umma_bf16(tmem_base + kEbColS, dq + 2, dk + 2, id_s, 1);
+            umma_bf16(tmem_base + kEbColDP, ddo, dv, id_s, 0);
+            umma_bf16(tmem_base + kEbColDP, ddo + 2, dv + 2, id_s, 1);
+            umma_commit(&bars->sd_full[gi]);
+          }
+          __syncwarp();
         };
         int st_next = 0, ph_next = 0;  // stage / phase of the next item whose S / dP will be issued
         if (my_items > 0) {
@@ -576,14 +591,17 @@ attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
           tc_fence_after();
           {  // dQ = dS . K   (B = K tile as MN-major: +1024 B per 16 keys)
             const uint64_t a0 = d_at(t128k, pds0 + uint32_t(gi) * 2u * kEncPTile + kEncPTile);
-            uint64_t b = d_at(t64, tiles0 + uint32_t(st) * 4u * kEncTile + kEncTile);
+            const uint64_t b0 = d_at(t64, tiles0 + uint32_t(st) * 4u * kEncTile + kEncTile);
             const uint32_t dcol = tmem_base + kEbColG + uint32_t(gi) * 96u;
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int j = 0; j < Geo::KS; ++j, b += 64)
-              umma_bf16(dcol, a0 + uint64_t((uint32_t(j >> 2) * 16384u + uint32_t(j & 3) * 32u) >> 4), b, id_q, j != 0);
+              for (int j = 0; j < Geo::KS; ++j)
+                umma_bf16(dcol, a0 + uint64_t((uint32_t(j >> 2) * 16384u + uint32_t(j & 3) * 32u) >> 4), b0 + uint64_t(64 * j), id_q, j != 0);
+              umma_commit(&bars->g_full[gi]);
+              umma_commit(&bars->ld_empty[st]);
+            }
+            __syncwarp();
           }
-          umma_commit(&bars->g_full[gi]);
-          umma_commit(&bars->ld_empty[st]);
           if (++st == kEbStages) st = 0;
         }
       } else {
@@ -595,12 +613,15 @@ attn_bwd_enc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_con
           tc_fence_after();
           const uint32_t tb = tiles0 + uint32_t(st) * 4u * kEncTile;
           const uint32_t sp = pds0 + uint32_t(gi) * 2u * kEncPTile;
-          uint64_t a = d_at(t128mn, role == 1 ? sp + kEncPTile : sp), b = d_at(t64, role == 1 ? tb : tb + 3 * kEncTile);
+          const uint64_t a = d_at(t128mn, role == 1 ? sp + kEncPTile : sp), b = d_at(t64, role == 1 ? tb : tb + 3 * kEncTile);
           const uint32_t dcol = tmem_base + kEbColG + uint32_t(gi) * 96u + (role == 1 ? 32u : 64u);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int s = 0; s < Geo::KS; ++s, a += 128, b += 64) umma_bf16(dcol, a, b, id_kv, s != 0);
-          umma_commit(&bars->g_full[gi]);
-          umma_commit(&bars->ld_empty[st]);
+            for (int s = 0; s < Geo::KS; ++s) umma_bf16(dcol, a + uint64_t(128 * s), b + uint64_t(64 * s), id_kv, s != 0);
+            umma_commit(&bars->g_full[gi]);
+            umma_commit(&bars->ld_empty[st]);
+          }
+          __syncwarp();
           if (++st == kEbStages) { st = 0; ph ^= 1; }
         }
       }

@@ -25,6 +25,17 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+// Warp index the compiler can prove warp-uniform (threadIdx.x >> 5 is not: it is thread-dependent to the uniformity
+// analysis).  Role dispatch on this value is a uniform branch, so descriptors computed inside stay in uniform registers.
+__device__ __forceinline__ int warp_id_uniform() { return __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0); }
+// One lane of a converged warp.  tcgen05.mma / commit issued as `if (elect_one_sync()) {...}` inside a warp-uniform role
+// branch compile to back-to-back UTCHMMAs; under `if (lane == 0)` every UTCHMMA is wrapped in an ELECT / R2UR.BROADCAST /
+// BRA.U.ANY waterfall plus four R2UR (~70 cycles of the issuing thread per MMA in short bursts; tools/probes/).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x = lo (low 16 bits), .y = hi
