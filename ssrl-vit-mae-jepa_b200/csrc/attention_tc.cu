@@ -192,7 +192,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   TcBars* bars = reinterpret_cast<TcBars*>(smem + TcSmem::bars);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_id_uniform(), lane = threadIdx.x & 31;  // uniform: role branches are warp-uniform control flow
   const int HP = H >> 1, D = H * 32;
   const int nitems = B * HP;
 
@@ -215,24 +215,30 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
   const uint32_t tmem_base = bars->tmem_base;
   pdl_wait();
 
+  // The TMA and tcgen05.mma issuers run their loops with the whole warp (uniform control flow: descriptors and
+  // coordinates stay in uniform registers) and elect one lane per burst; under `if (lane == 0)` the compiler wraps every
+  // UTCHMMA / UTMALDG in an ELECT / R2UR.BROADCAST waterfall (~70 cycles of the issuing thread per MMA, ptx.cuh).
   if (warp == 2) {
-    if (lane == 0) {
+    {
       int k = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++k) {
         const int s = k & 1;
         mbar_wait(&bars->kv_empty[s], ((k >> 1) & 1) ^ 1);
         const int b = item / HP, hp = item % HP;
         uint8_t* dst = smem + TcSmem::qkv + s * 3 * kTcTile;
-        mbar_expect_tx(&bars->kv_full[s], 3 * kTcTile);
-        tma_load_3d(dst, &mapQKV, &bars->kv_full[s], hp * 64, 0, b);
-        tma_load_3d(dst + kTcTile, &mapQKV, &bars->kv_full[s], D + hp * 64, 0, b);
-        tma_load_3d(dst + 2 * kTcTile, &mapQKV, &bars->kv_full[s], 2 * D + hp * 64, 0, b);
+        if (elect_one_sync()) {
+          mbar_expect_tx(&bars->kv_full[s], 3 * kTcTile);
+          tma_load_3d(dst, &mapQKV, &bars->kv_full[s], hp * 64, 0, b);
+          tma_load_3d(dst + kTcTile, &mapQKV, &bars->kv_full[s], D + hp * 64, 0, b);
+          tma_load_3d(dst + 2 * kTcTile, &mapQKV, &bars->kv_full[s], 2 * D + hp * 64, 0, b);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1 || warp == 3) {
     // one tcgen05.mma issuer per query tile (warp 1: tile 0, warp 3: tile 1): their waits do not couple the two softmax
     // pipelines; the TMEM regions are disjoint and the smem operands read-only
-    if (lane == 0) {
+    {
       const int tile = warp == 1 ? 0 : 1;
       const uint32_t idesc_s = umma_idesc_bf16(128, kTcLp, 0, 0);   // S: both operands K-major
       const uint32_t idesc_o = umma_idesc_bf16(128, 32, 0, 1);      // O: A = P K-major, B = V MN-major
@@ -245,20 +251,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
         const uint32_t q = tiles(n) + uint32_t(tile) * 128u * 128u + uint32_t(n & 1) * 64u;
         const uint32_t kk = tiles(n) + kTcTile + uint32_t(n & 1) * 64u;
         const uint32_t d = tmem_base + (tile ? kColS1 : kColS0);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int k16 = 0; k16 < 2; ++k16)
-          umma_bf16(d, umma_sdesc_sw128(q + k16 * 32, 16, 1024), umma_sdesc_sw128(kk + k16 * 32, 16, 1024), idesc_s, k16 != 0);
-        umma_commit(&bars->s_full[tile]);
+          for (int k16 = 0; k16 < 2; ++k16)
+            umma_bf16(d, umma_sdesc_sw128(q + k16 * 32, 16, 1024), umma_sdesc_sw128(kk + k16 * 32, 16, 1024), idesc_s, k16 != 0);
+          umma_commit(&bars->s_full[tile]);
+        }
+        __syncwarp();
       };
-      auto issue_pv = [&](int n) {
+      auto issue_pv = [&](int n, bool last_of_item) {
         const uint32_t v = tiles(n) + 2 * kTcTile + uint32_t(n & 1) * 64u;
         const uint32_t d = tmem_base + (tile ? kColO1 : kColO0) + uint32_t(n & 1) * 32u;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int j = 0; j < kTcLp / 16; ++j)
-          umma_bf16(d, umma_sdesc_sw128(p_s + uint32_t(j >> 2) * box_bytes + uint32_t(j & 3) * 32u, 16, 1024),
-                    umma_sdesc_sw128(v + uint32_t(j) * 2048u, kTcTile, 1024), idesc_o, j != 0);
-        umma_commit(&bars->o_full[tile][n & 1]);
-        umma_commit(&bars->p_free[tile]);
+          for (int j = 0; j < kTcLp / 16; ++j)
+            umma_bf16(d, umma_sdesc_sw128(p_s + uint32_t(j >> 2) * box_bytes + uint32_t(j & 3) * 32u, 16, 1024),
+                      umma_sdesc_sw128(v + uint32_t(j) * 2048u, kTcTile, 1024), idesc_o, j != 0);
+          umma_commit(&bars->o_full[tile][n & 1]);
+          umma_commit(&bars->p_free[tile]);
+          if (last_of_item) umma_commit(&bars->kv_empty[(n >> 1) & 1]);  // this issuer's MMAs on the item's Q / K / V are all in flight
+        }
+        __syncwarp();
       };
       uint32_t ph_sfree = 0, ph_pready = 0, ph_ofree[2] = {0, 0};
       if (nheads > 0) {
@@ -279,8 +292,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
         mbar_wait(&bars->p_ready[tile], ph_pready); ph_pready ^= 1;
         if (n >= 2) { mbar_wait(&bars->o_free[tile][n & 1], ph_ofree[n & 1]); ph_ofree[n & 1] ^= 1; }
         tc_fence_after();
-        issue_pv(n);
-        if (n & 1) umma_commit(&bars->kv_empty[(n >> 1) & 1]);  // this issuer's MMAs on the item's Q / K / V are all in flight
+        issue_pv(n, (n & 1) != 0);
       }
     }
   } else if (warp == 0 || warp >= 4) {
@@ -367,7 +379,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   TcbBars* bars = reinterpret_cast<TcbBars*>(smem + TcbSmem::bars);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_id_uniform(), lane = threadIdx.x & 31;  // uniform: role branches are warp-uniform control flow
   const int D = H * 32;
   const int nitems = B * H;  // work item = (sample, head)
   const int nheads = nitems > int(blockIdx.x) ? (nitems - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x) : 0;
@@ -392,21 +404,24 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
   pdl_wait();
 
   if (warp == 2) {
-    if (lane == 0) {
+    {  // (whole warp + elect.sync: see the forward kernel)
       for (int k = 0; k < nheads; ++k) {
         const int item = int(blockIdx.x) + k * int(gridDim.x);
         const int b = item / H, h = item % H, buf = k & 1;
         uint8_t* dst = smem + TcbSmem::tiles + buf * 4 * TcbSmem::tile;
         mbar_wait(&bars->ld_empty[buf], ((k >> 1) & 1) ^ 1);
-        mbar_expect_tx(&bars->ld_full[buf], 4 * TcbSmem::tile);
-        tma_load_3d(dst, &mapQKV, &bars->ld_full[buf], h * 32, 0, b);
-        tma_load_3d(dst + TcbSmem::tile, &mapDO, &bars->ld_full[buf], h * 32, 0, b);
-        tma_load_3d(dst + 2 * TcbSmem::tile, &mapQKV, &bars->ld_full[buf], D + h * 32, 0, b);
-        tma_load_3d(dst + 3 * TcbSmem::tile, &mapQKV, &bars->ld_full[buf], 2 * D + h * 32, 0, b);
+        if (elect_one_sync()) {
+          mbar_expect_tx(&bars->ld_full[buf], 4 * TcbSmem::tile);
+          tma_load_3d(dst, &mapQKV, &bars->ld_full[buf], h * 32, 0, b);
+          tma_load_3d(dst + TcbSmem::tile, &mapDO, &bars->ld_full[buf], h * 32, 0, b);
+          tma_load_3d(dst + 2 * TcbSmem::tile, &mapQKV, &bars->ld_full[buf], D + h * 32, 0, b);
+          tma_load_3d(dst + 3 * TcbSmem::tile, &mapQKV, &bars->ld_full[buf], 2 * D + h * 32, 0, b);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t id_s = umma_idesc_bf16(128, kTcLp, 0, 0);   // S, dP: both operands K-major
       const uint32_t id_q = umma_idesc_bf16(128, 32, 0, 1);      // dQ: A K-major, B MN-major
       const uint32_t id_kv = umma_idesc_bf16(128, 32, 1, 1);     // dK, dV: both MN-major
@@ -425,38 +440,47 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
         const uint64_t dq_ = d_at(t64k, tb + ro), ddo = d_at(t64k, tb + TcbSmem::tile + ro);
         const uint64_t dk_ = d_at(t64k, tb + 2 * TcbSmem::tile + ko), dv_ = d_at(t64k, tb + 3 * TcbSmem::tile + ko);
         const uint32_t d = tmem_base + kbSD + uint32_t(hf) * 160u;
-        umma_bf16(d, dq_, dk_, id_s80, 0);
-        umma_bf16(d, dq_ + 2, dk_ + 2, id_s80, 1);       // +32 B per K = 16
-        umma_bf16(d + 80, ddo, dv_, id_s80, 0);
-        umma_bf16(d + 80, ddo + 2, dv_ + 2, id_s80, 1);
-        umma_commit(&bars->sd_full[t][hf]);
+        if (elect_one_sync()) {
+          umma_bf16(d, dq_, dk_, id_s80, 0);
+          umma_bf16(d, dq_ + 2, dk_ + 2, id_s80, 1);       // +32 B per K = 16
+          umma_bf16(d + 80, ddo, dv_, id_s80, 0);
+          umma_bf16(d + 80, ddo + 2, dv_ + 2, id_s80, 1);
+          umma_commit(&bars->sd_full[t][hf]);
+        }
+        __syncwarp();
       };
       auto issue_grads = [&](int n, int t, bool last_of_head) {
         const uint32_t tb = tiles0 + uint32_t(n & 1) * 4u * TcbSmem::tile, ro = uint32_t(t) * 8192u;
         const uint32_t box = t ? 4096u : 16384u;
-        // dQ_t = dS_t . K   (B = K tile as MN-major: 32 head dims per 64-byte row, +1024 B per 16 keys)
-        {
-          const uint64_t a0 = d_at(t128k, sds[t]);
-          uint64_t b = d_at(t64k, tb + 2 * TcbSmem::tile);
-#pragma unroll
-          for (int j = 0; j < kTcLp / 16; ++j, b += 64)
-            umma_bf16(tmem_base + kbDQ + uint32_t(t) * 32u, a0 + uint64_t((uint32_t(j >> 2) * box + uint32_t(j & 3) * 32u) >> 4), b, id_q, j != 0);
-        }
-        umma_commit(&bars->dq_full[t]);
-        // dV += P_t^T dO_t,  dK += dS_t^T Q_t   (M = keys: tile m covers keys 128 m ..; K = the query rows of tile t)
         const int ksteps = t ? 2 : 8;
         const uint64_t tmn = umma_sdesc_sw128(0, box, 1024);          // P / dS tiles as MN-major A (LBO = box stride)
+        if (elect_one_sync()) {
+          // dQ_t = dS_t . K   (B = K tile as MN-major: 32 head dims per 64-byte row, +1024 B per 16 keys)
+          {
+            const uint64_t a0 = d_at(t128k, sds[t]);
+            uint64_t b = d_at(t64k, tb + 2 * TcbSmem::tile);
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
-          uint64_t a = d_at(tmn, sp[t] + uint32_t(2 * m) * box), b = d_at(t64k, tb + TcbSmem::tile + ro);
-          for (int s = 0; s < ksteps; ++s, a += 128, b += 64)          // +2048 B / +1024 B per 16 query rows
-            umma_bf16(tmem_base + kbDV + uint32_t(m) * 32u, a, b, id_kv, (t != 0 || s != 0) ? 1u : 0u);
-          a = d_at(tmn, sds[t] + uint32_t(2 * m) * box); b = d_at(t64k, tb + ro);
-          for (int s = 0; s < ksteps; ++s, a += 128, b += 64)
-            umma_bf16(tmem_base + kbDK + uint32_t(m) * 32u, a, b, id_kv, (t != 0 || s != 0) ? 1u : 0u);
+            for (int j = 0; j < kTcLp / 16; ++j, b += 64)
+              umma_bf16(tmem_base + kbDQ + uint32_t(t) * 32u, a0 + uint64_t((uint32_t(j >> 2) * box + uint32_t(j & 3) * 32u) >> 4), b, id_q, j != 0);
+          }
+          umma_commit(&bars->dq_full[t]);
+          // dV += P_t^T dO_t,  dK += dS_t^T Q_t   (M = keys: tile m covers keys 128 m ..; K = the query rows of tile t)
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            uint64_t a = d_at(tmn, sp[t] + uint32_t(2 * m) * box), b = d_at(t64k, tb + TcbSmem::tile + ro);
+            for (int s = 0; s < ksteps; ++s, a += 128, b += 64)          // +2048 B / +1024 B per 16 query rows
+              umma_bf16(tmem_base + kbDV + uint32_t(m) * 32u, a, b, id_kv, (t != 0 || s != 0) ? 1u : 0u);
+            a = d_at(tmn, sds[t] + uint32_t(2 * m) * box); b = d_at(t64k, tb + ro);
+            for (int s = 0; s < ksteps; ++s, a += 128, b += 64)
+              umma_bf16(tmem_base + kbDK + uint32_t(m) * 32u, a, b, id_kv, (t != 0 || s != 0) ? 1u : 0u);
+          }
+          umma_commit(&bars->pds_free[t]);
+          if (last_of_head) {
+            umma_commit(&bars->dkv_full);
+            umma_commit(&bars->ld_empty[n & 1]);
+          }
         }
-        umma_commit(&bars->pds_free[t]);
-        if (last_of_head) umma_commit(&bars->dkv_full);
+        __syncwarp();
       };
       uint32_t ph_sdfree[2][2] = {{0, 0}, {0, 0}}, ph_ready[2] = {0, 0}, ph_dqfree[2] = {0, 0}, ph_dkvfree = 0;
       auto wait_sdfree = [&](int t, int hf) { mbar_wait(&bars->sd_free[t][hf], ph_sdfree[t][hf]); ph_sdfree[t][hf] ^= 1; };
@@ -496,7 +520,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
         if (n > 0) { mbar_wait(&bars->dq_free[1], ph_dqfree[1]); ph_dqfree[1] ^= 1; }
         tc_fence_after();
         issue_grads(n, 1, true);
-        umma_commit(&bars->ld_empty[n & 1]);
       }
     }
   } else if (warp == 0 || warp >= 4) {
