@@ -476,7 +476,7 @@ gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, c
   const int nst = p.nstages;
   uint8_t* ring = smem + p.off_ring;
   GemmSmemHdr* hdr = reinterpret_cast<GemmSmemHdr*>(smem + p.off_hdr);
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_id_uniform();  // (provably warp-uniform: role branches are uniform control flow)
   const int lane = threadIdx.x & 31;
   const int total = p.mtiles * p.nchunks;
 
@@ -503,23 +503,29 @@ gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, c
   const uint32_t tmem_base = hdr->tmem_base;
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
+  // The TMA and MMA warps run their loops with all 32 lanes (warp-uniform control flow keeps descriptors / coordinates in
+  // uniform registers) and elect one lane per burst: under `if (lane == 0)` every UTCHMMA / UTMALDG sits in an
+  // ELECT / R2UR.BROADCAST waterfall and costs the issuing thread ~70 cycles -- more than the tensor pipe needs for N <= 128.
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < total; item += gridDim.x) {
         const int mt = item / p.nchunks, nc = item % p.nchunks;
         for (int kb = 0; kb < p.nkb; ++kb) {
           mbar_wait(&hdr->empty[stage], phase ^ 1);
           uint8_t* sa = ring + stage * stage_bytes;
-          mbar_expect_tx(&hdr->full[stage], stage_bytes);
-          tma_load_2d(sa, &mapA, &hdr->full[stage], kb * BK, mt * BM);
-          tma_load_2d(sa + a_bytes, &mapB, &hdr->full[stage], kb * BK, nc * p.bn);
+          if (elect_one_sync()) {
+            mbar_expect_tx(&hdr->full[stage], stage_bytes);
+            tma_load_2d(sa, &mapA, &hdr->full[stage], kb * BK, mt * BM);
+            tma_load_2d(sa + a_bytes, &mapB, &hdr->full[stage], kb * BK, nc * p.bn);
+          }
+          __syncwarp();
           if (++stage == nst) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = umma_idesc_bf16(BM, p.bn, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t accphase = 0;
@@ -532,17 +538,20 @@ gemm_tn_kernel(const GemmTnParams p, const __grid_constant__ CUtensorMap mapA, c
           tc_fence_after();
           const uint32_t sa = smem_u32(ring + stage * stage_bytes);
           const uint32_t sb = sa + a_bytes;
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // K-major SW128: rows are 128 B, 8-row groups 1024 B apart (SBO); +32 B per K=16 step
-            const uint64_t adesc = umma_sdesc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t bdesc = umma_sdesc_sw128(sb + k * 32, 16, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) {
+              // K-major SW128: rows are 128 B, 8-row groups 1024 B apart (SBO); +32 B per K=16 step
+              const uint64_t adesc = umma_sdesc_sw128(sa + k * 32, 16, 1024);
+              const uint64_t bdesc = umma_sdesc_sw128(sb + k * 32, 16, 1024);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+            }
+            umma_commit(&hdr->empty[stage]);
+            if (kb == p.nkb - 1) umma_commit(&hdr->tfull[acc]);
           }
-          umma_commit(&hdr->empty[stage]);
+          __syncwarp();
           if (++stage == nst) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&hdr->tfull[acc]);
         acc ^= 1; if (acc == 0) accphase ^= 1;
       }
     }
@@ -791,7 +800,7 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
   const int nst = p.nstages;
   GemmSmemHdr* hdr = reinterpret_cast<GemmSmemHdr*>(smem + nst * stage_bytes);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_id_uniform();
   const int lane = threadIdx.x & 31;
   const int pc0 = blockIdx.x * p.pcc;                    // first 128-column P chunk of this CTA
   const int q0 = blockIdx.z * 256;                       // first Q column of this CTA's output tile
@@ -818,23 +827,27 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
   const uint32_t tmem_base = hdr->tmem_base;
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
   if (nmb > 0) {
+    // (TMA / MMA warps: all lanes run the loop, one elected lane issues -- see gemm_tn_kernel)
     if (warp == 0) {
-      if (lane == 0) {
+      {
         int stage = 0; uint32_t phase = 0;
         for (int mb = 0; mb < nmb; ++mb) {
           const int m0 = m_begin + mb * WR;
           mbar_wait(&hdr->empty[stage], phase ^ 1);
           uint8_t* sp = smem + stage * stage_bytes;
-          mbar_expect_tx(&hdr->full[stage], tx_bytes);
-          for (int j = 0; j < npb; ++j)  // columns past Pc are zero-filled by the TMA
-            tma_load_2d(sp + j * box_bytes, &mapP, &hdr->full[stage], pc0 * 128 + j * 64, m0);
-          for (int j = 0; j < nqb; ++j)
-            tma_load_2d(sp + p_bytes + j * box_bytes, &mapQ, &hdr->full[stage], q0 + j * 64, m0);
+          if (elect_one_sync()) {
+            mbar_expect_tx(&hdr->full[stage], tx_bytes);
+            for (int j = 0; j < npb; ++j)  // columns past Pc are zero-filled by the TMA
+              tma_load_2d(sp + j * box_bytes, &mapP, &hdr->full[stage], pc0 * 128 + j * 64, m0);
+            for (int j = 0; j < nqb; ++j)
+              tma_load_2d(sp + p_bytes + j * box_bytes, &mapQ, &hdr->full[stage], q0 + j * 64, m0);
+          }
+          __syncwarp();
           if (++stage == nst) { stage = 0; phase ^= 1; }
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      {
         const uint32_t idesc = umma_idesc_bf16(BM, Qn, 1, 1);
         int stage = 0; uint32_t phase = 0;
         for (int mb = 0; mb < nmb; ++mb) {
@@ -842,20 +855,23 @@ gemm_wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap mapP,
           tc_fence_after();
           const uint32_t sp = smem_u32(smem + stage * stage_bytes);
           const uint32_t sq = sp + p_bytes;
-          for (int c = 0; c < p.pcc; ++c) {
+          if (elect_one_sync()) {
+            for (int c = 0; c < p.pcc; ++c) {
 #pragma unroll
-            for (int k = 0; k < WR / 16; ++k) {
-              // MN-major SW128: 64 MN elements contiguous (128 B) per reduction row; 8-row groups 1024 B apart
-              // (SBO); successive 64-element MN groups one TMA box apart (LBO); +2048 B per K=16 step.
-              const uint64_t adesc = umma_sdesc_sw128(sp + uint32_t(2 * c) * box_bytes + k * 2048, box_bytes, 1024);
-              const uint64_t bdesc = umma_sdesc_sw128(sq + k * 2048, box_bytes, 1024);
-              umma_bf16(tmem_base + uint32_t(c) * 256u, adesc, bdesc, idesc, (mb | k) != 0);
+              for (int k = 0; k < WR / 16; ++k) {
+                // MN-major SW128: 64 MN elements contiguous (128 B) per reduction row; 8-row groups 1024 B apart
+                // (SBO); successive 64-element MN groups one TMA box apart (LBO); +2048 B per K=16 step.
+                const uint64_t adesc = umma_sdesc_sw128(sp + uint32_t(2 * c) * box_bytes + k * 2048, box_bytes, 1024);
+                const uint64_t bdesc = umma_sdesc_sw128(sq + k * 2048, box_bytes, 1024);
+                umma_bf16(tmem_base + uint32_t(c) * 256u, adesc, bdesc, idesc, (mb | k) != 0);
+              }
             }
+            umma_commit(&hdr->empty[stage]);
+            if (mb == nmb - 1) umma_commit(&hdr->tfull[0]);
           }
-          umma_commit(&hdr->empty[stage]);
+          __syncwarp();
           if (++stage == nst) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&hdr->tfull[0]);
       }
     } else {
       const int q = warp & 3;

@@ -86,7 +86,7 @@ mlp_fwd_kernel(const MlpFwdParams p, const __grid_constant__ CUtensorMap mapW1, 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   MlpHdr* hdr = reinterpret_cast<MlpHdr*>(smem + kMlpOffHdr);
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_id_uniform();  // provably warp-uniform: role branches are uniform control flow
   const int lane = threadIdx.x & 31;
   const int D = p.D, NC = p.NC;
 
@@ -124,8 +124,9 @@ mlp_fwd_kernel(const MlpFwdParams p, const __grid_constant__ CUtensorMap mapW1, 
   const uint32_t a_s = smem_u32(smem + kMlpOffA), h_s = smem_u32(smem + kMlpOffH), g_s = smem_u32(smem + kMlpOffG);
   const uint32_t ring_s = smem_u32(smem + kMlpOffRing);
 
+  // (TMA / MMA warps: all lanes run the loops, one elected lane issues -- no ELECT / R2UR waterfall per UTCHMMA, see ptx.cuh)
   if (warp == 0) {
-    if (lane == 0) {
+    {
       int stage = 0; uint32_t phase = 0;
       const uint32_t w1_bytes = uint32_t(p.nkb) * 8192u, w2_bytes = uint32_t(D) * 128u;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -134,22 +135,28 @@ mlp_fwd_kernel(const MlpFwdParams p, const __grid_constant__ CUtensorMap mapW1, 
           if (c >= 0) {  // W2 columns [64c, +64): one box of [D rows x 64 k]
             mbar_wait(&hdr->w_empty[stage], phase ^ 1);
             uint8_t* dst = smem + kMlpOffRing + stage * kMlpStageBytes;
-            mbar_expect_tx(&hdr->w_full[stage], w2_bytes);
-            tma_load_2d(dst, &mapW2, &hdr->w_full[stage], c * kMlpHC, 0);
+            if (elect_one_sync()) {
+              mbar_expect_tx(&hdr->w_full[stage], w2_bytes);
+              tma_load_2d(dst, &mapW2, &hdr->w_full[stage], c * kMlpHC, 0);
+            }
+            __syncwarp();
             if (++stage == kMlpStages) { stage = 0; phase ^= 1; }
           }
           if (c + 4 < NC) {  // W1 rows [64(c+4), +64): nkb boxes of [64 rows x 64 k]; k >= D is zero-filled
             mbar_wait(&hdr->w_empty[stage], phase ^ 1);
             uint8_t* dst = smem + kMlpOffRing + stage * kMlpStageBytes;
-            mbar_expect_tx(&hdr->w_full[stage], w1_bytes);
-            for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(dst + kb * 8192, &mapW1, &hdr->w_full[stage], kb * BK, (c + 4) * kMlpHC);
+            if (elect_one_sync()) {
+              mbar_expect_tx(&hdr->w_full[stage], w1_bytes);
+              for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(dst + kb * 8192, &mapW1, &hdr->w_full[stage], kb * BK, (c + 4) * kMlpHC);
+            }
+            __syncwarp();
             if (++stage == kMlpStages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc1 = umma_idesc_bf16(BM, kMlpHC, 0, 0), idesc2 = umma_idesc_bf16(BM, D, 0, 0);
       const int ks1 = D >> 4;
       int stage = 0; uint32_t phase = 0;
@@ -171,14 +178,18 @@ mlp_fwd_kernel(const MlpFwdParams p, const __grid_constant__ CUtensorMap mapW1, 
             mbar_wait(&hdr->w_full[stage], phase);
             tc_fence_after();
             const uint32_t sb = ring_s + stage * kMlpStageBytes;
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int k = 0; k < kMlpHC / 16; ++k) {
-              const uint64_t adesc = umma_sdesc_sw128(h_s + hb * 16384 + k * 32, 16, 1024);
-              const uint64_t bdesc = umma_sdesc_sw128(sb + k * 32, 16, 1024);
-              umma_bf16(tmem_base, adesc, bdesc, idesc2, (c > 0 || k != 0) ? 1u : 0u);
+              for (int k = 0; k < kMlpHC / 16; ++k) {
+                const uint64_t adesc = umma_sdesc_sw128(h_s + hb * 16384 + k * 32, 16, 1024);
+                const uint64_t bdesc = umma_sdesc_sw128(sb + k * 32, 16, 1024);
+                umma_bf16(tmem_base, adesc, bdesc, idesc2, (c > 0 || k != 0) ? 1u : 0u);
+              }
+              umma_commit(&hdr->w_empty[stage]);
+              umma_commit(&hdr->h_free[hb]);
+              if (c == NC - 1) umma_commit(&hdr->out_full);
             }
-            umma_commit(&hdr->w_empty[stage]);
-            umma_commit(&hdr->h_free[hb]);
+            __syncwarp();
             if (++stage == kMlpStages) { stage = 0; phase ^= 1; }
           }
           if (c + 4 < NC) {  // fc1 chunk c+4: pre[pb] = A[128 x D] * W1[64 x D]^T
@@ -188,19 +199,21 @@ mlp_fwd_kernel(const MlpFwdParams p, const __grid_constant__ CUtensorMap mapW1, 
             tc_fence_after();
             const uint32_t sb = ring_s + stage * kMlpStageBytes;
             const uint32_t d_tmem = tmem_base + kMlpTmemPre + pb * kMlpHC;
-            for (int ks = 0; ks < ks1; ++ks) {
-              const int kb = ks >> 2, k = ks & 3;
-              const uint64_t adesc = umma_sdesc_sw128(a_s + kb * 16384 + k * 32, 16, 1024);
-              const uint64_t bdesc = umma_sdesc_sw128(sb + kb * 8192 + k * 32, 16, 1024);
-              umma_bf16(d_tmem, adesc, bdesc, idesc1, ks != 0);
+            if (elect_one_sync()) {
+              for (int ks = 0; ks < ks1; ++ks) {
+                const int kb = ks >> 2, k = ks & 3;
+                const uint64_t adesc = umma_sdesc_sw128(a_s + kb * 16384 + k * 32, 16, 1024);
+                const uint64_t bdesc = umma_sdesc_sw128(sb + kb * 8192 + k * 32, 16, 1024);
+                umma_bf16(d_tmem, adesc, bdesc, idesc1, ks != 0);
+              }
+              umma_commit(&hdr->w_empty[stage]);
+              umma_commit(&hdr->pre_full[pb]);
             }
-            umma_commit(&hdr->w_empty[stage]);
-            umma_commit(&hdr->pre_full[pb]);
+            __syncwarp();
             if (++stage == kMlpStages) { stage = 0; phase ^= 1; }
             if (t == 1 && c >= 0) MLP_TS(2, 3 + 2 * c);
           }
         }
-        umma_commit(&hdr->out_full);
         if (t == 1) MLP_TS(2, 40);
         g0 += uint32_t(NC);
       }

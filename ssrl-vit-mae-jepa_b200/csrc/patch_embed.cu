@@ -44,7 +44,7 @@ patch_embed_kernel(const PeParams p, const __grid_constant__ CUtensorMap mapW) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   PeHdr* hdr = reinterpret_cast<PeHdr*>(smem + p.off_hdr);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const int D = p.D, nkb = p.nkb;
   const uint32_t w_box = uint32_t(D) * 128u, a_buf = uint32_t(nkb) * 16384u;
 
@@ -73,7 +73,7 @@ patch_embed_kernel(const PeParams p, const __grid_constant__ CUtensorMap mapW) {
       for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smem + kb * w_box, &mapW, &hdr->w_full, kb * BK, 0);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // all lanes run the loop, one elected lane issues (no ELECT / R2UR waterfall per UTCHMMA, see ptx.cuh)
       const uint32_t idesc = umma_idesc_bf16(BM, D, 0, 0);
       const int ks_n = p.pd >> 4;
       mbar_wait(&hdr->w_full, 0);
@@ -84,14 +84,17 @@ patch_embed_kernel(const PeParams p, const __grid_constant__ CUtensorMap mapW) {
         mbar_wait(&hdr->a_ready[b], ph);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + b * 256u;
-        for (int ks = 0; ks < ks_n; ++ks) {
-          const int kb = ks >> 2, k = ks & 3;
-          const uint64_t adesc = umma_sdesc_sw128(a_s + b * a_buf + kb * 16384 + k * 32, 16, 1024);
-          const uint64_t bdesc = umma_sdesc_sw128(w_s + kb * w_box + k * 32, 16, 1024);
-          umma_bf16(d_tmem, adesc, bdesc, idesc, ks != 0);
+        if (elect_one_sync()) {
+          for (int ks = 0; ks < ks_n; ++ks) {
+            const int kb = ks >> 2, k = ks & 3;
+            const uint64_t adesc = umma_sdesc_sw128(a_s + b * a_buf + kb * 16384 + k * 32, 16, 1024);
+            const uint64_t bdesc = umma_sdesc_sw128(w_s + kb * w_box + k * 32, 16, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, ks != 0);
+          }
+          umma_commit(&hdr->a_free[b]);
+          umma_commit(&hdr->acc_full[b]);
         }
-        umma_commit(&hdr->a_free[b]);
-        umma_commit(&hdr->acc_full[b]);
+        __syncwarp();
       }
     }
   } else {
