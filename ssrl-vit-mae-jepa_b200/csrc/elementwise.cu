@@ -160,9 +160,20 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const __nv_bfloat1
   }
 }
 
+// sum over the LPR-lane group of the calling lane (LPR = 32: the warp)
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // ---------------------------------------------------------------------------------------------
-// LayerNorm forward / backward: one warp per row, D <= 128*NV, D % 4 == 0; lane owns the float4 column groups
-// {128*j + 4*lane}, j < NV (NV = 2 covers configs/mae.yaml: D = 144 / 192; NV = 4 / 8 cover D <= 512 / 1024).
+// LayerNorm forward / backward: LPR lanes per row (32: one warp per row; 16: two rows per warp), D <= 4*LPR*NV,
+// D % 4 == 0; a lane owns the float4 column groups {4*LPR*j + 4*sub}, j < NV, sub = lane % LPR.  With one warp per row
+// D = 144 / 192 (configs/mae.yaml) fill 36 / 48 of the 64 float4 slots of two passes (the second pass is a 64- / 256-byte
+// request per row); 16 lanes per row and NV = 3 fill 36 / 48 of 48 (D = 192: every lane busy in every pass).
+// NV = 4 / 8 with LPR = 32 cover D <= 512 / 1024.
 // ROWS rows are processed per warp iteration with all their loads issued before the first reduction (these
 // kernels are pure HBM streams, so bytes in flight per warp is what matters).
 // ---------------------------------------------------------------------------------------------
@@ -174,7 +185,7 @@ __device__ __forceinline__ long long map_row(long long r, const int64_t* gather_
 
 // ADD: the normalised row is x[map(r)] + delta[r] (delta bf16, compact rows: a Linear output that has not been added to
 // the residual stream yet); the sum is also written to x_out[r] (fp32, compact) for the backward.
-template <int NV, int ROWS, bool GATHER, bool ADD = false>
+template <int NV, int ROWS, bool GATHER, bool ADD = false, int LPR = 32>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x,
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta,
@@ -186,13 +197,13 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                            float* __restrict__ x_out) {
   pdl_trigger();
   pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
+  const int lane = threadIdx.x & (LPR - 1);  // position inside the row's lane group
+  const int wpb = blockDim.x / LPR;          // rows in flight per block and pass
   float4 gm[NV], bt[NV];
   bool has[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    const int c = 128 * j + 4 * lane;
+    const int c = 4 * LPR * j + 4 * lane;
     has[j] = c < D;
     gm[j] = bt[j] = make_float4(0, 0, 0, 0);
     if (has[j]) { gm[j] = *reinterpret_cast<const float4*>(gamma + c); bt[j] = *reinterpret_cast<const float4*>(beta + c); }
@@ -202,13 +213,16 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   // source rows of the NEXT iteration (the index load of a gathered norm is fetched one iteration ahead, so that it is
   // not a dependent round trip in front of every row load)
   long long xr_next[ROWS];
-  const long long ra0 = (long long)blockIdx.x * wpb + (threadIdx.x >> 5);
+  const long long ra0 = (long long)blockIdx.x * wpb + (threadIdx.x / LPR);
+  // two rows per warp (LPR = 16): the row loop must stay warp-uniform (full-mask shuffles inside), so it runs while the
+  // warp's FIRST row exists; a missing second row is processed as a duplicate of the first and not stored
+  const int gsel = int(threadIdx.x / LPR) % (32 / LPR);
 #pragma unroll
   for (int k = 0; k < ROWS; ++k) {
     const long long r = ra0 + k * stride;
-    xr_next[k] = (GATHER && ra0 < rows) ? map_row(r < rows ? r : ra0, gather_idx, n_sel, L_src) : 0;
+    xr_next[k] = (GATHER && ra0 - gsel < rows) ? map_row(r < rows ? r : ra0 - gsel, gather_idx, n_sel, L_src) : 0;
   }
-  for (long long ra = ra0; ra < rows; ra += ROWS * stride) {
+  for (long long ra = ra0; ra - gsel < rows; ra += ROWS * stride) {
     float4 v[ROWS][NV];
     uint2 dl[ROWS][NV];
     long long rr[ROWS];
@@ -217,15 +231,15 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
     for (int k = 0; k < ROWS; ++k) {
       rr[k] = ra + k * stride;
       ok[k] = rr[k] < rows;
-      if (!ok[k]) rr[k] = ra;
+      if (!ok[k]) rr[k] = ra - gsel;
       const float* src = x + (GATHER ? xr_next[k] : rr[k]) * D;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         v[k][j] = make_float4(0, 0, 0, 0);
         dl[k][j] = make_uint2(0u, 0u);
         if (has[j]) {
-          v[k][j] = *reinterpret_cast<const float4*>(src + 128 * j + 4 * lane);
-          if (ADD) dl[k][j] = *reinterpret_cast<const uint2*>(delta + rr[k] * D + 128 * j + 4 * lane);
+          v[k][j] = *reinterpret_cast<const float4*>(src + 4 * LPR * j + 4 * lane);
+          if (ADD) dl[k][j] = *reinterpret_cast<const uint2*>(delta + rr[k] * D + 4 * LPR * j + 4 * lane);
         }
       }
     }
@@ -236,16 +250,16 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
         for (int j = 0; j < NV; ++j) {
           v[k][j].x += bf16_lo(dl[k][j].x); v[k][j].y += bf16_hi(dl[k][j].x);
           v[k][j].z += bf16_lo(dl[k][j].y); v[k][j].w += bf16_hi(dl[k][j].y);
-          if (has[j] && ok[k]) *reinterpret_cast<float4*>(x_out + rr[k] * D + 128 * j + 4 * lane) = v[k][j];
+          if (has[j] && ok[k]) *reinterpret_cast<float4*>(x_out + rr[k] * D + 4 * LPR * j + 4 * lane) = v[k][j];
         }
     }
     if (GATHER) {
       const long long rn = ra + ROWS * stride;
-      if (rn < rows) {
+      if (rn - gsel < rows) {
 #pragma unroll
         for (int k = 0; k < ROWS; ++k) {
           const long long r = rn + k * stride;
-          xr_next[k] = map_row(r < rows ? r : rn, gather_idx, n_sel, L_src);
+          xr_next[k] = map_row(r < rows ? r : rn - gsel, gather_idx, n_sel, L_src);
         }
       }
     }
@@ -254,7 +268,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
       float sum = 0.f;
 #pragma unroll
       for (int j = 0; j < NV; ++j) sum += v[k][j].x + v[k][j].y + v[k][j].z + v[k][j].w;
-      const float mu = warp_sum(sum) * invD;
+      const float mu = group_sum<LPR>(sum) * invD;
       float sq = 0.f;
 #pragma unroll
       for (int j = 0; j < NV; ++j)
@@ -262,7 +276,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
           const float a = v[k][j].x - mu, b = v[k][j].y - mu, c = v[k][j].z - mu, d = v[k][j].w - mu;
           sq += a * a + b * b + c * c + d * d;
         }
-      const float rs = rsqrtf(warp_sum(sq) * invD + eps);
+      const float rs = rsqrtf(group_sum<LPR>(sq) * invD + eps);
       if (!ok[k]) continue;
       const long long r = rr[k];
       __nv_bfloat16* dst = xn + r * D;
@@ -272,7 +286,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
           uint2 o;
           o.x = pack_bf16x2((v[k][j].x - mu) * rs * gm[j].x + bt[j].x, (v[k][j].y - mu) * rs * gm[j].y + bt[j].y);
           o.y = pack_bf16x2((v[k][j].z - mu) * rs * gm[j].z + bt[j].z, (v[k][j].w - mu) * rs * gm[j].w + bt[j].w);
-          *reinterpret_cast<uint2*>(dst + 128 * j + 4 * lane) = o;
+          *reinterpret_cast<uint2*>(dst + 4 * LPR * j + 4 * lane) = o;
         }
       if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
     }
@@ -281,7 +295,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 
 // DINC: dx_in is indexed by the compact row r (like g), not by the mapped row (the residual gradient of a gathered
 // sub-stream: the masked-rows-only tail of the last decoder block).
-template <int NV, int ROWS, int MINB, bool GATHER, bool DINC = false>
+template <int NV, int ROWS, int MINB, bool GATHER, bool DINC = false, int LPR = 32>
 __global__ void __launch_bounds__(256, MINB) layernorm_bwd_kernel(
     const __nv_bfloat16* __restrict__ g, const float* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dx_in,
@@ -290,8 +304,8 @@ __global__ void __launch_bounds__(256, MINB) layernorm_bwd_kernel(
   pdl_trigger();
   pdl_wait();
   __shared__ float s_dg[128 * NV], s_db[128 * NV];
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
+  const int lane = threadIdx.x & (LPR - 1);  // position inside the row's lane group
+  const int wpb = blockDim.x / LPR;          // rows in flight per block and pass
   for (int i = threadIdx.x; i < 128 * NV; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
   __syncthreads();
   float4 wv[NV];
@@ -299,7 +313,7 @@ __global__ void __launch_bounds__(256, MINB) layernorm_bwd_kernel(
   float dg[NV][4], db[NV][4];
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    const int c = 128 * j + 4 * lane;
+    const int c = 4 * LPR * j + 4 * lane;
     has[j] = c < D;
     wv[j] = make_float4(0, 0, 0, 0);
     if (has[j]) wv[j] = *reinterpret_cast<const float4*>(gamma + c);
@@ -309,13 +323,16 @@ __global__ void __launch_bounds__(256, MINB) layernorm_bwd_kernel(
   const float invD = 1.0f / D;
   const long long stride = (long long)gridDim.x * wpb;
   long long xr_next[ROWS];  // see layernorm_fwd_kernel
-  const long long ra0 = (long long)blockIdx.x * wpb + (threadIdx.x >> 5);
+  const long long ra0 = (long long)blockIdx.x * wpb + (threadIdx.x / LPR);
+  // two rows per warp (LPR = 16): the row loop must stay warp-uniform (full-mask shuffles inside), so it runs while the
+  // warp's FIRST row exists; a missing second row is processed as a duplicate of the first and not stored
+  const int gsel = int(threadIdx.x / LPR) % (32 / LPR);
 #pragma unroll
   for (int k = 0; k < ROWS; ++k) {
     const long long r = ra0 + k * stride;
-    xr_next[k] = (GATHER && ra0 < rows) ? map_row(r < rows ? r : ra0, gather_idx, n_sel, L_src) : 0;
+    xr_next[k] = (GATHER && ra0 - gsel < rows) ? map_row(r < rows ? r : ra0 - gsel, gather_idx, n_sel, L_src) : 0;
   }
-  for (long long ra = ra0; ra < rows; ra += ROWS * stride) {
+  for (long long ra = ra0; ra - gsel < rows; ra += ROWS * stride) {
     long long rrow[ROWS], xr[ROWS];
     bool ok[ROWS];
     uint2 gg[ROWS][NV];
@@ -325,12 +342,12 @@ __global__ void __launch_bounds__(256, MINB) layernorm_bwd_kernel(
     for (int k = 0; k < ROWS; ++k) {
       rrow[k] = ra + k * stride;
       ok[k] = rrow[k] < rows;
-      if (!ok[k]) rrow[k] = ra;
+      if (!ok[k]) rrow[k] = ra - gsel;
       xr[k] = GATHER ? xr_next[k] : rrow[k];
       mu[k] = mean[rrow[k]]; rs[k] = rstd[rrow[k]];
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        const int c = 128 * j + 4 * lane;
+        const int c = 4 * LPR * j + 4 * lane;
         gg[k][j] = make_uint2(0, 0);
         xv[k][j] = di[k][j] = make_float4(0, 0, 0, 0);
         if (has[j]) {
@@ -342,11 +359,11 @@ __global__ void __launch_bounds__(256, MINB) layernorm_bwd_kernel(
     }
     if (GATHER) {
       const long long rn = ra + ROWS * stride;
-      if (rn < rows) {
+      if (rn - gsel < rows) {
 #pragma unroll
         for (int k = 0; k < ROWS; ++k) {
           const long long r = rn + k * stride;
-          xr_next[k] = map_row(r < rows ? r : rn, gather_idx, n_sel, L_src);
+          xr_next[k] = map_row(r < rows ? r : rn - gsel, gather_idx, n_sel, L_src);
         }
       }
     }
@@ -370,13 +387,13 @@ __global__ void __launch_bounds__(256, MINB) layernorm_bwd_kernel(
           s2 += dxh[j][e] * xh[j][e];
         }
       }
-      s1 = warp_sum(s1) * invD;
-      s2 = warp_sum(s2) * invD;
+      s1 = group_sum<LPR>(s1) * invD;
+      s2 = group_sum<LPR>(s2) * invD;
       if (!ok[k]) continue;
 #pragma unroll
       for (int j = 0; j < NV; ++j)
         if (has[j]) {
-          const int c = 128 * j + 4 * lane;
+          const int c = 4 * LPR * j + 4 * lane;
           float4 o;
           o.x = rs[k] * (dxh[j][0] - s1 - xh[j][0] * s2) + di[k][j].x;
           o.y = rs[k] * (dxh[j][1] - s1 - xh[j][1] * s2) + di[k][j].y;
@@ -393,8 +410,8 @@ __global__ void __launch_bounds__(256, MINB) layernorm_bwd_kernel(
     if (has[j]) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        atomicAdd(&s_dg[128 * j + 4 * lane + e], dg[j][e]);
-        atomicAdd(&s_db[128 * j + 4 * lane + e], db[j][e]);
+        atomicAdd(&s_dg[4 * LPR * j + 4 * lane + e], dg[j][e]);
+        atomicAdd(&s_db[4 * LPR * j + 4 * lane + e], db[j][e]);
       }
     }
   __syncthreads();
@@ -968,6 +985,12 @@ extern "C" int mae_assemble_tokens(const void* tok, const float* cls, const floa
   return MAE_CHECK_LAUNCH();
 }
 
+// A/B switch: MAE_LN_LPR=32 keeps one warp per row for D <= 192
+static bool ln_half_warp_rows() {
+  static const bool v = !(getenv("MAE_LN_LPR") && atoi(getenv("MAE_LN_LPR")) == 32);
+  return v;
+}
+
 extern "C" int mae_layernorm_fwd(const float* x, const float* gamma, const float* beta, const int64_t* gather_idx,
                                  int n_sel, int L_src, int rows, int D, float eps, void* xn, float* mean, float* rstd,
                                  cudaStream_t stream) {
@@ -977,7 +1000,11 @@ extern "C" int mae_layernorm_fwd(const float* x, const float* gamma, const float
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(xn);
   static const int bps = getenv("MAE_LN_FWD_BPS") ? atoi(getenv("MAE_LN_FWD_BPS")) : 16;
   const dim3 grid(grid_for(rows, 8, 148 * bps)), block(256);
-  if (D <= 256) {
+  if (D <= 192 && ln_half_warp_rows()) {  // 16 lanes per row, two rows per warp (see the kernel comment)
+    const dim3 grid2(grid_for(rows, 16, 148 * bps));
+    if (gather_idx) mae_launch(layernorm_fwd_kernel<3, 2, true, false, 16>, grid2, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd, (const __nv_bfloat16*)nullptr, (float*)nullptr);
+    else mae_launch(layernorm_fwd_kernel<3, 2, false, false, 16>, grid2, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd, (const __nv_bfloat16*)nullptr, (float*)nullptr);
+  } else if (D <= 256) {
     if (gather_idx) mae_launch(layernorm_fwd_kernel<2, 2, true>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd, (const __nv_bfloat16*)nullptr, (float*)nullptr);
     else mae_launch(layernorm_fwd_kernel<2, 2, false>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd, (const __nv_bfloat16*)nullptr, (float*)nullptr);
   } else if (D <= 512) {
@@ -999,7 +1026,11 @@ extern "C" int mae_layernorm_fwd_add(const float* x, const void* delta, const fl
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(xn);
   const __nv_bfloat16* dl = reinterpret_cast<const __nv_bfloat16*>(delta);
   const dim3 grid(grid_for(rows, 8, 148 * 16)), block(256);
-  if (gather_idx) mae_launch(layernorm_fwd_kernel<2, 2, true, true>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd, dl, x_out);
+  if (D <= 192 && ln_half_warp_rows()) {
+    const dim3 grid2(grid_for(rows, 16, 148 * 16));
+    if (gather_idx) mae_launch(layernorm_fwd_kernel<3, 2, true, true, 16>, grid2, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd, dl, x_out);
+    else mae_launch(layernorm_fwd_kernel<3, 2, false, true, 16>, grid2, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd, dl, x_out);
+  } else if (gather_idx) mae_launch(layernorm_fwd_kernel<2, 2, true, true>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd, dl, x_out);
   else mae_launch(layernorm_fwd_kernel<2, 2, false, true>, grid, block, 0, stream, x, gamma, beta, gather_idx, n_sel, L_src, rows, D, eps, o, mean, rstd, dl, x_out);
   return MAE_CHECK_LAUNCH();
 }
@@ -1014,7 +1045,10 @@ extern "C" int mae_layernorm_bwd_scatter(const void* g, const float* x, const fl
   const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(g);
   __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(dx_out_bf16);
   const dim3 grid(grid_for(rows, 8, 148 * 6)), block(256);
-  mae_launch(layernorm_bwd_kernel<2, 2, 3, true, true>, grid, block, 0, stream, gp, x, mean, rstd, gamma, dx_in_compact, gather_idx, n_sel, L_src, rows, D, dx_out, ob, dgamma, dbeta);
+  if (D <= 192 && ln_half_warp_rows())
+    mae_launch(layernorm_bwd_kernel<3, 1, 2, true, true, 16>, dim3(grid_for(rows, 16, 148 * 2)), block, 0, stream, gp, x, mean, rstd, gamma, dx_in_compact, gather_idx, n_sel, L_src, rows, D, dx_out, ob, dgamma, dbeta);
+  else
+    mae_launch(layernorm_bwd_kernel<2, 2, 3, true, true>, grid, block, 0, stream, gp, x, mean, rstd, gamma, dx_in_compact, gather_idx, n_sel, L_src, rows, D, dx_out, ob, dgamma, dbeta);
   return MAE_CHECK_LAUNCH();
 }
 
@@ -1027,9 +1061,16 @@ extern "C" int mae_layernorm_bwd(const void* g, const float* x, const float* mea
   if (D > 1024 || (D % 4) || (gather_idx && (n_sel <= 0 || L_src <= 0))) return MAE_ERR_SHAPE;
   const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(g);
   __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(dx_out_bf16);
-  static const int bps = getenv("MAE_LN_BWD_BPS") ? atoi(getenv("MAE_LN_BWD_BPS")) : 6;  // 3 resident CTAs per SM: two full waves
+  static const int bps_env = getenv("MAE_LN_BWD_BPS") ? atoi(getenv("MAE_LN_BWD_BPS")) : 0;
+  const int bps = bps_env ? bps_env : 6;  // 3 resident CTAs per SM: two full waves
   const dim3 grid(grid_for(rows, 8, 148 * bps)), block(256);
-  if (D <= 256) {
+  if (D <= 192 && ln_half_warp_rows()) {
+    // 2 resident CTAs per SM, one wave: measured best (D = 192: 137 us = 0.99 of the copy bandwidth; more CTAs only add
+    // d-gamma / d-beta atomics on the same 2 D addresses)
+    const dim3 grid2(grid_for(rows, 16, 148 * (bps_env ? bps_env : 2)));
+    if (gather_idx) mae_launch(layernorm_bwd_kernel<3, 1, 2, true, false, 16>, grid2, block, 0, stream, gp, x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out, ob, dgamma, dbeta);
+    else mae_launch(layernorm_bwd_kernel<3, 1, 2, false, false, 16>, grid2, block, 0, stream, gp, x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out, ob, dgamma, dbeta);
+  } else if (D <= 256) {
     if (gather_idx) mae_launch(layernorm_bwd_kernel<2, 2, 3, true>, grid, block, 0, stream, gp, x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out, ob, dgamma, dbeta);
     else mae_launch(layernorm_bwd_kernel<2, 2, 3, false>, grid, block, 0, stream, gp, x, mean, rstd, gamma, dx_in, gather_idx, n_sel, L_src, rows, D, dx_out, ob, dgamma, dbeta);
   } else if (D <= 512) {
