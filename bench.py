@@ -171,7 +171,7 @@ def algorithmic_cost(name, a):
     if name == "mae_attention_fwd":
         B, L, H, hd = a[1], a[2], a[3], a[4]
         return B * L * H * hd * 2.0 * 4 + B * H * L * 4.0, 4.0 * B * H * L * L * hd, f"B={B} L={L} H={H} hd={hd}"
-    if name == "mae_attention_bwd":
+    if name in ("mae_attention_bwd", "mae_attention_bwd_ws"):
         B, L, H, hd = a[4], a[5], a[6], a[7]
         return B * L * H * hd * 2.0 * 8 + B * H * L * 4.0, 10.0 * B * H * L * L * hd, f"B={B} L={L} H={H} hd={hd}"
     if name == "mae_layernorm_fwd":

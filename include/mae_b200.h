@@ -133,6 +133,11 @@ int mae_attention_fwd(const void* qkv_bf16, int B, int L, int H, int hd, void* o
                       mae_stream_t stream);
 int mae_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse, int B,
                       int L, int H, int hd, void* dqkv_bf16, mae_stream_t stream);
+/* Same op with a caller-provided scratch buffer (>= B*L*H*4 bytes, 16-byte aligned): kernels that want
+ * delta = rowsum(dout o out) per (token, head) compute it there with a coalesced pre-pass instead of per-thread row
+ * gathers inside the attention kernel (decoder-sized tcgen05 backward: ~0.9x the time).  ws may be NULL. */
+int mae_attention_bwd_ws(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse, int B,
+                         int L, int H, int hd, void* dqkv_bf16, void* ws, long long ws_bytes, mae_stream_t stream);
 
 /* repeat_token(mask_token) + set_at_index(idx_keep, embed) + decoder_pos_embed add (reference
  * src/models/mae.py:61-69 and MAEDecoderTIMM.decode's pos add): x_dec (B,L,D) f32. */

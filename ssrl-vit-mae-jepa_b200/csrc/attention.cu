@@ -469,16 +469,29 @@ extern "C" int mae_attention_fwd(const void* qkv, int B, int L, int H, int hd, v
   MAE_ATTN_DISPATCH(launch_fwd, qkv, B, L, H, out, lse, stream)
 }
 
-extern "C" int mae_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int B, int L,
-                                 int H, int hd, void* dqkv, cudaStream_t stream) {
+static int attention_bwd_impl(const void* qkv, const void* out, const void* dout, const float* lse, int B, int L, int H, int hd,
+                              void* dqkv, float* delta_ws, cudaStream_t stream) {
   if (B <= 0) return MAE_OK;
   if (!qkv || !out || !dout || !lse || !dqkv) return MAE_ERR_NULL;
   const int nt = pick_nt(L);
   if (!nt || L < 1 || H < 1) return MAE_ERR_SHAPE;
   {
     static const bool no_tc = getenv("MAE_ATTN_NO_TC") != nullptr || getenv("MAE_ATTN_NO_TC_BWD") != nullptr;
-    if (!no_tc && hd == 32 && L > 128 && L <= 160 && (H % 2) == 0) return attn_bwd_tc(qkv, out, dout, lse, B, L, H, dqkv, stream);
+    static const bool no_delta = getenv("MAE_ATTN_NO_DELTA_PREPASS") != nullptr;  // A/B switch
+    if (!no_tc && hd == 32 && L > 128 && L <= 160 && (H % 2) == 0)
+      return attn_bwd_tc(qkv, out, dout, lse, B, L, H, dqkv, no_delta ? nullptr : delta_ws, stream);
     if (!no_tc && attn_enc_covers(L, hd)) return attn_bwd_enc(qkv, out, dout, lse, B, L, H, hd, dqkv, stream);
   }
   MAE_ATTN_DISPATCH(launch_bwd, qkv, out, dout, lse, B, L, H, dqkv, stream)
+}
+
+extern "C" int mae_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int B, int L,
+                                 int H, int hd, void* dqkv, cudaStream_t stream) {
+  return attention_bwd_impl(qkv, out, dout, lse, B, L, H, hd, dqkv, nullptr, stream);
+}
+
+extern "C" int mae_attention_bwd_ws(const void* qkv, const void* out, const void* dout, const float* lse, int B, int L,
+                                    int H, int hd, void* dqkv, void* ws, long long ws_bytes, cudaStream_t stream) {
+  float* delta = (ws && ws_bytes >= (long long)B * L * H * 4 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) ? reinterpret_cast<float*>(ws) : nullptr;
+  return attention_bwd_impl(qkv, out, dout, lse, B, L, H, hd, dqkv, delta, stream);
 }

@@ -371,10 +371,15 @@ __device__ __forceinline__ void store_row32(__nv_bfloat16* dst, const uint32_t (
   }
 }
 
+// delta = rowsum(dO o O): DELTA = true reads it from `delta` (B, L, H) f32, written by attn_delta_kernel right before
+// this launch (coalesced pre-pass); DELTA = false gathers the O and dO row segments per thread (64-byte pieces, 32 live
+// registers, on the softmax warps' critical path: ~70 us of the launch).
+template <bool DELTA>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ CUtensorMap mapDO,
                    const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
-                   const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, int B, int L, int H, float scale) {
+                   const float* __restrict__ lse, const float* __restrict__ delta_in, __nv_bfloat16* __restrict__ dqkv,
+                   int B, int L, int H, float scale) {
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -536,29 +541,37 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
     // per-row constants of head m: log-sum-exp (in log2 units) and delta = sum_d dO o O, straight from global memory, one
     // head ahead (rows >= L: lse = +inf makes P and dS vanish).  issue (loads only) and finish (arithmetic) are separate
     // so that the loads of head n + 1 stay in flight across the epilogue waits of head n.
-    uint4 rc_o[4], rc_d[4];
-    float rc_l = INFINITY;
+    uint4 rc_o[DELTA ? 1 : 4], rc_d[DELTA ? 1 : 4];
+    float rc_l = INFINITY, rc_delta = 0.f;
     auto row_consts_issue = [&](int m) {
-      rc_l = INFINITY;
+      rc_l = INFINITY; rc_delta = 0.f;
+      if constexpr (!DELTA) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { rc_o[k] = make_uint4(0, 0, 0, 0); rc_d[k] = make_uint4(0, 0, 0, 0); }
+        for (int k = 0; k < 4; ++k) { rc_o[k] = make_uint4(0, 0, 0, 0); rc_d[k] = make_uint4(0, 0, 0, 0); }
+      }
       if (m >= nheads || row >= L) return;
       const int item = int(blockIdx.x) + m * int(gridDim.x);
       const int b = item / H, h = item % H;
       rc_l = __ldg(lse + (size_t(b) * H + h) * L + row);
-      const uint4* op = reinterpret_cast<const uint4*>(out + (size_t(b) * L + row) * D + h * 32);
-      const uint4* dp = reinterpret_cast<const uint4*>(dout + (size_t(b) * L + row) * D + h * 32);
+      if constexpr (DELTA) {
+        rc_delta = __ldg(delta_in + (size_t(b) * L + row) * H + h);
+      } else {
+        const uint4* op = reinterpret_cast<const uint4*>(out + (size_t(b) * L + row) * D + h * 32);
+        const uint4* dp = reinterpret_cast<const uint4*>(dout + (size_t(b) * L + row) * D + h * 32);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { rc_o[k] = __ldg(op + k); rc_d[k] = __ldg(dp + k); }
+        for (int k = 0; k < 4; ++k) { rc_o[k] = __ldg(op + k); rc_d[k] = __ldg(dp + k); }
+      }
     };
     auto row_consts_finish = [&](float& lse2, float& delta) {
       lse2 = rc_l * l2e;
-      delta = 0.f;
+      delta = rc_delta;
+      if constexpr (!DELTA) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint4 o4 = rc_o[k], d4 = rc_d[k];
         delta += bf16_lo(o4.x) * bf16_lo(d4.x) + bf16_hi(o4.x) * bf16_hi(d4.x) + bf16_lo(o4.y) * bf16_lo(d4.y) + bf16_hi(o4.y) * bf16_hi(d4.y) +
                  bf16_lo(o4.z) * bf16_lo(d4.z) + bf16_hi(o4.z) * bf16_hi(d4.z) + bf16_lo(o4.w) * bf16_lo(d4.w) + bf16_hi(o4.w) * bf16_hi(d4.w);
+      }
       }
     };
     float lse2_next, delta_next;
@@ -667,22 +680,51 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// delta[(b L + l) H + h] = sum_d out[b, l, h, d] * dout[b, l, h, d]: one thread per (token, head), hd contiguous bf16 each
+// from both tensors (consecutive threads read consecutive 2 hd-byte pieces: fully coalesced), one float out.
+__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                                                        long long n, int hd, float* __restrict__ delta) {
+  pdl_trigger();
+  pdl_wait();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint4* op = reinterpret_cast<const uint4*>(out + t * hd);
+  const uint4* dp = reinterpret_cast<const uint4*>(dout + t * hd);
+  float acc = 0.f;
+  for (int k = 0; k < hd / 8; ++k) {
+    const uint4 o4 = __ldg(op + k), d4 = __ldg(dp + k);
+    acc += bf16_lo(o4.x) * bf16_lo(d4.x) + bf16_hi(o4.x) * bf16_hi(d4.x) + bf16_lo(o4.y) * bf16_lo(d4.y) + bf16_hi(o4.y) * bf16_hi(d4.y) +
+           bf16_lo(o4.z) * bf16_lo(d4.z) + bf16_hi(o4.z) * bf16_hi(d4.z) + bf16_lo(o4.w) * bf16_lo(d4.w) + bf16_hi(o4.w) * bf16_hi(d4.w);
+  }
+  delta[t] = acc;
+}
+
 int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, int B, int L, int H, void* dqkv,
-                cudaStream_t st) {
+                float* delta_ws, cudaStream_t st) {
   CUtensorMap mq, md;
   const int D = H * 32;
   int rc = make_tmap_bf16_3d(&mq, qkv, 3 * D, L, B, 3 * D, kTcLp, 32);
   if (rc) return rc;
   rc = make_tmap_bf16_3d(&md, dout, D, L, B, D, kTcLp, 32);
   if (rc) return rc;
-  static bool done[kMaxDevices] = {};
-  if (!ensure_dyn_smem(attn_bwd_tc_kernel, TcbSmem::total + 1024, done)) return MAE_ERR_LAUNCH;
   const int sms = num_sms();
   const int nitems = B * H;
   const int grid = nitems < sms ? nitems : sms;
-  mae_launch(attn_bwd_tc_kernel, dim3(grid), dim3(kTcThreads), size_t(TcbSmem::total) + 1024, st, mq, md,
-             reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), lse, reinterpret_cast<__nv_bfloat16*>(dqkv), B, L, H,
-             1.0f / sqrtf(32.0f));
+  const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(out);
+  const __nv_bfloat16* d_o = reinterpret_cast<const __nv_bfloat16*>(dout);
+  if (delta_ws) {
+    const long long n = (long long)B * L * H;
+    mae_launch(attn_delta_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, o, d_o, n, 32, delta_ws);
+    static bool done[kMaxDevices] = {};
+    if (!ensure_dyn_smem(attn_bwd_tc_kernel<true>, TcbSmem::total + 1024, done)) return MAE_ERR_LAUNCH;
+    mae_launch(attn_bwd_tc_kernel<true>, dim3(grid), dim3(kTcThreads), size_t(TcbSmem::total) + 1024, st, mq, md, o, d_o, lse,
+               (const float*)delta_ws, reinterpret_cast<__nv_bfloat16*>(dqkv), B, L, H, 1.0f / sqrtf(32.0f));
+  } else {
+    static bool done[kMaxDevices] = {};
+    if (!ensure_dyn_smem(attn_bwd_tc_kernel<false>, TcbSmem::total + 1024, done)) return MAE_ERR_LAUNCH;
+    mae_launch(attn_bwd_tc_kernel<false>, dim3(grid), dim3(kTcThreads), size_t(TcbSmem::total) + 1024, st, mq, md, o, d_o, lse,
+               (const float*)nullptr, reinterpret_cast<__nv_bfloat16*>(dqkv), B, L, H, 1.0f / sqrtf(32.0f));
+  }
   return MAE_CHECK_LAUNCH();
 }
 

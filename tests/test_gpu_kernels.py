@@ -428,6 +428,14 @@ def test_attention_tc_repeatable_and_item_distribution(B, L, H):
         assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2])
     out, lse, dqkv = outs[0]
     assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all() and torch.isfinite(dqkv.float()).all()
+    # the workspace entry point (delta = rowsum(dO o O) from a coalesced pre-pass instead of per-thread gathers): same sums
+    ws = torch.full((B * L * H + 64,), float("nan"), device=dev)
+    dqkv_ws = torch.full_like(qkv, float("nan"))
+    calls.mae_attention_bwd_ws(p(qkv), p(out), p(dout), p(lse), B, L, H, hd, p(dqkv_ws), p(ws), B * L * H * 4, stream())
+    assert torch.isnan(ws[B * L * H:]).all()  # the scratch is not overrun
+    ref_delta = (out.float() * dout.float()).view(B, L, H, hd).sum(-1)
+    assert max_err(ws[:B * L * H].view(B, L, H), ref_delta) < 1e-4 * hd
+    assert rel_err(dqkv_ws, dqkv) < 2e-3
     # spot-check samples spread over the batch (first, middle, last) against fp32 torch
     for b in sorted({0, B // 2, B - 1}):
         qf = qkv[b:b + 1].float().requires_grad_(True)

@@ -20,6 +20,9 @@ def run(B, L, H, hd):
         return e0.elapsed_time(e1) / n * 1e3
     f = t(lambda i: calls.mae_attention_fwd(qkvs[i % 3].data_ptr(), B, L, H, hd, out.data_ptr(), lse.data_ptr(), st))
     b = t(lambda i: calls.mae_attention_bwd(qkvs[i % 3].data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), B, L, H, hd, dqkv.data_ptr(), st))
+    ws = torch.empty(B * L * H, device="cuda")
+    bw = t(lambda i: calls.mae_attention_bwd_ws(qkvs[i % 3].data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), B, L, H, hd, dqkv.data_ptr(), ws.data_ptr(), ws.numel() * 4, st))
+    print(f"   with delta pre-pass (mae_attention_bwd_ws): bwd {bw:.1f} us")
     print(f"B={B} L={L} H={H} hd={hd} no_tc={os.environ.get('MAE_ATTN_NO_TC', '0')}: fwd {f:.1f} us  bwd {b:.1f} us")
 run(2000, 145, 6, 32)
 run(2000, 36, 6, 24)
