@@ -352,7 +352,9 @@ struct TcbSmem {  // P0/dS0 first: the MN-major reads of the second key tile run
   static constexpr uint32_t tile = kTcLp * 64;            // 10240 B
   static constexpr uint32_t tiles = 122880;               // [2 buffers][Q, dO, K, V]
   static constexpr uint32_t bars = tiles + 2 * 4 * tile;  // 204800
-  static constexpr uint32_t total = bars + 1024;
+  // gradient staging of the tile-0 warps: per warp [dQ | dK | dV] x [32 rows x 64 bytes] (64-byte swizzle) for TMA stores
+  static constexpr uint32_t stg = bars + 1024;
+  static constexpr uint32_t total = stg + 4 * 3 * 2048;
 };
 // TMEM: two S / dP buffers of 80 key columns each (buffer = key half; S at +0, dP at +80): the two query tiles of a head
 // take turns in them half by half, so tile 1's softmax overlaps tile 0's second half and the next head's first half
@@ -377,7 +379,7 @@ __device__ __forceinline__ void store_row32(__nv_bfloat16* dst, const uint32_t (
 template <bool DELTA>
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ CUtensorMap mapDO,
-                   const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                   const __grid_constant__ CUtensorMap mapG, const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
                    const float* __restrict__ lse, const float* __restrict__ delta_in, __nv_bfloat16* __restrict__ dqkv,
                    int B, int L, int H, float scale) {
   pdl_trigger();
@@ -392,6 +394,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
   if (warp == 2 && lane == 0) {
     tma_prefetch_desc(&mapQKV);
     tma_prefetch_desc(&mapDO);
+    tma_prefetch_desc(&mapG);
     for (int t = 0; t < 2; ++t) {
       mbar_init(&bars->ld_full[t], 1); mbar_init(&bars->ld_empty[t], 1);
       for (int hf = 0; hf < 2; ++hf) { mbar_init(&bars->sd_full[t][hf], 1); mbar_init(&bars->sd_free[t][hf], t == 0 ? 4 : 1); }
@@ -577,8 +580,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
     float lse2_next, delta_next;
     row_consts_issue(0);
     row_consts_finish(lse2_next, delta_next);
-    __nv_bfloat16* prev_base = nullptr;  // tile-0 warps: dqkv row of the head whose dK / dV epilogue is pending
-    auto dkv_epilogue = [&](__nv_bfloat16* base) {
+    // Gradient rows leave through shared memory and TMA stores for tile 0 (a row per thread written straight to global
+    // memory is a 16-byte piece of 32 different 1152-byte-strided rows per instruction: ~80 us of LSU time per launch,
+    // measured by skipping the stores); tile 1's 17 rows keep the direct stores.
+    const uint32_t stg_s = smem_u32(smem + TcbSmem::stg) + uint32_t(quarter) * 3u * 2048u;
+    auto stage_row32 = [&](uint32_t tile_s, const uint32_t (&o)[32], float mul) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        sts16(tile_s + uint32_t(lane) * 64u + (uint32_t(k ^ ((lane >> 1) & 3)) << 4),
+              pack_bf16x2(__uint_as_float(o[8 * k]) * mul, __uint_as_float(o[8 * k + 1]) * mul),
+              pack_bf16x2(__uint_as_float(o[8 * k + 2]) * mul, __uint_as_float(o[8 * k + 3]) * mul),
+              pack_bf16x2(__uint_as_float(o[8 * k + 4]) * mul, __uint_as_float(o[8 * k + 5]) * mul),
+              pack_bf16x2(__uint_as_float(o[8 * k + 6]) * mul, __uint_as_float(o[8 * k + 7]) * mul));
+    };
+    int prev_item = -1;  // tile-0 warps: the head whose dK / dV epilogue is pending
+    auto dkv_epilogue = [&](int item_m) {
+      const int bm = item_m / H, hm = item_m % H;
       mbar_wait(&bars->dkv_full, ph_dkvfull); ph_dkvfull ^= 1;
       tc_fence_after();
       uint32_t o[32], o2[32];
@@ -588,9 +605,24 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->dkv_free);
-      if (row < L) {
-        store_row32(base + D, o, scale);
-        store_row32(base + 2 * D, o2, 1.0f);
+      if (tile) {
+        if (row < L) {
+          __nv_bfloat16* base = dqkv + (size_t(bm) * L + row) * 3 * D + hm * 32;
+          store_row32(base + D, o, scale);
+          store_row32(base + 2 * D, o2, 1.0f);
+        }
+      } else {
+        // the staging tiles were last read by the stores of two heads ago; only the dQ store of the previous head may be pending
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        stage_row32(stg_s + 2048u, o, scale);
+        stage_row32(stg_s + 4096u, o2, 1.0f);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&mapG, stg_s + 2048u, D + hm * 32, quarter * 32, bm);
+          tma_store_3d(&mapG, stg_s + 4096u, 2 * D + hm * 32, quarter * 32, bm);
+        }
       }
     };
 #pragma unroll 1
@@ -653,7 +685,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->pds_ready[tile]);
       row_consts_issue(n + 1);  // in flight during the epilogue waits below
-      if (!tile && n > 0) dkv_epilogue(prev_base);  // the previous head's dK / dV rows
+      if (!tile && n > 0) dkv_epilogue(prev_item);  // the previous head's dK / dV rows
       // dQ rows of this tile
       {
         mbar_wait(&bars->dq_full[tile], ph_dqfull); ph_dqfull ^= 1;
@@ -664,16 +696,26 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->dq_free[tile]);
-        if (row < L) store_row32(dqkv + (size_t(b) * L + row) * 3 * D + h * 32, o, scale);
+        if (tile) {
+          if (row < L) store_row32(dqkv + (size_t(b) * L + row) * 3 * D + h * 32, o, scale);
+        } else {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");  // (the dK / dV stores just issued may be pending)
+          __syncwarp();
+          stage_row32(stg_s, o, scale);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) tma_store_3d(&mapG, stg_s, h * 32, quarter * 32, b);
+        }
       }
       // dK / dV rows (keys = TMEM lanes) once both query tiles have been accumulated.  The tile-0 warps defer this to
       // after the next head's softmax (dkv_epilogue below): the wait for tile 1 and its gradient MMAs is the longest of the
       // head, and the next head's S0 / dP0 are already in TMEM.
-      if (tile) dkv_epilogue(dqkv + (size_t(b) * L + row) * 3 * D + h * 32);
-      else prev_base = dqkv + (size_t(b) * L + row) * 3 * D + h * 32;
+      if (tile) dkv_epilogue(item);
+      else prev_item = item;
       row_consts_finish(lse2_next, delta_next);
     }
-    if (!tile && nheads > 0) dkv_epilogue(prev_base);
+    if (!tile && nheads > 0) dkv_epilogue(prev_item);
+    if (!tile && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores must complete before the smem goes away
   }
   tc_fence_before();
   __syncthreads();
@@ -707,6 +749,9 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
   if (rc) return rc;
   rc = make_tmap_bf16_3d(&md, dout, D, L, B, D, kTcLp, 32);
   if (rc) return rc;
+  CUtensorMap mg;  // gradient stores: [32 cols x 32 rows] boxes of dqkv (B, L, 3 D), 64-byte swizzle
+  rc = make_tmap_bf16_3d(&mg, dqkv, 3 * D, L, B, 3 * D, 32, 32);
+  if (rc) return rc;
   const int sms = num_sms();
   const int nitems = B * H;
   const int grid = nitems < sms ? nitems : sms;
@@ -717,12 +762,12 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
     mae_launch(attn_delta_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, o, d_o, n, 32, delta_ws);
     static bool done[kMaxDevices] = {};
     if (!ensure_dyn_smem(attn_bwd_tc_kernel<true>, TcbSmem::total + 1024, done)) return MAE_ERR_LAUNCH;
-    mae_launch(attn_bwd_tc_kernel<true>, dim3(grid), dim3(kTcThreads), size_t(TcbSmem::total) + 1024, st, mq, md, o, d_o, lse,
+    mae_launch(attn_bwd_tc_kernel<true>, dim3(grid), dim3(kTcThreads), size_t(TcbSmem::total) + 1024, st, mq, md, mg, o, d_o, lse,
                (const float*)delta_ws, reinterpret_cast<__nv_bfloat16*>(dqkv), B, L, H, 1.0f / sqrtf(32.0f));
   } else {
     static bool done[kMaxDevices] = {};
     if (!ensure_dyn_smem(attn_bwd_tc_kernel<false>, TcbSmem::total + 1024, done)) return MAE_ERR_LAUNCH;
-    mae_launch(attn_bwd_tc_kernel<false>, dim3(grid), dim3(kTcThreads), size_t(TcbSmem::total) + 1024, st, mq, md, o, d_o, lse,
+    mae_launch(attn_bwd_tc_kernel<false>, dim3(grid), dim3(kTcThreads), size_t(TcbSmem::total) + 1024, st, mq, md, mg, o, d_o, lse,
                (const float*)nullptr, reinterpret_cast<__nv_bfloat16*>(dqkv), B, L, H, 1.0f / sqrtf(32.0f));
   }
   return MAE_CHECK_LAUNCH();
