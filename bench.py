@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "MAE pretrain images/sec (fwd+bwd+AdamW, device-timed)"  # BASELINE.json's metric; the reference arm is host-timed
-GEMM_TN_DRAM_BYTES_PER_STEP = 10.332e9  # profiles/r02_gemm_tn_dram_traffic.csv (B=2000, the 44 gemm_tn launches of one step)
+GEMM_TN_DRAM_BYTES_PER_STEP = 10.332e9  # profiles/r02z_gemm_tn_dram_traffic.csv (B=2000, the 44 gemm_tn launches of one step: 6.37 GB read + 3.96 GB written)
 FLOPS_PER_IMAGE = 1_124_504_064  # fwd+bwd, patch-embed on kept patches only, no patch-embed dgrad
 CFG = {
     "general": {"image_size": 96, "patch_size": 8, "in_chans": 3},
@@ -309,12 +309,12 @@ def kernel_breakdown(trainer, images, noise, pk):
         tfs = gemm_flops / (g_ms * 1e-3) / 1e12
         roof = {"kernel": f"gemm_tn_kernel (tcgen05 + TMA; the {n_gemm} forward/dgrad GEMM launches of one step)",
                 "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-                # ncu dram__bytes_read.sum + dram__bytes_write.sum over the 53 gemm_tn launches of one step of this build
-                # (profiles/r01r_gemm_tn_dram_traffic.csv: 6.98 GB read + 4.43 GB written), per launch like the figure below
+                # ncu dram__bytes_read.sum + dram__bytes_write.sum over the 44 gemm_tn launches of one step of this build
+                # (profiles/r02z_gemm_tn_dram_traffic.csv: 6.37 GB read + 3.96 GB written), per launch like the figure below
                 "traffic": (GEMM_TN_DRAM_BYTES_PER_STEP / max(1, n_gemm)) if images.shape[0] == 2000 else None,
                 "algorithmic_bytes_per_launch": gemm_bytes / max(1, n_gemm),
                 "peak_source": pk["source"] + " (copy bandwidth)",
-                "traffic_note": "measured once with ncu (cold L2 per launch), not live: 11.41 GB per step vs the algorithmic "
+                "traffic_note": "measured once with ncu (cold L2 per launch), not live: 10.33 GB per step vs the algorithmic "
                                 "bytes below -> no wasted re-reads (outputs still resident in L2 at kernel end are not counted)",
                 "algorithmic_bytes_per_step": gemm_bytes, "ms_per_step": g_ms,
                 "tensor": {"achieved_tflops": tfs, "peak_tflops": pk["tf_sustained"], "frac": tfs / pk["tf_sustained"],
