@@ -9,16 +9,19 @@
 // belongs to the same sample slot.  Padding costs tensor FLOPs (which this shape has to spare: 3 % of peak before), not
 // HBM bytes.
 //
-// Loads: ONE 4-D TMA box per operand and item over (head dim, 3H slices, token, sample) = [32 x 1 x LP x G]: the box is
-// larger than the tensor along the head dim (24 -> 32) and the token dim (36 -> 40), so TMA zero-fills the K padding of
-// the MMAs and the rows between samples; samples past the batch end are zero-filled the same way.  Tiles are
-// [128 rows x 64 bytes], 64-byte swizzle; rows G*LP..127 are zeroed once.  The same tile serves as K-major operand
-// (S = Q K^T, dP = dO V^T) and as MN-major operand (O = P V, dQ = dS K, dK = dS^T Q, dV = P^T dO): no transposes.
+// Operand tiles are [128 rows x 64 bytes], 64-byte swizzle, head dim 24 -> 32 and rows 36 -> 40 zero-padded, rows
+// G*LP..127 zeroed once.  Backward: ONE 4-D TMA box per operand and item over (head dim, 3H slices, token, sample) =
+// [32 x 1 x LP x G]: the box is larger than the tensor along the head dim and the token dim, so TMA zero-fills the K
+// padding of the MMAs and the rows between samples; samples past the batch end are zero-filled the same way.  Forward:
+// four loader warps copy the live 16-byte chunks with cp.async from a per-thread chunk table (TMA serves such a box at
+// ~3.3 cycles per 48-byte row) and never touch the padding.  The same tile serves as K-major operand (S = Q K^T,
+// dP = dO V^T) and as MN-major operand (O = P V, dQ = dS K, dK = dS^T Q, dV = P^T dO): no transposes.
 //
-// Persistent, one CTA per SM: softmax groups of 4 warps (one TMEM lane quarter each; three groups in the forward, two in
-// the backward) take the CTA's items in turn, so one group's softmax runs under the other groups' MMAs; one TMA producer
-// warp, one tcgen05.mma issuer warp.  MMAs complete in issue order, which the schedule uses: the accumulators of a group's previous item are
-// complete whenever the S of its next item is, so each group drains them right after pulling S (no extra waits).
+// Persistent, one CTA per SM: two softmax groups of 4 warps (one TMEM lane quarter each) take the CTA's items in turn, so
+// one group's softmax runs under the other group's MMAs; the MMAs come from separate issuer warps (forward: S | P V of
+// the even items | P V of the odd items; backward: S, dP and dQ | dK | dV), each running warp-uniform and electing one
+// lane per burst.  The forward relies on MMAs of ONE issuer completing in issue order only where the barriers say so:
+// every accumulator is drained behind its own mbarrier.
 #include <stdlib.h>
 
 #include "mae_internal.h"
@@ -175,7 +178,7 @@ struct ItemIter {
 // =============================================================================================
 template <int NG>
 struct EfCfg {
-  static constexpr int kStages = NG == 3 ? 5 : 6;
+  static constexpr int kStages = NG == 3 ? 5 : 6;                 // (NG = 3 was measured too: no faster, 128-register cap)
   static constexpr int kLoadAhead = 4;                            // cp.async groups in flight per loader thread (<= 4)
   static constexpr int kThreads = (4 * NG + 7) * 32;  // softmax groups + 4 loader warps + S issuer + two P V issuers
   static constexpr uint32_t qkv = 0;                              // [stages][Q, K, V]
