@@ -168,10 +168,10 @@ def algorithmic_cost(name, a):
     if name == "mae_gemm_wgrad":
         Pc, Qc, M = a[1], a[3], a[4]
         return M * (Pc + Qc) * 2.0 + Pc * Qc * 4.0, 2.0 * M * Pc * Qc, f"M={M} P={Pc} Q={Qc}"
-    if name == "mae_attention_fwd":
+    if name in ("mae_attention_fwd", "mae_attention_fwd_q"):
         B, L, H, hd = a[1], a[2], a[3], a[4]
         return B * L * H * hd * 2.0 * 4 + B * H * L * 4.0, 4.0 * B * H * L * L * hd, f"B={B} L={L} H={H} hd={hd}"
-    if name in ("mae_attention_bwd", "mae_attention_bwd_ws"):
+    if name in ("mae_attention_bwd", "mae_attention_bwd_ws", "mae_attention_bwd_q"):
         B, L, H, hd = a[4], a[5], a[6], a[7]
         return B * L * H * hd * 2.0 * 8 + B * H * L * 4.0, 10.0 * B * H * L * L * hd, f"B={B} L={L} H={H} hd={hd}"
     if name == "mae_layernorm_fwd":
@@ -201,7 +201,7 @@ def algorithmic_cost(name, a):
     if name == "mae_assemble_tokens":
         B, nk, D = a[4], a[5], a[6]
         return B * nk * D * 6.0, 0.0, f"B={B} kept={nk} D={D}"
-    if name == "mae_scatter_decoder_tokens":
+    if name in ("mae_scatter_decoder_tokens", "mae_scatter_decoder_tokens_grouped"):
         B, L, nk, D = a[5], a[6], a[7], a[8]
         return B * nk * D * 2.0 + B * L * D * 4.0, 0.0, f"B={B} L={L} D={D}"
     if name == "mae_scatter_decoder_tokens_ln":

@@ -133,6 +133,14 @@ int mae_attention_fwd(const void* qkv_bf16, int B, int L, int H, int hd, void* o
                       mae_stream_t stream);
 int mae_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse, int B,
                       int L, int H, int hd, void* dqkv_bf16, mae_stream_t stream);
+/* The same op when only the first q_rows query tokens matter (the caller keeps the rows it needs first, e.g. the last
+ * decoder block of the MAE, whose kept tokens are keys / values only).  Forward: out / lse rows >= q_rows are unspecified
+ * (the decoder-sized tcgen05 kernel skips its second query tile for q_rows <= 128 and writes zeros to out rows >= 128).
+ * Backward: dout is treated as zero on rows >= q_rows; dqkv is complete (zero dQ on those rows). */
+int mae_attention_fwd_q(const void* qkv_bf16, int B, int L, int H, int hd, int q_rows, void* out_bf16, float* lse,
+                        mae_stream_t stream);
+int mae_attention_bwd_q(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse, int B,
+                        int L, int H, int hd, int q_rows, void* dqkv_bf16, mae_stream_t stream);
 /* Same op with a caller-provided scratch buffer (>= B*L*H*4 bytes, 16-byte aligned): kernels that want
  * delta = rowsum(dout o out) per (token, head) compute it there with a coalesced pre-pass instead of per-thread row
  * gathers inside the attention kernel (decoder-sized tcgen05 backward: ~0.9x the time).  ws may be NULL. */
@@ -142,6 +150,12 @@ int mae_attention_bwd_ws(const void* qkv_bf16, const void* out_bf16, const void*
 /* repeat_token(mask_token) + set_at_index(idx_keep, embed) + decoder_pos_embed add (reference
  * src/models/mae.py:61-69 and MAEDecoderTIMM.decode's pos add): x_dec (B,L,D) f32. */
 int mae_scatter_decoder_tokens(const void* emb_bf16, const float* mask_token, const float* dec_pos,
+                               const int64_t* idx_keep, const int64_t* idx_mask, int B, int L, int num_keep, int D,
+                               float* x_dec, mae_stream_t stream);
+/* Same tokens, stored as [mask tokens in idx_mask order | kept tokens in idx_keep order] per sample (row r < L - num_keep
+ * holds token idx_mask[r], row L - num_keep + i holds token idx_keep[i]): the rows the prediction head reads come first,
+ * so the last decoder block can use mae_attention_fwd_q / bwd_q with q_rows = L - num_keep. */
+int mae_scatter_decoder_tokens_grouped(const void* emb_bf16, const float* mask_token, const float* dec_pos,
                                const int64_t* idx_keep, const int64_t* idx_mask, int B, int L, int num_keep, int D,
                                float* x_dec, mae_stream_t stream);
 

@@ -30,7 +30,10 @@ SIGNATURES = {
     "mae_attention_fwd": [_vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "mae_attention_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "mae_attention_bwd_ws": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _ll, _vp],
+    "mae_attention_fwd_q": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "mae_attention_bwd_q": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "mae_scatter_decoder_tokens": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "mae_scatter_decoder_tokens_grouped": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "mae_scatter_decoder_tokens_ln": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp],
     "mae_masked_mse": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "mae_colsum_bf16": [_vp, _i, _i, _vp, _vp],

@@ -455,22 +455,32 @@ using namespace mae;
     default: return MAE_ERR_SHAPE;                                                                            \
   }
 
-extern "C" int mae_attention_fwd(const void* qkv, int B, int L, int H, int hd, void* out, float* lse,
-                                 cudaStream_t stream) {
+static int attention_fwd_impl(const void* qkv, int B, int L, int H, int hd, void* out, float* lse, int q_rows, cudaStream_t stream) {
   if (B <= 0) return MAE_OK;
   if (!qkv || !out || !lse) return MAE_ERR_NULL;
   const int nt = pick_nt(L);
   if (!nt || L < 1 || H < 1) return MAE_ERR_SHAPE;
   {
     static const bool no_tc = getenv("MAE_ATTN_NO_TC") != nullptr;  // A/B switch: keep everything on the mma.sync kernels
-    if (!no_tc && hd == 32 && L > 128 && L <= 160 && (H % 2) == 0) return attn_fwd_tc(qkv, B, L, H, out, lse, stream);
+    if (!no_tc && hd == 32 && L > 128 && L <= 160 && (H % 2) == 0) return attn_fwd_tc(qkv, B, L, H, out, lse, q_rows, stream);
     if (!no_tc && attn_enc_covers(L, hd)) return attn_fwd_enc(qkv, B, L, H, hd, out, lse, stream);
   }
   MAE_ATTN_DISPATCH(launch_fwd, qkv, B, L, H, out, lse, stream)
 }
 
+extern "C" int mae_attention_fwd(const void* qkv, int B, int L, int H, int hd, void* out, float* lse,
+                                 cudaStream_t stream) {
+  return attention_fwd_impl(qkv, B, L, H, hd, out, lse, L, stream);
+}
+
+extern "C" int mae_attention_fwd_q(const void* qkv, int B, int L, int H, int hd, int q_rows, void* out, float* lse,
+                                   cudaStream_t stream) {
+  if (q_rows < 1 || q_rows > L) return MAE_ERR_SHAPE;
+  return attention_fwd_impl(qkv, B, L, H, hd, out, lse, q_rows, stream);
+}
+
 static int attention_bwd_impl(const void* qkv, const void* out, const void* dout, const float* lse, int B, int L, int H, int hd,
-                              void* dqkv, float* delta_ws, cudaStream_t stream) {
+                              void* dqkv, float* delta_ws, int q_rows, cudaStream_t stream) {
   if (B <= 0) return MAE_OK;
   if (!qkv || !out || !dout || !lse || !dqkv) return MAE_ERR_NULL;
   const int nt = pick_nt(L);
@@ -479,7 +489,7 @@ static int attention_bwd_impl(const void* qkv, const void* out, const void* dout
     static const bool no_tc = getenv("MAE_ATTN_NO_TC") != nullptr || getenv("MAE_ATTN_NO_TC_BWD") != nullptr;
     static const bool no_delta = getenv("MAE_ATTN_NO_DELTA_PREPASS") != nullptr;  // A/B switch
     if (!no_tc && hd == 32 && L > 128 && L <= 160 && (H % 2) == 0)
-      return attn_bwd_tc(qkv, out, dout, lse, B, L, H, dqkv, no_delta ? nullptr : delta_ws, stream);
+      return attn_bwd_tc(qkv, out, dout, lse, B, L, H, dqkv, no_delta ? nullptr : delta_ws, q_rows, stream);
     if (!no_tc && attn_enc_covers(L, hd)) return attn_bwd_enc(qkv, out, dout, lse, B, L, H, hd, dqkv, stream);
   }
   MAE_ATTN_DISPATCH(launch_bwd, qkv, out, dout, lse, B, L, H, dqkv, stream)
@@ -487,11 +497,17 @@ static int attention_bwd_impl(const void* qkv, const void* out, const void* dout
 
 extern "C" int mae_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int B, int L,
                                  int H, int hd, void* dqkv, cudaStream_t stream) {
-  return attention_bwd_impl(qkv, out, dout, lse, B, L, H, hd, dqkv, nullptr, stream);
+  return attention_bwd_impl(qkv, out, dout, lse, B, L, H, hd, dqkv, nullptr, L, stream);
 }
 
 extern "C" int mae_attention_bwd_ws(const void* qkv, const void* out, const void* dout, const float* lse, int B, int L,
                                     int H, int hd, void* dqkv, void* ws, long long ws_bytes, cudaStream_t stream) {
   float* delta = (ws && ws_bytes >= (long long)B * L * H * 4 && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) ? reinterpret_cast<float*>(ws) : nullptr;
-  return attention_bwd_impl(qkv, out, dout, lse, B, L, H, hd, dqkv, delta, stream);
+  return attention_bwd_impl(qkv, out, dout, lse, B, L, H, hd, dqkv, delta, L, stream);
+}
+
+extern "C" int mae_attention_bwd_q(const void* qkv, const void* out, const void* dout, const float* lse, int B, int L,
+                                   int H, int hd, int q_rows, void* dqkv, cudaStream_t stream) {
+  if (q_rows < 1 || q_rows > L) return MAE_ERR_SHAPE;
+  return attention_bwd_impl(qkv, out, dout, lse, B, L, H, hd, dqkv, nullptr, q_rows, stream);
 }

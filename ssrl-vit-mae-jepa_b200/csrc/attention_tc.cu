@@ -54,7 +54,7 @@ static_assert(TcSmem::p1 + 2 * 4096 + 16384 <= TcSmem::total, "P1 over-read stay
 // anything with one warp per scheduler.
 __device__ __forceinline__ void tc_softmax_warp(TcBars* bars, uint8_t* smem, uint32_t tmem_base, const CUtensorMap* mapO,
                                                 const int tile, int quarter, int lane, bool storer, int nitems, int L, int H,
-                                                float scale, float* __restrict__ lse) {
+                                                float scale, float* __restrict__ lse, const uint32_t nbar) {
   const int HP = H >> 1;
   const float sl2 = scale * 1.4426950408889634f;
   const int row = tile ? 128 + lane : quarter * 32 + lane;   // query token of this thread
@@ -148,7 +148,7 @@ __device__ __forceinline__ void tc_softmax_warp(TcBars* bars, uint8_t* smem, uin
         if (par == 1) {  // both heads of the item are staged: one TMA store [160 x 64] for the pair
           const int item_m = int(blockIdx.x) + (m >> 1) * int(gridDim.x);
           fence_proxy_async_smem();
-          asm volatile("bar.sync 1, 160;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"r"(nbar) : "memory");  // the softmax warps of the item (160 threads; 128 without tile 1)
           if (storer && lane == 0) {
             tma_store_3d(mapO, ost, (item_m % HP) * 64, 0, item_m / HP);
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -176,7 +176,7 @@ __device__ __forceinline__ void tc_softmax_warp(TcBars* bars, uint8_t* smem, uin
       }
       const int item_m = int(blockIdx.x) + (m >> 1) * int(gridDim.x);
       fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 160;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"r"(nbar) : "memory");  // the softmax warps of the item (160 threads; 128 without tile 1)
       if (storer && lane == 0) {
         tma_store_3d(mapO, ost, (item_m % HP) * 64, 0, item_m / HP);
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -187,7 +187,10 @@ __device__ __forceinline__ void tc_softmax_warp(TcBars* bars, uint8_t* smem, uin
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ CUtensorMap mapO,
-                   float* __restrict__ lse, int B, int L, int H, float scale) {
+                   float* __restrict__ lse, int B, int L, int H, float scale, int skip1) {
+  // skip1: only query rows 0..127 are wanted (the caller keeps the rows it needs first: last decoder block, whose rows past
+  // the masked tokens are keys / values only): query tile 1, its issuer and its softmax warp do nothing; O rows >= 128 are
+  // written as zeros, lse rows >= 128 are not written.
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -200,7 +203,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
     tma_prefetch_desc(&mapQKV);
     tma_prefetch_desc(&mapO);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->kv_full[i], 1); mbar_init(&bars->kv_empty[i], 2);
+      mbar_init(&bars->kv_full[i], 1); mbar_init(&bars->kv_empty[i], skip1 ? 1 : 2);
       mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_free[i], i == 0 ? 4 : 1);
       mbar_init(&bars->p_ready[i], i == 0 ? 4 : 1); mbar_init(&bars->p_free[i], 1);
       for (int j = 0; j < 2; ++j) { mbar_init(&bars->o_full[i][j], 1); mbar_init(&bars->o_free[i][j], i == 0 ? 4 : 1); }
@@ -209,6 +212,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(&bars->tmem_base, 512);
+  // rows 128..159 of the O staging tile: zero unless query tile 1 writes them
+  for (uint32_t i = threadIdx.x; i < 32u * 128u / 16u; i += kTcThreads) reinterpret_cast<uint4*>(smem + TcSmem::ostg + 128 * 128)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -235,7 +241,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
         __syncwarp();
       }
     }
-  } else if (warp == 1 || warp == 3) {
+  } else if (warp == 1 || (warp == 3 && !skip1)) {
     // one tcgen05.mma issuer per query tile (warp 1: tile 0, warp 3: tile 1): their waits do not couple the two softmax
     // pipelines; the TMEM regions are disjoint and the smem operands read-only
     {
@@ -295,16 +301,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
         issue_pv(n, (n & 1) != 0);
       }
     }
-  } else if (warp == 0 || warp >= 4) {
+  } else if ((warp == 0 && !skip1) || warp >= 4) {
     // warp 0: query tile 1 (TMEM lane quarter 0 = rows 128..159 of the tile-1 accumulators); warps 4..7: tile 0
-    tc_softmax_warp(bars, smem, tmem_base, &mapO, warp == 0 ? 1 : 0, warp & 3, lane, warp == 4, nitems, L, H, scale, lse);
+    tc_softmax_warp(bars, smem, tmem_base, &mapO, warp == 0 ? 1 : 0, warp & 3, lane, warp == 4, nitems, L, H, scale, lse,
+                    skip1 ? 128u : 160u);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-int attn_fwd_tc(const void* qkv, int B, int L, int H, void* out, float* lse, cudaStream_t st) {
+int attn_fwd_tc(const void* qkv, int B, int L, int H, void* out, float* lse, int q_rows, cudaStream_t st) {
   CUtensorMap mq, mo;
   const int D = H * 32;
   int rc = make_tmap_bf16_3d(&mq, qkv, 3 * D, L, B, 3 * D, kTcLp);
@@ -317,7 +324,7 @@ int attn_fwd_tc(const void* qkv, int B, int L, int H, void* out, float* lse, cud
   const int nitems = B * (H / 2);
   const int grid = nitems < sms ? nitems : sms;
   mae_launch(attn_fwd_tc_kernel, dim3(grid), dim3(kTcThreads), size_t(TcSmem::total) + 1024, st, mq, mo, lse, B, L, H,
-             1.0f / sqrtf(32.0f));
+             1.0f / sqrtf(32.0f), q_rows <= 128 ? 1 : 0);
   return MAE_CHECK_LAUNCH();
 }
 
@@ -381,7 +388,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_constant__ CUtensorMap mapDO,
                    const __grid_constant__ CUtensorMap mapG, const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
                    const float* __restrict__ lse, const float* __restrict__ delta_in, __nv_bfloat16* __restrict__ dqkv,
-                   int B, int L, int H, float scale) {
+                   int B, int L, int H, float scale, int q_rows) {
+  // q_rows <= 128 ("skip1"): only the first q_rows query rows carry a gradient (dout is treated as zero on the others: the
+  // last decoder block, whose rows past the masked tokens are keys / values only).  Query tile 1 then contributes nothing:
+  // no S1 / dP1, no tile-1 softmax, no tile-1 gradient MMAs; the S / dP buffers are drained by tile 0 alone, so the next
+  // head's S0 / dP0 are issued while tile 0 still works on this head.  dQ rows >= q_rows are written as zeros.
+  const bool skip1 = q_rows <= 128;
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -492,8 +504,33 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
       };
       uint32_t ph_sdfree[2][2] = {{0, 0}, {0, 0}}, ph_ready[2] = {0, 0}, ph_dqfree[2] = {0, 0}, ph_dkvfree = 0;
       auto wait_sdfree = [&](int t, int hf) { mbar_wait(&bars->sd_free[t][hf], ph_sdfree[t][hf]); ph_sdfree[t][hf] ^= 1; };
+      if (skip1) {
+        if (nheads > 0) {
+          mbar_wait(&bars->ld_full[0], 0);
+          tc_fence_after();
+          issue_sdp(0, 0, 0);
+          issue_sdp(0, 0, 1);
+        }
+        for (int n = 0; n < nheads; ++n) {
+          if (n + 1 < nheads) {  // next head's S0 / dP0 as soon as tile 0 has pulled each buffer of this head
+            mbar_wait(&bars->ld_full[(n + 1) & 1], ((n + 1) >> 1) & 1);
+            for (int hf = 0; hf < 2; ++hf) {
+              wait_sdfree(0, hf);
+              tc_fence_after();
+              issue_sdp(n + 1, 0, hf);
+            }
+          }
+          mbar_wait(&bars->pds_ready[0], ph_ready[0]); ph_ready[0] ^= 1;
+          if (n > 0) {
+            mbar_wait(&bars->dq_free[0], ph_dqfree[0]); ph_dqfree[0] ^= 1;
+            mbar_wait(&bars->dkv_free, ph_dkvfree); ph_dkvfree ^= 1;
+          }
+          tc_fence_after();
+          issue_grads(n, 0, true);
+        }
+      }
       bool sdp0_issued = false;  // tile 0's S / dP of the current head were issued ahead (inside the previous head)
-      for (int n = 0; n < nheads; ++n) {
+      for (int n = 0; n < (skip1 ? 0 : nheads); ++n) {
         if (!sdp0_issued) {
           mbar_wait(&bars->ld_full[n & 1], (n >> 1) & 1);
           for (int hf = 0; hf < 2; ++hf) {  // each buffer was last used by the previous head's tile 1
@@ -552,7 +589,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
 #pragma unroll
         for (int k = 0; k < 4; ++k) { rc_o[k] = make_uint4(0, 0, 0, 0); rc_d[k] = make_uint4(0, 0, 0, 0); }
       }
-      if (m >= nheads || row >= L) return;
+      if (m >= nheads || row >= L || row >= q_rows) return;  // (rows without a gradient: lse = +inf makes P and dS vanish)
       const int item = int(blockIdx.x) + m * int(gridDim.x);
       const int b = item / H, h = item % H;
       rc_l = __ldg(lse + (size_t(b) * H + h) * L + row);
@@ -625,8 +662,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapQKV, const __grid_cons
         }
       }
     };
+    if (tile && skip1) {
+      // no tile-1 queries: this warp only drains the dK / dV rows of keys 128.. (accumulated from tile 0's queries) and
+      // writes the zero dQ rows of the tokens >= 128
 #pragma unroll 1
-    for (int n = 0; n < nheads; ++n) {
+      for (int n = 0; n < nheads; ++n) {
+        const int item = int(blockIdx.x) + n * int(gridDim.x);
+        dkv_epilogue(item);
+        if (row < L) {
+          uint4* dst = reinterpret_cast<uint4*>(dqkv + (size_t(item / H) * L + row) * 3 * D + (item % H) * 32);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dst[k] = make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+#pragma unroll 1
+    for (int n = 0; n < ((tile && skip1) ? 0 : nheads); ++n) {
       const int item = int(blockIdx.x) + n * int(gridDim.x);
       const int b = item / H, h = item % H;
       const float lse2 = lse2_next, delta = delta_next;
@@ -742,7 +793,7 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 }
 
 int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, int B, int L, int H, void* dqkv,
-                float* delta_ws, cudaStream_t st) {
+                float* delta_ws, int q_rows, cudaStream_t st) {
   CUtensorMap mq, md;
   const int D = H * 32;
   int rc = make_tmap_bf16_3d(&mq, qkv, 3 * D, L, B, 3 * D, kTcLp, 32);
@@ -763,12 +814,12 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
     static bool done[kMaxDevices] = {};
     if (!ensure_dyn_smem(attn_bwd_tc_kernel<true>, TcbSmem::total + 1024, done)) return MAE_ERR_LAUNCH;
     mae_launch(attn_bwd_tc_kernel<true>, dim3(grid), dim3(kTcThreads), size_t(TcbSmem::total) + 1024, st, mq, md, mg, o, d_o, lse,
-               (const float*)delta_ws, reinterpret_cast<__nv_bfloat16*>(dqkv), B, L, H, 1.0f / sqrtf(32.0f));
+               (const float*)delta_ws, reinterpret_cast<__nv_bfloat16*>(dqkv), B, L, H, 1.0f / sqrtf(32.0f), q_rows);
   } else {
     static bool done[kMaxDevices] = {};
     if (!ensure_dyn_smem(attn_bwd_tc_kernel<false>, TcbSmem::total + 1024, done)) return MAE_ERR_LAUNCH;
     mae_launch(attn_bwd_tc_kernel<false>, dim3(grid), dim3(kTcThreads), size_t(TcbSmem::total) + 1024, st, mq, md, mg, o, d_o, lse,
-               (const float*)nullptr, reinterpret_cast<__nv_bfloat16*>(dqkv), B, L, H, 1.0f / sqrtf(32.0f));
+               (const float*)nullptr, reinterpret_cast<__nv_bfloat16*>(dqkv), B, L, H, 1.0f / sqrtf(32.0f), q_rows);
   }
   return MAE_CHECK_LAUNCH();
 }

@@ -429,7 +429,9 @@ __global__ void __launch_bounds__(256) scatter_decoder_kernel(const __nv_bfloat1
                                                              const float* __restrict__ dec_pos,
                                                              const int64_t* __restrict__ idx_keep,
                                                              const int64_t* __restrict__ idx_mask, int B, int L,
-                                                             int num_keep, int D, float* __restrict__ x_dec) {
+                                                             int num_keep, int D, float* __restrict__ x_dec, int grouped) {
+  // grouped: the stream is stored as [mask tokens in idx_mask order | kept tokens in idx_keep order] per sample instead
+  // of in token order (row-wise operators and attention do not care; the positional embedding still follows the token)
   pdl_trigger();
   pdl_wait();
   const int D4 = D >> 2;
@@ -451,7 +453,8 @@ __global__ void __launch_bounds__(256) scatter_decoder_kernel(const __nv_bfloat1
     }
     const float4 p = *reinterpret_cast<const float4*>(dec_pos + size_t(l) * D + d);
     v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
-    *reinterpret_cast<float4*>(x_dec + (size_t(b) * L + l) * D + d) = v;
+    const int dst_row = grouped ? (jj < num_keep ? n_mask + jj : jj - num_keep) : l;
+    *reinterpret_cast<float4*>(x_dec + (size_t(b) * L + dst_row) * D + d) = v;
   }
 }
 
@@ -1089,7 +1092,17 @@ extern "C" int mae_scatter_decoder_tokens(const void* emb, const float* mask_tok
   if (B <= 0) return MAE_OK;
   if (!emb || !mask_token || !dec_pos || !idx_keep || !idx_mask || !x_dec) return MAE_ERR_NULL;
   if (D % 4 || num_keep < 1 || num_keep > L) return MAE_ERR_SHAPE;
-  mae_launch(scatter_decoder_kernel, dim3(grid_for((long long)B * L * (D / 4), 256)), dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(emb), mask_token, dec_pos, idx_keep, idx_mask, B, L, num_keep, D, x_dec);
+  mae_launch(scatter_decoder_kernel, dim3(grid_for((long long)B * L * (D / 4), 256)), dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(emb), mask_token, dec_pos, idx_keep, idx_mask, B, L, num_keep, D, x_dec, 0);
+  return MAE_CHECK_LAUNCH();
+}
+
+extern "C" int mae_scatter_decoder_tokens_grouped(const void* emb, const float* mask_token, const float* dec_pos,
+                                                  const int64_t* idx_keep, const int64_t* idx_mask, int B, int L,
+                                                  int num_keep, int D, float* x_dec, cudaStream_t stream) {
+  if (B <= 0) return MAE_OK;
+  if (!emb || !mask_token || !dec_pos || !idx_keep || !idx_mask || !x_dec) return MAE_ERR_NULL;
+  if (D % 4 || num_keep < 1 || num_keep > L) return MAE_ERR_SHAPE;
+  mae_launch(scatter_decoder_kernel, dim3(grid_for((long long)B * L * (D / 4), 256)), dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(emb), mask_token, dec_pos, idx_keep, idx_mask, B, L, num_keep, D, x_dec, 1);
   return MAE_CHECK_LAUNCH();
 }
 

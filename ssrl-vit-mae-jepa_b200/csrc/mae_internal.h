@@ -11,10 +11,11 @@
 namespace mae {
 int make_tmap_bf16(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows);
 // attention_tc.cu: tcgen05 attention for 128 < L <= 160, head_dim 32, even H
-int attn_fwd_tc(const void* qkv, int B, int L, int H, void* out, float* lse, cudaStream_t st);
+// q_rows: number of leading query rows whose outputs (gradients) are wanted; <= 128 skips the second query tile
+int attn_fwd_tc(const void* qkv, int B, int L, int H, void* out, float* lse, int q_rows, cudaStream_t st);
 // delta_ws: optional (B, L, H) f32 scratch: rowsum(dO o O) is then computed by a coalesced pre-pass instead of per-thread gathers
 int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, int B, int L, int H, void* dqkv,
-                float* delta_ws, cudaStream_t st);
+                float* delta_ws, int q_rows, cudaStream_t st);
 // attention_enc.cu: tcgen05 attention for short rows (L <= 64, head_dim 8..32): several samples per 128-row tile
 bool attn_enc_covers(int L, int hd);
 int attn_fwd_enc(const void* qkv, int B, int L, int H, int hd, void* out, float* lse, cudaStream_t st);

@@ -194,6 +194,11 @@ class MAEEngine:
         # masked-rows-only tail of the last decoder block: decoder_norm / decoder_pred only read the idx_mask rows, so the
         # block's norm2 -> mlp -> residual (and their backward) run on those rows alone (MAE_MASKED_TAIL=0: all rows)
         self.masked_tail = os.environ.get("MAE_MASKED_TAIL", "1") != "0"
+        # grouped decoder stream (with the masked tail): rows stored as [mask tokens | kept tokens] per sample, so the rows the
+        # prediction head reads come first and the last block's attention only needs its first Lm query rows: the decoder-
+        # sized tcgen05 kernels then skip their second query tile (mae_attention_fwd_q / bwd_q).  MAE_GROUPED_DECODER=0:
+        # token order
+        self.grouped_decoder = os.environ.get("MAE_GROUPED_DECODER", "1") != "0"
         # the small optimizer-only launches (W^T refresh, mask-token column sum, kept-row clearing) also on the side stream
         self.side_extras = os.environ.get("MAE_SIDE_EXTRAS", "1") != "0"
         # decoder-input assembly fused with the first decoder block's norm1: correct, but measured slower than the two
@@ -357,6 +362,9 @@ class MAEEngine:
         ws: Dict[str, Any] = {}
         ws["idx_keep"] = e((B, Lk), torch.int64)
         ws["idx_mask"] = e((B, Lm), torch.int64)
+        # decoder-stream ROW indices of the masked / kept tokens in the grouped layout (the same for every sample)
+        ws["pos_mask"] = torch.arange(Lm, dtype=torch.int64, device=device).repeat(B, 1).contiguous()
+        ws["pos_keep"] = (Lm + torch.arange(Lk, dtype=torch.int64, device=device)).repeat(B, 1).contiguous()
         ws["patches"] = e((B * (Lk - 1), pd), bf)
         ws["tok"] = e((B * (Lk - 1), De), bf)
 
@@ -392,6 +400,16 @@ class MAEEngine:
         self.dims = dict(B=B, L=L, Lk=Lk, Lm=Lm, De=De, Dd=Dd, pd=pd, Me=Me, Md=Md, Mm=Mm)
 
     # ---------------- forward pieces ----------------
+    def _use_grouped(self) -> bool:
+        return self.grouped_decoder and self._use_masked_tail() and not self.scatter_ln
+
+    def _rows_mask(self) -> int:
+        """Decoder-stream row indices (B, Lm) of the masked tokens."""
+        return _ptr(self.ws["pos_mask"] if self._use_grouped() else self.ws["idx_mask"])
+
+    def _rows_keep(self) -> int:
+        return _ptr(self.ws["pos_keep"] if self._use_grouped() else self.ws["idx_keep"])
+
     def _use_masked_tail(self) -> bool:
         return self.masked_tail and len(self.dec_blocks) > 0 and self.dims["Dd"] <= 256
 
@@ -411,7 +429,10 @@ class MAEEngine:
                                     _ptr(s["xn1"]), _ptr(s["mean1"]), _ptr(s["rstd1"]), st)
         calls.mae_gemm_tn(_ptr(s["xn1"]), self.pw(w.qkvw), M, 3 * D, D, EPI_BF16, self.pf(w.qkvb), _ptr(s["qkv"]),
                           None, None, st)
-        calls.mae_attention_fwd(_ptr(s["qkv"]), B, L, H, hd, _ptr(s["att"]), _ptr(s["lse"]), st)
+        if tail and self._use_grouped():  # only the masked tokens' rows (first Lm of every sample) are read downstream
+            calls.mae_attention_fwd_q(_ptr(s["qkv"]), B, L, H, hd, self.dims["Lm"], _ptr(s["att"]), _ptr(s["lse"]), st)
+        else:
+            calls.mae_attention_fwd(_ptr(s["qkv"]), B, L, H, hd, _ptr(s["att"]), _ptr(s["lse"]), st)
         calls.mae_gemm_tn(_ptr(s["att"]), self.pw(w.projw), M, D, D, EPI_RESID_F32, self.pf(w.projb),
                           _ptr(s["x_mid"]), None, _ptr(s["x_in"]), st)
         if self._use_fused_mlp(D, self.dims["Mm"] if tail else M):
@@ -419,7 +440,7 @@ class MAEEngine:
             # idx_mask rows on the way in and leaves the compact fp32 sums  x_mid[idx_mask] + mlp(...)  in x_dec
             ws, d = self.ws, self.dims
             if tail:
-                calls.mae_mlp_fwd(_ptr(s["x_mid"]), _ptr(ws["idx_mask"]), d["Lm"], L, d["Mm"], D, self.pf(w.n2w),
+                calls.mae_mlp_fwd(_ptr(s["x_mid"]), self._rows_mask(), d["Lm"], L, d["Mm"], D, self.pf(w.n2w),
                                   self.pf(w.n2b), LN_EPS, self.pw(w.fc1w), self.pf(w.fc1b), self.pw(w.fc2w), self.pf(w.fc2b),
                                   _ptr(s["xn2"]), _ptr(s["mean2"]), _ptr(s["rstd2"]), _ptr(s["h"]), _ptr(s["pre"]),
                                   _ptr(ws["x_dec"]), st)
@@ -431,7 +452,7 @@ class MAEEngine:
         if tail:
             ws, d = self.ws, self.dims
             Mt = d["Mm"]
-            calls.mae_layernorm_fwd(_ptr(s["x_mid"]), self.pf(w.n2w), self.pf(w.n2b), _ptr(ws["idx_mask"]), d["Lm"], L, Mt,
+            calls.mae_layernorm_fwd(_ptr(s["x_mid"]), self.pf(w.n2w), self.pf(w.n2b), self._rows_mask(), d["Lm"], L, Mt,
                                     D, LN_EPS, _ptr(s["xn2"]), _ptr(s["mean2"]), _ptr(s["rstd2"]), st)
             calls.mae_gemm_tn(_ptr(s["xn2"]), self.pw(w.fc1w), Mt, 4 * D, D, EPI_GELU_BF16, self.pf(w.fc1b), _ptr(s["h"]),
                               _ptr(s["pre"]), None, st)
@@ -568,9 +589,9 @@ class MAEEngine:
                                                 _ptr(ws["idx_mask"]), B, L, Lk, Dd, self.pf(w0.n1w), self.pf(w0.n1b), LN_EPS,
                                                 _ptr(x0), _ptr(s0["xn1"]), _ptr(s0["mean1"]), _ptr(s0["rstd1"]), st)
         else:
-            calls.mae_scatter_decoder_tokens(_ptr(ws["emb"]), self.pf(o("decoder.mask_token")),
-                                             self.pf(o("decoder.decoder_pos_embed")), _ptr(ws["idx_keep"]),
-                                             _ptr(ws["idx_mask"]), B, L, Lk, Dd, _ptr(x0), st)
+            scatter = calls.mae_scatter_decoder_tokens_grouped if self._use_grouped() else calls.mae_scatter_decoder_tokens
+            scatter(_ptr(ws["emb"]), self.pf(o("decoder.mask_token")), self.pf(o("decoder.decoder_pos_embed")),
+                    _ptr(ws["idx_keep"]), _ptr(ws["idx_mask"]), B, L, Lk, Dd, _ptr(x0), st)
         tail = self._use_masked_tail()
         for i, w in enumerate(self.dec_blocks):
             x_out = ws["dec"][i + 1]["x_in"] if i + 1 < n_dec else ws["x_dec"]
@@ -585,11 +606,11 @@ class MAEEngine:
             # decoder_norm over  x_mid[idx_mask rows] + mlp output ; the summed rows (compact) are kept in x_dec for the backward
             calls.mae_layernorm_fwd_add(_ptr(ws["dec"][-1]["x_mid"]), _ptr(ws["dlt"]),
                                         self.pf(o("decoder.decoder_norm.weight")), self.pf(o("decoder.decoder_norm.bias")),
-                                        _ptr(ws["idx_mask"]), Lm, L, d["Mm"], Dd, LN_EPS, _ptr(ws["x_dec"]),
+                                        self._rows_mask(), Lm, L, d["Mm"], Dd, LN_EPS, _ptr(ws["x_dec"]),
                                         _ptr(ws["xnd"]), _ptr(ws["meand"]), _ptr(ws["rstdd"]), st)
         else:
             calls.mae_layernorm_fwd(_ptr(ws["x_dec"]), self.pf(o("decoder.decoder_norm.weight")),
-                                    self.pf(o("decoder.decoder_norm.bias")), _ptr(ws["idx_mask"]), Lm, L, d["Mm"], Dd, LN_EPS,
+                                    self.pf(o("decoder.decoder_norm.bias")), self._rows_mask(), Lm, L, d["Mm"], Dd, LN_EPS,
                                     _ptr(ws["xnd"]), _ptr(ws["meand"]), _ptr(ws["rstdd"]), st)
         calls.mae_gemm_tn(_ptr(ws["xnd"]), self.pw(o("decoder.decoder_pred.weight")), d["Mm"], d["pd"], Dd, EPI_BF16,
                           self.pf(o("decoder.decoder_pred.bias")), _ptr(ws["pred"]), None, None, st)
@@ -672,7 +693,7 @@ class MAEEngine:
         if tail:
             # kept rows were zeroed by backward() (side stream); masked rows: LN'(g) + the (compact) residual gradient
             calls.mae_layernorm_bwd_scatter(_ptr(ws["g"]), _ptr(s["x_mid"]), _ptr(s["mean2"]), _ptr(s["rstd2"]),
-                                            self.pf(w.n2w), _ptr(dx), _ptr(ws["idx_mask"]), d["Lm"], L, Mt, D, _ptr(dx_out),
+                                            self.pf(w.n2w), _ptr(dx), self._rows_mask(), d["Lm"], L, Mt, D, _ptr(dx_out),
                                             _ptr(dxb_out), self.pg(w.n2w), self.pg(w.n2b), st)
         else:
             calls.mae_layernorm_bwd(_ptr(ws["g"]), _ptr(s["x_mid"]), _ptr(s["mean2"]), _ptr(s["rstd2"]), self.pf(w.n2w),
@@ -681,8 +702,12 @@ class MAEEngine:
         self._linear_bwd_w(_ptr(dxb_out), D, _ptr(s["att"]), D, M, w.projw, w.projb, st)
         calls.mae_gemm_tn(_ptr(dxb_out), self.pwt(w.projw), M, D, D, EPI_BF16, None, _ptr(ws["datt"]), None, None, st)
         self._wg_wait(_ptr(ws["dqkv"]))
-        calls.mae_attention_bwd(_ptr(s["qkv"]), _ptr(s["att"]), _ptr(ws["datt"]), _ptr(s["lse"]), B, L, H, hd,
-                                _ptr(ws["dqkv"]), st)
+        if tail and self._use_grouped():  # the gradient of the attention output is zero on the kept tokens' rows
+            calls.mae_attention_bwd_q(_ptr(s["qkv"]), _ptr(s["att"]), _ptr(ws["datt"]), _ptr(s["lse"]), B, L, H, hd,
+                                      d["Lm"], _ptr(ws["dqkv"]), st)
+        else:
+            calls.mae_attention_bwd(_ptr(s["qkv"]), _ptr(s["att"]), _ptr(ws["datt"]), _ptr(s["lse"]), B, L, H, hd,
+                                    _ptr(ws["dqkv"]), st)
         # attn.qkv + norm1
         self._linear_bwd_w(_ptr(ws["dqkv"]), 3 * D, _ptr(s["xn1"]), D, M, w.qkvw, w.qkvb, st)
         calls.mae_gemm_tn(_ptr(ws["dqkv"]), self.pwt(w.qkvw), M, D, 3 * D, EPI_BF16, None, _ptr(ws["g"]), None, None, st)
@@ -720,7 +745,7 @@ class MAEEngine:
             # kept rows of the last block's mid-stream gradient are zero (no gradient through its MLP): cleared early, off
             # the critical path; norm2's backward (which fills the masked rows) waits for it through dxb_b
             st2 = self._side_begin(st, extra=True)
-            calls.mae_zero_rows(_ptr(dx_b), _ptr(dxb_b), _ptr(ws["idx_keep"]), B, Lk, L, Dd, st2)
+            calls.mae_zero_rows(_ptr(dx_b), _ptr(dxb_b), self._rows_keep(), B, Lk, L, Dd, st2)
             self._side_end(_ptr(dxb_b))
             # decoder_norm saw the compact masked rows (x_dec holds their pre-norm values): compact gradient
             calls.mae_layernorm_bwd(_ptr(ws["g"]), _ptr(ws["x_dec"]), _ptr(ws["meand"]), _ptr(ws["rstdd"]),
@@ -729,9 +754,9 @@ class MAEEngine:
                                     self.pg(o("decoder.decoder_norm.bias")), st)
         else:
             # only the masked rows receive a gradient from the prediction head: zero the kept rows, LN-bwd writes the rest
-            calls.mae_zero_rows(_ptr(dx_a), _ptr(dxb_a), _ptr(ws["idx_keep"]), B, Lk, L, Dd, st)
+            calls.mae_zero_rows(_ptr(dx_a), _ptr(dxb_a), self._rows_keep(), B, Lk, L, Dd, st)
             calls.mae_layernorm_bwd(_ptr(ws["g"]), _ptr(ws["x_dec"]), _ptr(ws["meand"]), _ptr(ws["rstdd"]),
-                                    self.pf(o("decoder.decoder_norm.weight")), None, _ptr(ws["idx_mask"]), Lm, L, Mm, Dd,
+                                    self.pf(o("decoder.decoder_norm.weight")), None, self._rows_mask(), Lm, L, Mm, Dd,
                                     _ptr(dx_a), _ptr(dxb_a), self.pg(o("decoder.decoder_norm.weight")),
                                     self.pg(o("decoder.decoder_norm.bias")), st)
         cur, curb, nxt, nxtb = dx_a, dxb_a, dx_b, dxb_b
@@ -745,9 +770,9 @@ class MAEEngine:
                 bucket_cb(n_enc + i)
         # decoder input = scatter(embed) / mask_token, + frozen pos
         st2 = self._side_begin(st, extra=True)
-        calls.mae_colsum_rows_f32(_ptr(cur), _ptr(ws["idx_mask"]), B, Lm, L, 0, Dd, self.pg(o("decoder.mask_token")), st2)
+        calls.mae_colsum_rows_f32(_ptr(cur), self._rows_mask(), B, Lm, L, 0, Dd, self.pg(o("decoder.mask_token")), st2)
         self._side_end(_ptr(cur))
-        calls.mae_gather_rows_bf16(_ptr(cur), _ptr(ws["idx_keep"]), B, Lk, L, 0, Dd, _ptr(ws["demb"]), st)
+        calls.mae_gather_rows_bf16(_ptr(cur), self._rows_keep(), B, Lk, L, 0, Dd, _ptr(ws["demb"]), st)
         self._linear_bwd_w(_ptr(ws["demb"]), Dd, _ptr(ws["xnf"]), De, Me, o("decoder.decoder_embed.weight"),
                            o("decoder.decoder_embed.bias"), st)
         if bucket_cb is not None:

@@ -479,6 +479,31 @@ def test_attention_enc_repeatable_and_item_distribution(B, L, H, hd):
     assert rel_err(dqkv, qf.grad) < 3e-2
 
 
+@pytest.mark.parametrize("B,L,H,q_rows", [(3, 145, 6, 109), (150, 145, 2, 109), (301, 133, 4, 128), (2, 160, 2, 73)])
+def test_attention_leading_query_rows(B, L, H, q_rows):
+    """mae_attention_fwd_q / bwd_q (only the first q_rows query tokens matter: the decoder-sized tcgen05 kernels drop their
+    second query tile): the wanted output rows equal the full kernel's, the gradient equals the full kernel's gradient for a
+    dout that is zero on the other rows -- even when the dout passed in is NOT zero there."""
+    hd, D = 32, H * 32
+    g = torch.Generator().manual_seed(B * 3 + L)
+    qkv = bf(torch.randn(B, L, 3, H, hd, generator=g)).to(dev)
+    dout = bf(torch.randn(B, L, D, generator=g)).to(dev)
+    out = torch.full((B, L, D), float("nan"), dtype=torch.bfloat16, device=dev)
+    lse = torch.full((B, H, L), float("nan"), device=dev)
+    out_q, lse_q = out.clone(), lse.clone()
+    calls.mae_attention_fwd(p(qkv), B, L, H, hd, p(out), p(lse), stream())
+    calls.mae_attention_fwd_q(p(qkv), B, L, H, hd, q_rows, p(out_q), p(lse_q), stream())
+    assert torch.equal(out_q[:, :q_rows], out[:, :q_rows]) and torch.equal(lse_q[:, :, :q_rows], lse[:, :, :q_rows])
+    assert torch.isfinite(out_q.float()).all()  # rows that are not wanted may hold anything finite (they feed GEMMs)
+    dout0 = dout.clone(); dout0[:, q_rows:] = 0
+    ref = torch.full_like(qkv, float("nan")); got = torch.full_like(qkv, float("nan"))
+    calls.mae_attention_bwd(p(qkv), p(out), p(dout0), p(lse), B, L, H, hd, p(ref), stream())
+    calls.mae_attention_bwd_q(p(qkv), p(out_q), p(dout), p(lse_q), B, L, H, hd, q_rows, p(got), stream())
+    assert torch.isfinite(got.float()).all()
+    assert (got[:, q_rows:, 0] == 0).all()  # no query gradient on the other rows
+    assert rel_err(got, ref) < 2e-3 and max_err(got, ref) < 2e-2
+
+
 def test_scatter_decoder_and_row_ops():
     B, L, Lk, D = 5, 145, 36, 192
     g = torch.Generator().manual_seed(11)
@@ -490,6 +515,10 @@ def test_scatter_decoder_and_row_ops():
     calls.mae_scatter_decoder_tokens(p(emb), p(mt), p(pos), p(k), p(m), B, L, Lk, D, p(x), stream())
     ref = O.set_at_index(O.repeat_token(mt.view(1, 1, D), (B, L)), k, emb.float().view(B, Lk, D)) + pos
     assert max_err(x, ref) < 1e-6
+    # grouped layout: [mask tokens in idx_mask order | kept tokens in idx_keep order] = the same rows, permuted
+    xg = torch.full((B, L, D), float("nan"), device=dev)
+    calls.mae_scatter_decoder_tokens_grouped(p(emb), p(mt), p(pos), p(k), p(m), B, L, Lk, D, p(xg), stream())
+    assert torch.equal(xg, torch.cat([O.get_at_index(x, m), O.get_at_index(x, k)], dim=1))
     src = torch.randn(B, L, D, generator=g).to(dev)
     out = torch.empty(B * Lk, D, dtype=torch.bfloat16, device=dev)
     calls.mae_gather_rows_bf16(p(src), p(k), B, Lk, L, 0, D, p(out), stream())
