@@ -136,7 +136,8 @@ int mae_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* do
 /* The same op when only the first q_rows query tokens matter (the caller keeps the rows it needs first, e.g. the last
  * decoder block of the MAE, whose kept tokens are keys / values only).  Forward: out / lse rows >= q_rows are unspecified
  * (the decoder-sized tcgen05 kernel skips its second query tile for q_rows <= 128 and writes zeros to out rows >= 128).
- * Backward: dout is treated as zero on rows >= q_rows; dqkv is complete (zero dQ on those rows). */
+ * Backward: the caller guarantees dout == 0 on rows >= q_rows (kernels are free to skip them: the tcgen05 kernel does and
+ * ignores whatever is there; shapes served by other kernels run the plain backward); dqkv is complete (zero dQ there). */
 int mae_attention_fwd_q(const void* qkv_bf16, int B, int L, int H, int hd, int q_rows, void* out_bf16, float* lse,
                         mae_stream_t stream);
 int mae_attention_bwd_q(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse, int B,
